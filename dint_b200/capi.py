@@ -1,0 +1,228 @@
+"""ctypes binding of the C ABI in include/dint_b200.h (libdint_b200.so).
+
+This is the stub a maintainer of a Python host would write; the library itself has no
+Python or torch dependency. Every call raises DintError on a non-zero return code —
+there is no CPU fallback behind any of them.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _build
+
+DICT_RECT, DICT_PACKED, DICT_MULTI = 0, 1, 2
+MODE_RAW, MODE_DOCIDS, MODE_FREQS = 0, 1, 2
+E_NODEVICE = -5
+
+KIND_OF_TYPE = {"single_rect_dint": DICT_RECT, "single_packed_dint": DICT_PACKED, "multi_packed_dint": DICT_MULTI}
+
+SEGMENT_DTYPE = np.dtype([("in_off", "<u8"), ("out_off", "<u8"), ("n", "<u4"), ("doc_base", "<u4")])
+BLOCK_DTYPE = np.dtype([("in_off", "<u8"), ("out_off", "<u8"), ("size", "<u4"), ("cur_base", "<u4"),
+                        ("block_max", "<u4"), ("reserved", "<u4")])
+assert SEGMENT_DTYPE.itemsize == 24 and BLOCK_DTYPE.itemsize == 32
+
+# every symbol include/dint_b200.h declares (checked by tests/test_abi.py)
+SYMBOLS = [
+    "dint_last_error", "dint_abi_version", "dint_kernel_launches",
+    "dint_dict_create", "dint_dict_create_mapped", "dint_dict_destroy", "dint_dict_kind", "dint_dict_num_rows",
+    "dint_dict_device_bytes", "dint_dict_copy",
+    "dint_vroom_plan_create", "dint_vroom_plan_destroy", "dint_vroom_plan_num_lists", "dint_vroom_plan_num_ints",
+    "dint_vroom_plan_num_segments", "dint_vroom_plan_segments", "dint_vroom_plan_list_offsets",
+    "dint_vroom_plan_list_byte_offsets",
+    "dint_index_plan_create", "dint_index_plan_destroy", "dint_index_plan_num_lists", "dint_index_plan_num_docs",
+    "dint_index_plan_num_postings", "dint_index_plan_num_blocks", "dint_index_plan_blocks",
+    "dint_index_plan_list_offsets", "dint_index_plan_endpoints", "dint_index_plan_layout",
+    "dint_decode_segments", "dint_decode_index", "dint_checksum_lists", "dint_decode_list_host",
+]
+
+
+class DintError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"dint_b200 error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        path = _build.build()
+        L = C.CDLL(path)
+        vp, sz, u32, u64, i32 = C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint64, C.c_int
+        L.dint_last_error.restype = C.c_char_p
+        L.dint_abi_version.restype = i32
+        L.dint_kernel_launches.restype = u64
+        L.dint_dict_create.argtypes = [i32, vp, sz, i32, C.POINTER(vp)]
+        L.dint_dict_create_mapped.argtypes = [i32, vp, sz, i32, C.POINTER(vp), C.POINTER(sz)]
+        L.dint_dict_destroy.argtypes = [vp]
+        L.dint_dict_destroy.restype = None
+        L.dint_dict_kind.argtypes = [vp]
+        L.dint_dict_num_rows.argtypes = [vp]
+        L.dint_dict_num_rows.restype = u32
+        L.dint_dict_device_bytes.argtypes = [vp]
+        L.dint_dict_device_bytes.restype = sz
+        L.dint_dict_copy.argtypes = [vp, u32, u32, vp, C.POINTER(u32)]
+        L.dint_vroom_plan_create.argtypes = [vp, vp, sz, u32, u32, C.POINTER(vp)]
+        L.dint_vroom_plan_destroy.argtypes = [vp]
+        L.dint_vroom_plan_destroy.restype = None
+        for f in ("num_lists", "num_ints", "num_segments"):
+            getattr(L, "dint_vroom_plan_" + f).argtypes = [vp]
+            getattr(L, "dint_vroom_plan_" + f).restype = u64
+        for f in ("segments", "list_offsets", "list_byte_offsets"):
+            getattr(L, "dint_vroom_plan_" + f).argtypes = [vp]
+            getattr(L, "dint_vroom_plan_" + f).restype = vp
+        L.dint_index_plan_create.argtypes = [i32, vp, sz, u32, C.POINTER(vp)]
+        L.dint_index_plan_destroy.argtypes = [vp]
+        L.dint_index_plan_destroy.restype = None
+        for f in ("num_lists", "num_docs", "num_postings", "num_blocks"):
+            getattr(L, "dint_index_plan_" + f).argtypes = [vp]
+            getattr(L, "dint_index_plan_" + f).restype = u64
+        for f in ("blocks", "list_offsets", "endpoints"):
+            getattr(L, "dint_index_plan_" + f).argtypes = [vp]
+            getattr(L, "dint_index_plan_" + f).restype = vp
+        L.dint_index_plan_layout.argtypes = [vp] + [C.POINTER(u64)] * 5
+        L.dint_decode_segments.argtypes = [vp, vp, sz, vp, sz, u32, vp, i32, vp]
+        L.dint_decode_index.argtypes = [vp, vp, vp, sz, vp, sz, u32, vp, vp, vp]
+        L.dint_checksum_lists.argtypes = [vp, vp, sz, vp, vp]
+        L.dint_decode_list_host.argtypes = [vp, vp, sz, vp, u32, u32, C.POINTER(sz)]
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise DintError(rc, lib().dint_last_error().decode(errors="replace"))
+
+
+def _np_ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _view(ptr, count, dtype):
+    """copy `count` items of `dtype` out of library-owned memory"""
+    if count == 0:
+        return np.zeros(0, dtype=dtype)
+    nbytes = count * np.dtype(dtype).itemsize
+    buf = (C.c_uint8 * nbytes).from_address(ptr)
+    return np.frombuffer(buf, dtype=dtype, count=count).copy()
+
+
+class Dictionary:
+    """A reference dictionary file, parsed and (device >= 0) resident in HBM."""
+
+    def __init__(self, kind, data, device=-1, mapped=False):
+        self.kind = kind
+        self.device = device
+        a = np.frombuffer(data, dtype=np.uint8)
+        h = C.c_void_p()
+        self.consumed = len(a)
+        if mapped:
+            used = C.c_size_t(0)
+            check(lib().dint_dict_create_mapped(kind, _np_ptr(a), len(a), device, C.byref(h), C.byref(used)))
+            self.consumed = used.value
+        else:
+            check(lib().dint_dict_create(kind, _np_ptr(a), len(a), device, C.byref(h)))
+        self.handle = h
+
+    @classmethod
+    def from_file(cls, kind, path, device=-1):
+        with open(path, "rb") as f:
+            return cls(kind, f.read(), device)
+
+    @property
+    def num_rows(self):
+        return lib().dint_dict_num_rows(self.handle)
+
+    @property
+    def device_bytes(self):
+        return lib().dint_dict_device_bytes(self.handle)
+
+    def copy(self, cls_, i):
+        out = np.zeros(16, dtype=np.uint32)
+        ln = C.c_uint32(0)
+        check(lib().dint_dict_copy(self.handle, cls_, i, _np_ptr(out), C.byref(ln)))
+        return ln.value, out
+
+    def close(self):
+        if self.handle:
+            lib().dint_dict_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class VroomPlan:
+    """Segment table of a vroom .bin (host pre-pass)."""
+
+    def __init__(self, dictionary, data, block_size=256, chunk_ints=0):
+        a = np.frombuffer(data, dtype=np.uint8)
+        h = C.c_void_p()
+        check(lib().dint_vroom_plan_create(dictionary.handle, _np_ptr(a), len(a), block_size, chunk_ints, C.byref(h)))
+        L = lib()
+        self.n_lists = L.dint_vroom_plan_num_lists(h)
+        self.n_ints = L.dint_vroom_plan_num_ints(h)
+        self.n_segments = L.dint_vroom_plan_num_segments(h)
+        self.segments = _view(L.dint_vroom_plan_segments(h), self.n_segments, SEGMENT_DTYPE)
+        self.list_offsets = _view(L.dint_vroom_plan_list_offsets(h), self.n_lists + 1, np.uint64)
+        self.list_byte_offsets = _view(L.dint_vroom_plan_list_byte_offsets(h), self.n_lists + 1, np.uint64)
+        self.block_size = block_size
+        self.in_bytes = len(a)
+        L.dint_vroom_plan_destroy(h)
+
+
+class IndexPlan:
+    """Block table of a frozen dict_freq_index .bin (host pre-pass)."""
+
+    def __init__(self, kind, data, block_size=256):
+        a = np.frombuffer(data, dtype=np.uint8)
+        h = C.c_void_p()
+        check(lib().dint_index_plan_create(kind, _np_ptr(a), len(a), block_size, C.byref(h)))
+        L = lib()
+        self.kind = kind
+        self.n_lists = L.dint_index_plan_num_lists(h)
+        self.num_docs = L.dint_index_plan_num_docs(h)
+        self.n_postings = L.dint_index_plan_num_postings(h)
+        self.n_blocks = L.dint_index_plan_num_blocks(h)
+        self.blocks = _view(L.dint_index_plan_blocks(h), self.n_blocks, BLOCK_DTYPE)
+        self.list_offsets = _view(L.dint_index_plan_list_offsets(h), self.n_lists + 1, np.uint64)
+        self.endpoints = _view(L.dint_index_plan_endpoints(h), self.n_lists + 1, np.uint64)
+        v = [C.c_uint64(0) for _ in range(5)]
+        check(L.dint_index_plan_layout(h, *[C.byref(x) for x in v]))
+        self.lists_off, self.lists_len, self.docs_dict_off, self.freqs_dict_off, self.end_off = [x.value for x in v]
+        self.block_size = block_size
+        L.dint_index_plan_destroy(h)
+
+
+def decode_segments(dictionary, d_in_ptr, in_bytes, d_segs_ptr, n_segs, d_out_ptr, mode, stream=0, block_size=256):
+    check(lib().dint_decode_segments(dictionary.handle, d_in_ptr, in_bytes, d_segs_ptr, n_segs, block_size, d_out_ptr,
+                                     mode, stream))
+
+
+def decode_index(docs_dict, freqs_dict, d_lists_ptr, lists_bytes, d_blocks_ptr, n_blocks, block_size, d_docids_ptr,
+                 d_freqs_ptr, stream=0):
+    check(lib().dint_decode_index(docs_dict.handle, freqs_dict.handle, d_lists_ptr, lists_bytes, d_blocks_ptr, n_blocks,
+                                  block_size, d_docids_ptr, d_freqs_ptr, stream))
+
+
+def checksum_lists(d_values_ptr, d_list_offsets_ptr, n_lists, d_sums_ptr, stream=0):
+    check(lib().dint_checksum_lists(d_values_ptr, d_list_offsets_ptr, n_lists, d_sums_ptr, stream))
+
+
+def decode_list_host(dictionary, data, n, block_size=256):
+    """One Decoder::decode(dict, in, out, universe, n) call on host buffers. Returns (values, consumed)."""
+    a = np.frombuffer(data, dtype=np.uint8)
+    out = np.zeros(max(n, 1), dtype=np.uint32)
+    used = C.c_size_t(0)
+    check(lib().dint_decode_list_host(dictionary.handle, _np_ptr(a), len(a), _np_ptr(out), n, block_size, C.byref(used)))
+    return out[:n], used.value
+
+
+def kernel_launches():
+    return lib().dint_kernel_launches()

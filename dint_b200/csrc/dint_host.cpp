@@ -1,0 +1,543 @@
+// Host format layer of dint_b200: byte-for-byte consumers of the reference's on-disk
+// formats, and the one-time pre-passes that turn a .bin into flat descriptor tables
+// for the device decoder. No decoding of integers happens here.
+//
+// Reference formats followed (paths relative to the reference root):
+//   dictionary files      rectangular_dictionary.hpp:72-92, single_dictionary.hpp:72-107,
+//                         multi_dictionary.hpp:70-121
+//   vroom .bin            vroom_env/encode.cpp:177-190, vroom_env/jobs.hpp:89-95,
+//                         vroom_env/codecs.hpp:110-124 (header), :93-107 (vbyte)
+//   frozen index .bin     dict_freq_index.hpp:209-214, external/succinct/mapper.hpp:100-156,
+//                         external/succinct/bit_vector.hpp:228-231,
+//                         include/ds2i/compact_elias_fano.hpp:14-61 + :69-136 (bit layout),
+//                         include/dint/dict_posting_list.hpp:10-56 (per-list layout)
+#include <algorithm>
+#include <atomic>
+#include <memory>
+#include <mutex>
+#include <new>
+
+#include "dint_internal.hpp"
+
+namespace dint {
+
+static thread_local std::string g_error;
+void set_error(const std::string& msg) { g_error = msg; }
+
+static inline uint32_t msb64(uint64_t x) { return 63u - uint32_t(__builtin_clzll(x)); }
+
+// TightVariableByte: 7-bit groups LSB first, terminator has bit 7 SET (block_codecs.hpp:87-101)
+static inline const uint8_t* vbyte(const uint8_t* p, const uint8_t* end, uint32_t* v) {
+    uint32_t x = 0;
+    for (unsigned shift = 0; p < end; shift += 7) {
+        uint8_t c = *p++;
+        x += uint32_t(c & 127u) << (shift & 31u);
+        if (c & 128u) {
+            *v = x;
+            return p;
+        }
+    }
+    return nullptr;
+}
+
+// ---------------------------------------------------------------------------------------
+// dictionaries -> unified "expanded rows" representation
+//   row r = 16 payload words (zero padded), lens[r] = length - 1, sums[r] = sum(v + 1)
+// For packed/multi the (len-1)<<24 | offset indirection is resolved here, once, so the
+// device never chases m_offsets -> m_table (two dependent loads per codeword on the CPU).
+// ---------------------------------------------------------------------------------------
+static void finish_rows(dint_dict* d) {
+    d->h_sums.assign(d->n_rows, 0);
+    for (uint32_t r = 0; r < d->n_rows; ++r) {
+        uint32_t len = uint32_t(d->h_lens[r]) + 1;
+        uint32_t s = len;  // runs: all zeros -> sum(v+1) = len
+        for (uint32_t j = 0; j < std::min(len, kEntry); ++j) s += d->h_rows[size_t(r) * kEntry + j];
+        d->h_sums[r] = s;
+    }
+}
+
+static int build_rect(dint_dict* d, const uint8_t* table_words, size_t n_table_words) {
+    // rows of 17 words: 16 payload + length (rectangular_dictionary.hpp:206-213)
+    uint32_t m = uint32_t(n_table_words / (kEntry + 1));
+    if (m > kNumEntries) return DINT_E_FORMAT;
+    d->n_rows = kNumEntries;
+    d->n_classes = 1;
+    d->class_size[0] = kNumEntries;
+    d->h_rows.assign(size_t(kNumEntries) * kEntry, 0);
+    d->h_lens.assign(kNumEntries, 0);
+    // builder::init() (rectangular_dictionary.hpp:43-56): reserved rows exist even if the file is short
+    for (uint32_t i = 0, size = 256; i < 5; ++i, size /= 2) d->h_lens[2 + i] = uint8_t(size - 1);
+    for (uint32_t r = 0; r < m; ++r) {
+        const uint8_t* row = table_words + size_t(r) * (kEntry + 1) * 4;
+        std::memcpy(&d->h_rows[size_t(r) * kEntry], row, kEntry * 4);
+        uint32_t len = rd32(row + kEntry * 4);
+        if (len > 256) {
+            set_error("rectangular dictionary: entry length > 256");
+            return DINT_E_FORMAT;
+        }
+        d->h_lens[r] = uint8_t(len ? len - 1 : 0);
+    }
+    finish_rows(d);
+    return DINT_OK;
+}
+
+static int build_packed(dint_dict* d, const uint8_t* starts, uint32_t n_starts, const uint8_t* offsets,
+                        uint32_t n_offsets, const uint8_t* table, uint32_t n_table) {
+    d->n_rows = n_offsets;
+    if (n_starts) {
+        if (n_starts > 8) return DINT_E_FORMAT;
+        d->n_classes = n_starts;
+        for (uint32_t c = 0; c < n_starts; ++c) {
+            d->class_base[c] = rd32(starts + 4 * c);
+            if (d->class_base[c] > n_offsets) return DINT_E_FORMAT;
+        }
+        for (uint32_t c = 0; c < n_starts; ++c)
+            d->class_size[c] = (c + 1 < n_starts ? d->class_base[c + 1] : n_offsets) - d->class_base[c];
+    } else {
+        d->n_classes = 1;
+        d->class_size[0] = n_offsets;
+    }
+    d->h_rows.assign(size_t(n_offsets) * kEntry, 0);
+    d->h_lens.assign(n_offsets, 0);
+    for (uint32_t r = 0; r < n_offsets; ++r) {
+        uint32_t so = rd32(offsets + 4 * size_t(r));
+        uint32_t off = so & 0xFFFFFFu, len = (so >> 24) + 1;
+        d->h_lens[r] = uint8_t(len - 1);
+        uint32_t take = std::min(len, kEntry);
+        if (uint64_t(off) + take > n_table) {
+            // the reference memcpy's 16 words regardless (table padded by 16, multi_dictionary.hpp:108);
+            // only the first `len` matter, and those must exist
+            set_error("packed dictionary: entry runs past the table");
+            return DINT_E_FORMAT;
+        }
+        std::memcpy(&d->h_rows[size_t(r) * kEntry], table + 4 * size_t(off), take * 4);
+    }
+    finish_rows(d);
+    return DINT_OK;
+}
+
+static int parse_file(dint_dict* d, int kind, const uint8_t* f, size_t len) {
+    if (kind == DINT_DICT_RECT) {
+        if (len < 4) return DINT_E_FORMAT;
+        uint32_t m = rd32(f);
+        size_t words = size_t(m) * (kEntry + 1);
+        if (m > kNumEntries || len < 4 + words * 4) return DINT_E_FORMAT;
+        return build_rect(d, f + 4, words);
+    }
+    if (kind == DINT_DICT_PACKED) {
+        if (len < 12) return DINT_E_FORMAT;
+        uint32_t no = rd32(f + 4), nt = rd32(f + 8);
+        if (len < 12 + (size_t(no) + nt) * 4) return DINT_E_FORMAT;
+        return build_packed(d, nullptr, 0, f + 12, no, f + 12 + size_t(no) * 4, nt);
+    }
+    if (kind == DINT_DICT_MULTI) {
+        if (len < 16) return DINT_E_FORMAT;
+        uint32_t ns = rd32(f + 4), no = rd32(f + 8), nt = rd32(f + 12);
+        if (len < 16 + (size_t(ns) + no + nt) * 4) return DINT_E_FORMAT;
+        return build_packed(d, f + 16, ns, f + 16 + size_t(ns) * 4, no, f + 16 + (size_t(ns) + no) * 4, nt);
+    }
+    return DINT_E_ARG;
+}
+
+// mappable_vector<uint32_t> = u64 size + payload (mapper.hpp:128-146)
+static int parse_mapped(dint_dict* d, int kind, const uint8_t* p, size_t len, size_t* consumed) {
+    int nvec = kind == DINT_DICT_RECT ? 1 : kind == DINT_DICT_PACKED ? 2 : kind == DINT_DICT_MULTI ? 3 : 0;
+    if (!nvec) return DINT_E_ARG;
+    const uint8_t* vec[3] = {nullptr, nullptr, nullptr};
+    uint64_t cnt[3] = {0, 0, 0};
+    size_t off = 0;
+    for (int v = 0; v < nvec; ++v) {
+        if (off + 8 > len) return DINT_E_FORMAT;
+        cnt[v] = rd64(p + off);
+        off += 8;
+        if (cnt[v] > (len - off) / 4) return DINT_E_FORMAT;
+        vec[v] = p + off;
+        off += size_t(cnt[v]) * 4;
+    }
+    if (consumed) *consumed = off;
+    if (kind == DINT_DICT_RECT) return build_rect(d, vec[0], size_t(cnt[0]));
+    if (kind == DINT_DICT_PACKED) return build_packed(d, nullptr, 0, vec[0], uint32_t(cnt[0]), vec[1], uint32_t(cnt[1]));
+    return build_packed(d, vec[0], uint32_t(cnt[0]), vec[1], uint32_t(cnt[1]), vec[2], uint32_t(cnt[2]));
+}
+
+static int validate(dint_dict* d) {
+    for (uint32_t c = 0; c < d->n_classes; ++c) {
+        if (d->class_size[c] < kReserved) {
+            set_error("dictionary class smaller than the 7 reserved codewords");
+            return DINT_E_FORMAT;
+        }
+        uint32_t b = d->class_base[c];
+        // codeword space (single_dictionary.hpp:39-56): 0,1 exceptions; 2..6 runs of 256..16 zeros
+        for (uint32_t i = 0, size = 256; i < 5; ++i, size /= 2) {
+            if (uint32_t(d->h_lens[b + 2 + i]) + 1 != size) {
+                set_error("dictionary: reserved run codewords have unexpected lengths");
+                return DINT_E_FORMAT;
+            }
+        }
+    }
+    return DINT_OK;
+}
+
+}  // namespace dint
+
+using namespace dint;
+
+extern "C" {
+
+const char* dint_last_error(void) { return g_error.c_str(); }
+int dint_abi_version(void) { return DINT_B200_ABI_VERSION; }
+
+static int dict_finish(dint_dict* d, int rc, int device, dint_dict** out) {
+    if (rc == DINT_OK) rc = validate(d);
+    if (rc == DINT_OK && device >= 0) {
+        d->device = device;
+        rc = dint_dict_upload(d);
+    }
+    if (rc != DINT_OK) {
+        if (rc == DINT_E_FORMAT && g_error.empty()) set_error("malformed dictionary");
+        delete d;
+        return rc;
+    }
+    *out = d;
+    return DINT_OK;
+}
+
+int dint_dict_create(int kind, const void* file_bytes, size_t len, int device, dint_dict** out) {
+    if (!file_bytes || !out) return DINT_E_ARG;
+    g_error.clear();
+    dint_dict* d = new (std::nothrow) dint_dict;
+    if (!d) return DINT_E_NOMEM;
+    d->kind = kind;
+    return dict_finish(d, parse_file(d, kind, static_cast<const uint8_t*>(file_bytes), len), device, out);
+}
+
+int dint_dict_create_mapped(int kind, const void* bytes, size_t len, int device, dint_dict** out, size_t* consumed) {
+    if (!bytes || !out) return DINT_E_ARG;
+    g_error.clear();
+    dint_dict* d = new (std::nothrow) dint_dict;
+    if (!d) return DINT_E_NOMEM;
+    d->kind = kind;
+    return dict_finish(d, parse_mapped(d, kind, static_cast<const uint8_t*>(bytes), len, consumed), device, out);
+}
+
+void dint_dict_destroy(dint_dict* d) {
+    if (!d) return;
+    dint_dict_release_device(d);
+    delete d;
+}
+
+int dint_dict_kind(const dint_dict* d) { return d ? d->kind : DINT_E_ARG; }
+uint32_t dint_dict_num_rows(const dint_dict* d) { return d ? d->n_rows : 0; }
+size_t dint_dict_device_bytes(const dint_dict* d) {
+    return (d && d->d_rows) ? size_t(d->n_rows) * (kEntry * 4 + 1) : 0;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------
+// vroom pre-pass
+// ---------------------------------------------------------------------------------------
+namespace {
+
+struct walker {
+    const dint_dict* d;
+    const uint8_t* bin;
+    const uint8_t* end;
+    // walks `count` integers of u16 codewords of class `cls` starting at p; returns the end
+    // pointer or nullptr. acc accumulates sum(v + 1). cut: emit chunk boundaries.
+    template <typename Cut>
+    const uint8_t* walk16(const uint8_t* p, uint32_t cls, uint64_t count, uint32_t& acc, Cut&& cut) const {
+        const uint32_t base = d->class_base[cls], csize = d->class_size[cls];
+        uint64_t i = 0;
+        while (i < count) {
+            if (p + 2 > end) return nullptr;
+            uint32_t w = rd16(p);
+            uint32_t len;
+            if (w >= 2) {
+                if (w >= csize) return nullptr;
+                len = uint32_t(d->h_lens[base + w]) + 1;
+                acc += d->h_sums[base + w];
+                p += 2;
+            } else if (w == 1) {
+                if (p + 6 > end) return nullptr;
+                acc += rd32(p + 2) + 1;
+                len = 1;
+                p += 6;
+            } else {
+                if (p + 4 > end) return nullptr;
+                acc += uint32_t(rd16(p + 2)) + 1;
+                len = 1;
+                p += 4;
+            }
+            i += len;
+            if (i > count) return nullptr;  // entries must tile the list exactly (`i != n` loop)
+            cut(p, i, acc);
+        }
+        return p;
+    }
+    const uint8_t* walk8(const uint8_t* p, uint32_t cls, uint64_t count, uint32_t& acc) const {
+        const uint32_t base = d->class_base[cls], csize = d->class_size[cls];
+        uint64_t i = 0;
+        while (i < count) {
+            if (p + 1 > end) return nullptr;
+            uint32_t w = *p;
+            uint32_t len;
+            if (w >= 2) {
+                if (w >= csize) return nullptr;
+                len = uint32_t(d->h_lens[base + w]) + 1;
+                acc += d->h_sums[base + w];
+                p += 1;
+            } else if (w == 1) {
+                if (p + 5 > end) return nullptr;
+                acc += rd32(p + 1) + 1;
+                len = 1;
+                p += 5;
+            } else {
+                if (p + 3 > end) return nullptr;
+                acc += uint32_t(rd16(p + 1)) + 1;
+                len = 1;
+                p += 3;
+            }
+            i += len;
+            if (i > count) return nullptr;
+        }
+        return p;
+    }
+};
+
+}  // namespace
+
+extern "C" {
+
+int dint_vroom_plan_create(const dint_dict* d, const void* bin_, size_t len, uint32_t block_size, uint32_t chunk_ints,
+                           dint_vroom_plan** out) {
+    if (!d || (!bin_ && len) || !out) return DINT_E_ARG;
+    g_error.clear();
+    if (!block_size) block_size = kDefaultBlock;
+    if (!chunk_ints) chunk_ints = kDefaultChunk;
+    const uint8_t* bin = static_cast<const uint8_t*>(bin_);
+    const uint8_t* end = bin + len;
+    std::unique_ptr<dint_vroom_plan> plan(new (std::nothrow) dint_vroom_plan);
+    if (!plan) return DINT_E_NOMEM;
+    walker wk{d, bin, end};
+    const uint8_t* p = bin;
+    uint64_t out_off = 0;
+    plan->list_offsets.push_back(0);
+    while (p != end) {
+        plan->list_byte_offsets.push_back(uint64_t(p - bin));
+        uint32_t n = 0, universe = 0;
+        // header::read (vroom_env/codecs.hpp:117-123): n, then universe (unused by DINT decoders)
+        p = vbyte(p, end, &n);
+        if (p) p = vbyte(p, end, &universe);
+        if (!p) {
+            set_error("vroom .bin: truncated list header");
+            return DINT_E_FORMAT;
+        }
+        uint32_t acc = 0;
+        if (d->kind != DINT_DICT_MULTI) {
+            // single_dint::decode (vroom_env/dint_codecs.hpp:37-107): one u16 stream per list
+            const uint8_t* seg_p = p;
+            uint64_t seg_i = 0;
+            uint32_t seg_base = 0;
+            auto cut = [&](const uint8_t* q, uint64_t i, uint32_t a) {
+                if (i - seg_i >= chunk_ints && i < n) {
+                    plan->segments.push_back({uint64_t(seg_p - bin), out_off + seg_i, uint32_t(i - seg_i), seg_base});
+                    seg_p = q;
+                    seg_i = i;
+                    seg_base = a;
+                }
+            };
+            p = wk.walk16(p, 0, n, acc, cut);
+            if (!p) {
+                set_error("vroom .bin: codeword stream does not tile the list");
+                return DINT_E_FORMAT;
+            }
+            if (n > seg_i) plan->segments.push_back({uint64_t(seg_p - bin), out_off + seg_i, uint32_t(n - seg_i), seg_base});
+        } else {
+            // multi_opt_dint::decode (vroom_env/dint_codecs.hpp:521-619): ceil(n / block_size) blocks,
+            // each = selector byte + u16 stream (selector < 6) or u8 stream (selector - 6)
+            uint64_t done = 0;
+            while (done < n) {
+                uint32_t size = uint32_t(std::min<uint64_t>(block_size, n - done));
+                if (p >= end) {
+                    set_error("vroom .bin: truncated multi block");
+                    return DINT_E_FORMAT;
+                }
+                uint32_t sel = *p;
+                if (sel >= 2 * kSelectors || (sel % kSelectors) >= d->n_classes) {
+                    set_error("vroom .bin: bad selector byte");
+                    return DINT_E_FORMAT;
+                }
+                plan->segments.push_back({uint64_t(p - bin), out_off + done, size, acc});
+                const uint8_t* q = sel < kSelectors ? wk.walk16(p + 1, sel, size, acc, [](const uint8_t*, uint64_t, uint32_t) {})
+                                                    : wk.walk8(p + 1, sel - kSelectors, size, acc);
+                if (!q) {
+                    set_error("vroom .bin: codeword stream does not tile the block");
+                    return DINT_E_FORMAT;
+                }
+                p = q;
+                done += size;
+            }
+        }
+        out_off += n;
+        plan->list_offsets.push_back(out_off);
+    }
+    plan->list_byte_offsets.push_back(len);
+    plan->n_ints = out_off;
+    *out = plan.release();
+    return DINT_OK;
+}
+
+void dint_vroom_plan_destroy(dint_vroom_plan* p) { delete p; }
+uint64_t dint_vroom_plan_num_lists(const dint_vroom_plan* p) { return p ? p->list_offsets.size() - 1 : 0; }
+uint64_t dint_vroom_plan_num_ints(const dint_vroom_plan* p) { return p ? p->n_ints : 0; }
+uint64_t dint_vroom_plan_num_segments(const dint_vroom_plan* p) { return p ? p->segments.size() : 0; }
+const dint_segment* dint_vroom_plan_segments(const dint_vroom_plan* p) { return p ? p->segments.data() : nullptr; }
+const uint64_t* dint_vroom_plan_list_offsets(const dint_vroom_plan* p) { return p ? p->list_offsets.data() : nullptr; }
+const uint64_t* dint_vroom_plan_list_byte_offsets(const dint_vroom_plan* p) {
+    return p ? p->list_byte_offsets.data() : nullptr;
+}
+
+// ---------------------------------------------------------------------------------------
+// frozen dict_freq_index pre-pass
+// ---------------------------------------------------------------------------------------
+static inline uint64_t get_bits(const uint8_t* words, uint64_t pos, uint32_t len) {
+    if (!len) return 0;
+    uint64_t w = pos / 64, s = pos % 64;
+    uint64_t lo = rd64(words + w * 8) >> s;
+    if (s + len > 64) lo |= rd64(words + (w + 1) * 8) << (64 - s);
+    return len == 64 ? lo : lo & ((uint64_t(1) << len) - 1);
+}
+
+int dint_index_plan_create(int kind, const void* bin_, size_t len, uint32_t block_size, dint_index_plan** out) {
+    if (!bin_ || !out || kind < 0 || kind > 2) return DINT_E_ARG;
+    g_error.clear();
+    if (!block_size) block_size = kDefaultBlock;
+    const uint8_t* bin = static_cast<const uint8_t*>(bin_);
+    std::unique_ptr<dint_index_plan> plan(new (std::nothrow) dint_index_plan);
+    if (!plan) return DINT_E_NOMEM;
+    plan->kind = kind;
+    auto bad = [&](const char* m) {
+        set_error(std::string("index .bin: ") + m);
+        return DINT_E_FORMAT;
+    };
+    // u64 freeze flags | global_parameters 5 x u8 | u64 m_size | u64 m_num_docs |
+    // bit_vector { u64 bits, mappable_vector<u64> } | mappable_vector<u8> m_lists | dicts
+    size_t off = 8;
+    if (len < off + 5 + 32) return bad("truncated header");
+    const uint32_t log_s0 = bin[off], log_s1 = bin[off + 1];
+    off += 5;
+    plan->n_lists = rd64(bin + off);
+    plan->num_docs = rd64(bin + off + 8);
+    const uint64_t ef_bits = rd64(bin + off + 16), ef_words = rd64(bin + off + 24);
+    off += 32;
+    if (ef_words > (len - off) / 8 || ef_bits > ef_words * 64) return bad("endpoints bit vector out of range");
+    const uint8_t* words = bin + off;
+    off += size_t(ef_words) * 8;
+    if (off + 8 > len) return bad("truncated m_lists");
+    plan->lists_len = rd64(bin + off);
+    off += 8;
+    plan->lists_off = off;
+    if (plan->lists_len > len - off) return bad("m_lists out of range");
+    off += size_t(plan->lists_len);
+    plan->docs_dict_off = off;
+    {
+        dint_dict tmp;
+        size_t used = 0;
+        if (parse_mapped(&tmp, kind, bin + off, len - off, &used) != DINT_OK) return bad("docs dictionary");
+        off += used;
+        plan->freqs_dict_off = off;
+        dint_dict tmp2;
+        if (parse_mapped(&tmp2, kind, bin + off, len - off, &used) != DINT_OK) return bad("freqs dictionary");
+        off += used;
+        plan->end_off = off;
+    }
+    if (off != len) return bad("trailing bytes");
+
+    // Elias-Fano of the n_lists list start offsets, universe = m_lists.size()
+    // (dict_freq_index.hpp:96-99; compact_elias_fano.hpp:14-61)
+    const uint64_t n = plan->n_lists, universe = plan->lists_len;
+    plan->endpoints.assign(n + 1, 0);
+    if (n) {
+        const uint64_t l = universe > n ? msb64(universe / n) : 0;
+        const uint64_t hb_len = n + (universe >> l) + 2;
+        const uint64_t ptr_size = hb_len > 1 ? msb64(hb_len - 1) + 1 : 0;
+        const uint64_t p0 = (hb_len - n) >> log_s0, p1 = n >> log_s1;
+        const uint64_t hb_off = (p0 + p1) * ptr_size, lb_off = hb_off + hb_len;
+        if (lb_off + n * l != ef_bits) return bad("Elias-Fano geometry mismatch");
+        uint64_t i = 0;
+        for (uint64_t pos = 0; pos < hb_len && i < n;) {
+            uint32_t take = uint32_t(std::min<uint64_t>(64, hb_len - pos));
+            uint64_t w = get_bits(words, hb_off + pos, take);
+            while (w && i < n) {
+                uint32_t b = uint32_t(__builtin_ctzll(w));
+                w &= w - 1;
+                uint64_t high = pos + b - i - 1;
+                plan->endpoints[i] = (high << l) | get_bits(words, lb_off + i * l, uint32_t(l));
+                ++i;
+            }
+            pos += take;
+        }
+        if (i != n) return bad("Elias-Fano: fewer endpoints than lists");
+    }
+    plan->endpoints[n] = universe;
+
+    // per-list layout (dict_posting_list.hpp:10-56): vbyte n | u32 block_max[blocks] |
+    // u32 block_endpoint[blocks-1] | blocks {docs bytes, freqs bytes}
+    const uint8_t* lists = bin + plan->lists_off;
+    const uint8_t* lists_end = lists + plan->lists_len;
+    plan->list_offsets.assign(n + 1, 0);
+    uint64_t postings = 0;
+    for (uint64_t t = 0; t < n; ++t) {
+        if (plan->endpoints[t] >= plan->lists_len || (t && plan->endpoints[t] < plan->endpoints[t - 1]))
+            return bad("list endpoint out of range");
+        const uint8_t* data = lists + plan->endpoints[t];
+        uint32_t ln = 0;
+        const uint8_t* base = vbyte(data, lists_end, &ln);
+        if (!base || !ln) return bad("bad list header");
+        const uint64_t blocks = (uint64_t(ln) + block_size - 1) / block_size;
+        const uint8_t* maxs = base;
+        const uint8_t* eps = maxs + 4 * blocks;
+        const uint8_t* blocks_data = eps + 4 * (blocks - 1);
+        if (blocks_data > lists_end) return bad("block tables out of range");
+        plan->list_offsets[t] = postings;
+        for (uint64_t b = 0; b < blocks; ++b) {
+            dint_block blk;
+            uint32_t endpoint = b ? rd32(eps + 4 * (b - 1)) : 0;
+            blk.in_off = uint64_t(blocks_data - lists) + endpoint;
+            if (blk.in_off >= plan->lists_len) return bad("block endpoint out of range");
+            blk.out_off = postings + b * block_size;
+            blk.size = ((b + 1) * block_size <= ln) ? block_size : (ln % block_size);
+            blk.cur_base = (b ? rd32(maxs + 4 * (b - 1)) : 0xFFFFFFFFu) + 1;
+            blk.block_max = rd32(maxs + 4 * b);
+            blk.reserved = 0;
+            plan->blocks.push_back(blk);
+        }
+        postings += ln;
+    }
+    plan->list_offsets[n] = postings;
+    plan->n_postings = postings;
+    *out = plan.release();
+    return DINT_OK;
+}
+
+void dint_index_plan_destroy(dint_index_plan* p) { delete p; }
+uint64_t dint_index_plan_num_lists(const dint_index_plan* p) { return p ? p->n_lists : 0; }
+uint64_t dint_index_plan_num_docs(const dint_index_plan* p) { return p ? p->num_docs : 0; }
+uint64_t dint_index_plan_num_postings(const dint_index_plan* p) { return p ? p->n_postings : 0; }
+uint64_t dint_index_plan_num_blocks(const dint_index_plan* p) { return p ? p->blocks.size() : 0; }
+const dint_block* dint_index_plan_blocks(const dint_index_plan* p) { return p ? p->blocks.data() : nullptr; }
+const uint64_t* dint_index_plan_list_offsets(const dint_index_plan* p) { return p ? p->list_offsets.data() : nullptr; }
+const uint64_t* dint_index_plan_endpoints(const dint_index_plan* p) { return p ? p->endpoints.data() : nullptr; }
+int dint_index_plan_layout(const dint_index_plan* p, uint64_t* lists_off, uint64_t* lists_len, uint64_t* docs_dict_off,
+                           uint64_t* freqs_dict_off, uint64_t* end_off) {
+    if (!p) return DINT_E_ARG;
+    if (lists_off) *lists_off = p->lists_off;
+    if (lists_len) *lists_len = p->lists_len;
+    if (docs_dict_off) *docs_dict_off = p->docs_dict_off;
+    if (freqs_dict_off) *freqs_dict_off = p->freqs_dict_off;
+    if (end_off) *end_off = p->end_off;
+    return DINT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,80 @@
+// Internal declarations shared by the host format layer (dint_host.cpp) and the CUDA
+// translation unit (dint_kernels.cu). Not installed; the public surface is include/dint_b200.h.
+#pragma once
+
+#include <cstddef>
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/dint_b200.h"
+
+namespace dint {
+
+constexpr uint32_t kEntry = 16;        // constants::max_entry_size (dint_configuration.hpp:23)
+constexpr uint32_t kNumEntries = 65536;  // constants::num_entries   (dint_configuration.hpp:25)
+constexpr uint32_t kSelectors = 6;     // constants::num_selectors  (dint_configuration.hpp:20)
+constexpr uint32_t kReserved = 7;      // EXCEPTIONS + 5 run codewords (single_dictionary.hpp:22)
+constexpr uint32_t kDefaultBlock = 256;  // constants::block_size    (include/util.hpp:35)
+constexpr uint32_t kDefaultChunk = 1024;
+
+void set_error(const std::string& msg);
+
+inline uint16_t rd16(const uint8_t* p) { uint16_t v; std::memcpy(&v, p, 2); return v; }
+inline uint32_t rd32(const uint8_t* p) { uint32_t v; std::memcpy(&v, p, 4); return v; }
+inline uint64_t rd64(const uint8_t* p) { uint64_t v; std::memcpy(&v, p, 8); return v; }
+
+}  // namespace dint
+
+// Device-side view of a dictionary, passed by value to kernels.
+struct dint_dict_view {
+    const uint32_t* rows;   // [n_rows] x 16 words, 64-byte aligned rows: entry payload, zero padded
+    const uint8_t* lens;    // [n_rows] entry length - 1
+    uint32_t class_base[8]; // first row of each class (single kinds: one class at 0)
+    uint32_t n_rows;
+    uint32_t n_classes;
+};
+
+struct dint_dict {
+    int kind = 0;
+    int device = -1;
+    uint32_t n_rows = 0;
+    uint32_t n_classes = 1;
+    uint32_t class_base[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    uint32_t class_size[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    std::vector<uint32_t> h_rows;  // n_rows * 16
+    std::vector<uint8_t> h_lens;   // len - 1
+    std::vector<uint32_t> h_sums;  // sum(v_j + 1) over the entry, mod 2^32 (for doc_base of chunks)
+    uint32_t* d_rows = nullptr;
+    uint8_t* d_lens = nullptr;
+    dint_dict_view view() const {
+        dint_dict_view v;
+        v.rows = d_rows;
+        v.lens = d_lens;
+        for (int i = 0; i < 8; ++i) v.class_base[i] = class_base[i];
+        v.n_rows = n_rows;
+        v.n_classes = n_classes;
+        return v;
+    }
+};
+
+struct dint_vroom_plan {
+    uint64_t n_ints = 0;
+    std::vector<dint_segment> segments;
+    std::vector<uint64_t> list_offsets;       // n_lists + 1
+    std::vector<uint64_t> list_byte_offsets;  // n_lists + 1
+};
+
+struct dint_index_plan {
+    int kind = 0;
+    uint64_t n_lists = 0, num_docs = 0, n_postings = 0;
+    uint64_t lists_off = 0, lists_len = 0, docs_dict_off = 0, freqs_dict_off = 0, end_off = 0;
+    std::vector<dint_block> blocks;
+    std::vector<uint64_t> list_offsets;  // n_lists + 1 (postings)
+    std::vector<uint64_t> endpoints;     // n_lists + 1 (bytes in m_lists)
+};
+
+// implemented in dint_kernels.cu
+int dint_dict_upload(dint_dict* d);
+void dint_dict_release_device(dint_dict* d);

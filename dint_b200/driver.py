@@ -1,0 +1,149 @@
+"""Host-side mirror of the reference's decode drivers, on top of the C ABI.
+
+  * `VroomFile`  + `decode_dint`   <->  vroom_env/decode.cpp:95-155 (decode_dint<Decoder, Dictionary>)
+                                       and vroom_env/statistics.hpp:7-34 (same JSON keys)
+  * `IndexFile`  + `scan_index`    <->  succinct::mapper::map(dict_freq_index) + a full
+                                       document_enumerator scan (dict_freq_index.hpp:174-181,
+                                       dict_posting_list.hpp:113-124, 164-169)
+
+PyTorch is used only as plumbing: device buffers, streams, events. All decoding happens in
+libdint_b200.so; if the library or a CUDA device is missing these calls raise.
+"""
+import json
+
+import numpy as np
+import torch
+
+from . import capi
+
+TYPES = ("single_rect_dint", "single_packed_dint", "multi_packed_dint")
+
+
+def _require_cuda(device):
+    if not torch.cuda.is_available():
+        raise capi.DintError(capi.E_NODEVICE, "no CUDA device: dint_b200 has no CPU fallback")
+    return torch.device("cuda", device)
+
+
+def _to_device_bytes(data, dev, pinned=False):
+    t = torch.frombuffer(bytearray(data), dtype=torch.uint8) if not isinstance(data, torch.Tensor) else data
+    if pinned:
+        t = t.pin_memory()
+    return t.to(dev, non_blocking=pinned)
+
+
+def _structured_to_device(arr, dev):
+    raw = torch.from_numpy(np.ascontiguousarray(arr).view(np.uint8).reshape(-1))
+    return raw.to(dev)
+
+
+class VroomFile:
+    """A vroom-encoded .bin + its dictionary, resident on one GPU, ready for batch decode."""
+
+    def __init__(self, type_, bin_bytes, dict_bytes, device=0, block_size=256, chunk_ints=0):
+        if type_ not in capi.KIND_OF_TYPE:
+            raise ValueError(f"unknown type '{type_}'")  # decode.cpp:259 logs "ERROR: unknown type"
+        self.type = type_
+        self.dev = _require_cuda(device)
+        self.block_size = block_size
+        self.dict = capi.Dictionary(capi.KIND_OF_TYPE[type_], dict_bytes, device=device)
+        self.plan = capi.VroomPlan(self.dict, bin_bytes, block_size=block_size, chunk_ints=chunk_ints)
+        self.d_in = _to_device_bytes(bin_bytes, self.dev)
+        self.d_segs = _structured_to_device(self.plan.segments, self.dev)
+        self.d_list_offsets = torch.from_numpy(self.plan.list_offsets.astype(np.int64)).to(self.dev)
+        self.n_ints = int(self.plan.n_ints)
+        self.n_lists = int(self.plan.n_lists)
+
+    def decode(self, out=None, mode=capi.MODE_RAW, stream=None):
+        """Decode every list of the file into one packed int32 tensor of n_ints values."""
+        if out is None:
+            out = torch.empty(self.n_ints, dtype=torch.int32, device=self.dev)
+        st = (stream or torch.cuda.current_stream(self.dev)).cuda_stream
+        capi.decode_segments(self.dict, self.d_in.data_ptr(), self.plan.in_bytes, self.d_segs.data_ptr(),
+                             int(self.plan.n_segments), out.data_ptr(), mode, stream=st, block_size=self.block_size)
+        return out
+
+    def checksums(self, values, stream=None):
+        sums = torch.empty(self.n_lists, dtype=torch.int64, device=self.dev)
+        st = (stream or torch.cuda.current_stream(self.dev)).cuda_stream
+        capi.checksum_lists(values.data_ptr(), self.d_list_offsets.data_ptr(), self.n_lists, sums.data_ptr(), stream=st)
+        return sums
+
+
+class IndexFile:
+    """A frozen dict_freq_index .bin resident on one GPU (dictionaries are read from the file)."""
+
+    def __init__(self, type_, bin_bytes, device=0, block_size=256):
+        if type_ not in capi.KIND_OF_TYPE:
+            raise ValueError(f"unknown type '{type_}'")
+        self.type = type_
+        self.dev = _require_cuda(device)
+        kind = capi.KIND_OF_TYPE[type_]
+        self.block_size = block_size
+        self.plan = capi.IndexPlan(kind, bin_bytes, block_size=block_size)
+        p = self.plan
+        self.docs_dict = capi.Dictionary(kind, bin_bytes[p.docs_dict_off:p.freqs_dict_off], device=device, mapped=True)
+        self.freqs_dict = capi.Dictionary(kind, bin_bytes[p.freqs_dict_off:p.end_off], device=device, mapped=True)
+        self.d_bin = _to_device_bytes(bin_bytes, self.dev)
+        self.d_blocks = _structured_to_device(p.blocks, self.dev)
+        self.d_list_offsets = torch.from_numpy(p.list_offsets.astype(np.int64)).to(self.dev)
+        self.n_postings = int(p.n_postings)
+        self.n_lists = int(p.n_lists)
+
+    def scan(self, docids=None, freqs=None, want_docs=True, want_freqs=True, stream=None):
+        """docid() and freq() of every posting of every list, packed list after list."""
+        if want_docs and docids is None:
+            docids = torch.empty(self.n_postings, dtype=torch.int32, device=self.dev)
+        if want_freqs and freqs is None:
+            freqs = torch.empty(self.n_postings, dtype=torch.int32, device=self.dev)
+        st = (stream or torch.cuda.current_stream(self.dev)).cuda_stream
+        p = self.plan
+        capi.decode_index(self.docs_dict, self.freqs_dict, self.d_bin.data_ptr() + p.lists_off, p.lists_len,
+                          self.d_blocks.data_ptr(), int(p.n_blocks), self.block_size,
+                          docids.data_ptr() if want_docs else None, freqs.data_ptr() if want_freqs else None, stream=st)
+        return docids, freqs
+
+
+def decode_dint(type_, encoded_data_filename, dictionary_filename, device=0, repeat=1, block_size=256):
+    """vroom_env/decode.cpp:95-155 on the GPU: load, decode every list, report the reference's stats line."""
+    if not dictionary_filename:
+        raise RuntimeError("dictionary_filename must be specified")  # decode.cpp:98-100
+    try:
+        with open(encoded_data_filename, "rb") as f:
+            bin_bytes = f.read()
+    except OSError:
+        raise RuntimeError("Error opening index file")  # decode.cpp:104-106
+    with open(dictionary_filename, "rb") as f:
+        dict_bytes = f.read()
+    vf = VroomFile(type_, bin_bytes, dict_bytes, device=device, block_size=block_size)
+    out = torch.empty(vf.n_ints, dtype=torch.int32, device=vf.dev)
+    vf.decode(out)  # warm-up
+    torch.cuda.synchronize(vf.dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(repeat):
+        vf.decode(out)
+    e1.record()
+    torch.cuda.synchronize(vf.dev)
+    tot_elapsed = e0.elapsed_time(e1) / 1e3 / repeat
+    ns_x_int = tot_elapsed * 1e9 / max(vf.n_ints, 1)
+    stats = {"filename": encoded_data_filename, "num_sequences": str(vf.n_lists), "num_integers": str(vf.n_ints),
+             "type": type_, "tot_elapsed_time": str(tot_elapsed), "ns_x_int": str(ns_x_int),
+             "ints_x_sec": str(int(1e9 / ns_x_int)) if ns_x_int > 0 else "0"}
+    return stats, out
+
+
+def main(argv=None):
+    import argparse
+    ap = argparse.ArgumentParser(description="GPU counterpart of vroom_env/decode")
+    ap.add_argument("type")
+    ap.add_argument("encoded_data_filename")
+    ap.add_argument("--dict", dest="dictionary_filename")
+    ap.add_argument("--repeat", type=int, default=10)
+    a = ap.parse_args(argv)
+    stats, _ = decode_dint(a.type, a.encoded_data_filename, a.dictionary_filename, repeat=a.repeat)
+    print(json.dumps(stats))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,179 @@
+/* dint_b200 — B200-native decoder for DINT-compressed posting lists.
+ *
+ * C ABI of libdint_b200.so: the drop-in boundary for the reference's DECODE path
+ * (jermp/dint). Plain pointers and sizes only; no C++/torch types. All entry points
+ * return 0 on success or a negative DINT_E_* code (the reference has no error channel
+ * on this path: it asserts, or throws std::runtime_error on file open —
+ * vroom_env/decode.cpp:26-28, 98-100).
+ *
+ * What each group replaces in the reference (paths relative to the reference root):
+ *
+ *   dint_dict_*            Dictionary::builder::load + builder::build + Dictionary::copy
+ *                            include/dint/rectangular_dictionary.hpp:79-92, 206-213
+ *                            include/dint/single_dictionary.hpp:88-107, 230-238
+ *                            include/dint/multi_dictionary.hpp:93-121, 293-304
+ *   dint_vroom_plan_*      the `while (begin != end) header::read ...` walk of a vroom .bin
+ *                            vroom_env/decode.cpp:139-150, vroom_env/codecs.hpp:110-124
+ *   dint_index_plan_*      succinct::mapper::map(dict_freq_index) + Elias-Fano endpoints +
+ *                          document_enumerator's per-list block table
+ *                            include/dint/dict_freq_index.hpp:174-181, 209-214
+ *                            include/ds2i/compact_elias_fano.hpp:14-61
+ *                            include/dint/dict_posting_list.hpp:90-107
+ *   dint_decode_segments   single_opt_dint::decode / multi_opt_dint::decode over a batch
+ *                            vroom_env/dint_codecs.hpp:37-107, 315-323, 521-619
+ *   dint_decode_index      decode_docs_block + decode_freqs_block + next() over a batch,
+ *                          i.e. opt_dint_single_dict_block / opt_dint_multi_dict_block::decode
+ *                          and interpolative_block::decode for partial blocks
+ *                            include/dint/dict_posting_list.hpp:284-318, 113-124, 164-169
+ *                            include/dint/dint_codecs.hpp:13-49, 269-274, 460-510
+ *                            include/ds2i/block_codecs.hpp:130-150
+ *   dint_decode_list_host  one Decoder::decode(dict, in, out, universe, n) call, host buffers
+ *   dint_checksum_lists    (new) per-list 64-bit checksums used for large-scale parity
+ *
+ * Ownership: the caller owns every device buffer; nothing is allocated on the decode
+ * path. Outputs are PACKED (list after list, no slack) — unlike the reference, which
+ * needs a pre-zeroed buffer with 16..256 ints of slack (dint_codecs.hpp:11,
+ * dict_posting_list.hpp:104-105). Handles are immutable after creation and may be used
+ * from any stream of the device they were created on.
+ *
+ * There is NO CPU fallback: every decode entry point runs sm_100a kernels or fails.
+ */
+#ifndef DINT_B200_H
+#define DINT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DINT_B200_ABI_VERSION 1
+
+/* dictionary kinds == the reference's three dictionary types */
+enum {
+    DINT_DICT_RECT = 0,   /* single_rect_dint   : rectangular_dictionary   */
+    DINT_DICT_PACKED = 1, /* single_packed_dint : single_dictionary<pack>  */
+    DINT_DICT_MULTI = 2   /* multi_packed_dint  : multi_dictionary<pack>   */
+};
+
+/* output modes of dint_decode_segments */
+enum {
+    DINT_MODE_RAW = 0,    /* exactly what Decoder::decode writes: d-gap-1 / freq-1        */
+    DINT_MODE_DOCIDS = 1, /* fused prefix sum: docid[i] = docid[i-1] + v[i] + 1            */
+    DINT_MODE_FREQS = 2   /* fused +1 shift:   freq[i] = v[i] + 1                          */
+};
+
+enum {
+    DINT_OK = 0,
+    DINT_E_ARG = -1,     /* null pointer / bad enum / bad size                              */
+    DINT_E_FORMAT = -2,  /* malformed dictionary / .bin                                     */
+    DINT_E_CUDA = -3,    /* CUDA runtime error (dint_last_error() has the string)           */
+    DINT_E_NOMEM = -4,
+    DINT_E_NODEVICE = -5 /* no CUDA device: there is no CPU fallback                        */
+};
+
+/* One contiguous codeword stream that starts on a codeword boundary and produces
+ * exactly n integers: a whole vroom list, a chunk of a long list, or one 256-int
+ * block of a multi_packed vroom list. 24 bytes. */
+typedef struct dint_segment {
+    uint64_t in_off;   /* byte offset of the first codeword (multi: of the selector byte)  */
+    uint64_t out_off;  /* index of the first output integer                                */
+    uint32_t n;        /* integers produced                                                */
+    uint32_t doc_base; /* DOCIDS mode: docid[first] = doc_base + v[first]                  */
+} dint_segment;
+
+/* One block of a dict_freq_index posting list (docs bytes immediately followed by the
+ * freqs bytes). size == block_size -> DINT coded, size < block_size -> interpolative. 32 bytes. */
+typedef struct dint_block {
+    uint64_t in_off;    /* byte offset of the docs block inside m_lists                    */
+    uint64_t out_off;   /* posting index of the block's first posting                      */
+    uint32_t size;      /* postings in the block                                           */
+    uint32_t cur_base;  /* block_max[b-1] + 1 (0 for b == 0)                               */
+    uint32_t block_max; /* last docid of the block                                         */
+    uint32_t reserved;
+} dint_block;
+
+typedef struct dint_dict dint_dict;
+typedef struct dint_vroom_plan dint_vroom_plan;
+typedef struct dint_index_plan dint_index_plan;
+
+const char* dint_last_error(void);
+int dint_abi_version(void);
+/* number of kernels launched by this library in the calling process so far */
+uint64_t dint_kernel_launches(void);
+
+/* ---- dictionaries --------------------------------------------------------------- */
+/* Parse a reference dictionary FILE image (dict.<name>.<type>.DSF-65536-16) and upload it
+ * to `device`. device < 0: host-side tables only (enough for the *_plan_* pre-passes). */
+int dint_dict_create(int kind, const void* file_bytes, size_t len, int device, dint_dict** out);
+/* Same for the mappable_vector images embedded at the end of a frozen index .bin. */
+int dint_dict_create_mapped(int kind, const void* bytes, size_t len, int device, dint_dict** out, size_t* consumed);
+void dint_dict_destroy(dint_dict* d);
+int dint_dict_kind(const dint_dict* d);
+uint32_t dint_dict_num_rows(const dint_dict* d);
+/* bytes resident in HBM for this dictionary (rows + length table) */
+size_t dint_dict_device_bytes(const dint_dict* d);
+/* Dictionary::copy through the DEVICE tables (debug/parity): copies the 16-word row of
+ * entry i of class cls into out16 and returns its length through *len. */
+int dint_dict_copy(const dint_dict* d, uint32_t cls, uint32_t i, uint32_t* out16, uint32_t* len);
+
+/* ---- vroom .bin pre-pass (host, one time per file) ---------------------------------- */
+/* Walks the file exactly like vroom_env/decode.cpp does and emits the segment table.
+ * chunk_ints: long single-dictionary lists are cut into segments of about this many
+ * integers at codeword boundaries (0 = library default). block_size: the reference's
+ * constants::block_size the file was encoded with (multi only; 0 = 256). */
+int dint_vroom_plan_create(const dint_dict* d, const void* bin, size_t len, uint32_t block_size, uint32_t chunk_ints,
+                           dint_vroom_plan** out);
+void dint_vroom_plan_destroy(dint_vroom_plan* p);
+uint64_t dint_vroom_plan_num_lists(const dint_vroom_plan* p);
+uint64_t dint_vroom_plan_num_ints(const dint_vroom_plan* p);
+uint64_t dint_vroom_plan_num_segments(const dint_vroom_plan* p);
+const dint_segment* dint_vroom_plan_segments(const dint_vroom_plan* p);
+/* n_lists + 1 offsets into the packed output; list i is [off[i], off[i+1]) */
+const uint64_t* dint_vroom_plan_list_offsets(const dint_vroom_plan* p);
+/* n_lists + 1 byte offsets of the list headers; the last one is the file size */
+const uint64_t* dint_vroom_plan_list_byte_offsets(const dint_vroom_plan* p);
+
+/* ---- frozen dict_freq_index .bin pre-pass (host, one time per file) -------------------- */
+int dint_index_plan_create(int kind, const void* bin, size_t len, uint32_t block_size, dint_index_plan** out);
+void dint_index_plan_destroy(dint_index_plan* p);
+uint64_t dint_index_plan_num_lists(const dint_index_plan* p);
+uint64_t dint_index_plan_num_docs(const dint_index_plan* p);
+uint64_t dint_index_plan_num_postings(const dint_index_plan* p);
+uint64_t dint_index_plan_num_blocks(const dint_index_plan* p);
+const dint_block* dint_index_plan_blocks(const dint_index_plan* p);
+const uint64_t* dint_index_plan_list_offsets(const dint_index_plan* p); /* n_lists + 1 */
+const uint64_t* dint_index_plan_endpoints(const dint_index_plan* p);    /* n_lists + 1 byte offsets in m_lists */
+/* byte ranges inside the .bin */
+int dint_index_plan_layout(const dint_index_plan* p, uint64_t* lists_off, uint64_t* lists_len, uint64_t* docs_dict_off,
+                           uint64_t* freqs_dict_off, uint64_t* end_off);
+
+/* ---- device decode (stream ordered; all pointers are DEVICE pointers) ------------------ */
+/* d_in: the .bin bytes as they are on disk (in_bytes of them; no padding required).
+ * d_segs: n_segs descriptors. d_out: packed output, at least max(out_off + n) ints.
+ * stream: a cudaStream_t (0 = default stream). */
+int dint_decode_segments(const dint_dict* d, const uint8_t* d_in, size_t in_bytes, const dint_segment* d_segs,
+                         size_t n_segs, uint32_t block_size, uint32_t* d_out, int mode, void* stream);
+
+/* d_lists: the m_lists bytes of the index. Writes docids and freqs (enumerator
+ * semantics: docid(), freq()) of every block into the packed arrays. Either output
+ * may be NULL to skip it (docs blocks are still parsed to locate the freqs bytes). */
+int dint_decode_index(const dint_dict* docs_dict, const dint_dict* freqs_dict, const uint8_t* d_lists,
+                      size_t lists_bytes, const dint_block* d_blocks, size_t n_blocks, uint32_t block_size,
+                      uint32_t* d_docids, uint32_t* d_freqs, void* stream);
+
+/* sums[i] = sum_{j in list i} (value_j + 1) * (j + 1)  mod 2^64 */
+int dint_checksum_lists(const uint32_t* d_values, const uint64_t* d_list_offsets, size_t n_lists, uint64_t* d_sums,
+                        void* stream);
+
+/* ---- host-buffer convenience: one Decoder::decode(dict, in, out, universe, n) call ------ */
+/* in/out are HOST pointers; copies in, decodes on the device, copies out; *consumed is
+ * the reference's returned pointer minus `in`. out receives exactly n integers (RAW). */
+int dint_decode_list_host(const dint_dict* d, const uint8_t* in, size_t in_avail, uint32_t* out, uint32_t n,
+                          uint32_t block_size, size_t* consumed);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DINT_B200_H */

@@ -1,0 +1,234 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against
+  (1) the sha256 of the reference decoders' own output (tests/golden/manifest.json), and
+  (2) the oracle (oracle/dint_oracle.c) on the same inputs, element by element.
+Bit-exact: this is integer work, there is no tolerance."""
+import numpy as np
+import pytest
+import torch
+
+import golden_data as g
+import stream_builder as sb
+from dint_b200 import capi, driver
+from oracle_lib import KINDS
+
+pytestmark = pytest.mark.gpu
+
+
+def _np(t):
+    return t.cpu().numpy().view(np.uint32)
+
+
+@pytest.fixture(scope="module")
+def vroom_files(golden):
+    cache = {}
+
+    def get(type_, part, chunk_ints=0):
+        key = (type_, part, chunk_ints)
+        if key not in cache:
+            cache[key] = driver.VroomFile(type_, golden.bytes(golden.vroom_name(type_, part)),
+                                          golden.bytes(golden.dict_name(type_, part)), chunk_ints=chunk_ints)
+        return cache[key]
+    return get
+
+
+@pytest.mark.parametrize("type_", g.TYPES)
+@pytest.mark.parametrize("part,key", (("docs", "vroom_docs_gaps_sha256"), ("freqs", "vroom_freqs_minus1_sha256")))
+def test_vroom_raw_equals_reference_output(golden, oracle, vroom_files, type_, part, key):
+    """config 1: vroom decode of the whole test collection, full-output comparison"""
+    vf = vroom_files(type_, part)
+    before = capi.kernel_launches()
+    out = _np(vf.decode(mode=capi.MODE_RAW))
+    assert capi.kernel_launches() == before + 1
+    assert len(out) == golden.n_postings
+    assert g.sha(out.tobytes()) == golden.sha[key]
+    ho = oracle.dict_parse(KINDS[type_], golden.bytes(golden.dict_name(type_, part)))
+    want, _ = oracle.vroom_decode_file(ho, golden.bytes(golden.vroom_name(type_, part)), golden.n_postings, golden.n_lists)
+    assert np.array_equal(out, want)
+
+
+@pytest.mark.parametrize("type_", g.TYPES)
+@pytest.mark.parametrize("chunk", (0, 1, 33, 100))
+def test_vroom_fused_docids_and_freqs(golden, vroom_files, type_, chunk):
+    """fused prefix sum / +1 shift must reproduce the .docs / .freqs collection itself"""
+    d = _np(vroom_files(type_, "docs", chunk).decode(mode=capi.MODE_DOCIDS))
+    assert g.sha(d.tobytes()) == golden.sha["docids_sha256"]
+    f = _np(vroom_files(type_, "freqs", chunk).decode(mode=capi.MODE_FREQS))
+    assert g.sha(f.tobytes()) == golden.sha["freqs_sha256"]
+    r = _np(vroom_files(type_, "docs", chunk).decode(mode=capi.MODE_RAW))
+    assert g.sha(r.tobytes()) == golden.sha["vroom_docs_gaps_sha256"]
+
+
+@pytest.mark.parametrize("type_", g.TYPES)
+def test_index_scan_equals_reference_enumerator(golden, oracle, type_):
+    """config 2: every docid()/freq() of the frozen dict_freq_index (verify_collection semantics)"""
+    idx = driver.IndexFile(type_, golden.bytes(golden.index_name(type_)))
+    d, f = idx.scan()
+    d, f = _np(d), _np(f)
+    assert g.sha(d.tobytes()) == golden.sha["docids_sha256"]
+    assert g.sha(f.tobytes()) == golden.sha["freqs_sha256"]
+    wd, wf, _ = oracle.index_decode(KINDS[type_], golden.bytes(golden.index_name(type_)), golden.n_postings)
+    assert np.array_equal(d, wd) and np.array_equal(f, wf)
+    # either stream alone
+    d2, _ = idx.scan(want_freqs=False)
+    _, f2 = idx.scan(want_docs=False)
+    assert np.array_equal(_np(d2), wd) and np.array_equal(_np(f2), wf)
+
+
+def test_query_log_ragged_batch(golden, oracle):
+    """config 3: ragged batch = only the lists touched by a query log (here: a seeded sample of
+    1088 distinct terms, the size of test_data/queries' vocabulary), decoded in one launch"""
+    type_ = "single_packed_dint"
+    vf = driver.VroomFile(type_, golden.bytes(golden.vroom_name(type_, "docs")), golden.bytes(golden.dict_name(type_, "docs")))
+    rng = np.random.default_rng(42)
+    terms = np.sort(rng.choice(vf.n_lists, 1088, replace=False))
+    segs = vf.plan.segments
+    list_of = np.searchsorted(vf.plan.list_offsets, segs["out_off"], side="right") - 1
+    pick = segs[np.isin(list_of, terms)].copy()
+    lens = pick["n"].astype(np.int64)
+    new_off = np.concatenate([[0], np.cumsum(lens)])
+    src_off = pick["out_off"].astype(np.int64)
+    pick["out_off"] = new_off[:-1]
+    d_segs = torch.from_numpy(pick.view(np.uint8).reshape(-1)).cuda()
+    out = torch.zeros(int(new_off[-1]), dtype=torch.int32, device="cuda")
+    capi.decode_segments(vf.dict, vf.d_in.data_ptr(), vf.plan.in_bytes, d_segs.data_ptr(), len(pick), out.data_ptr(),
+                         capi.MODE_DOCIDS, stream=torch.cuda.current_stream().cuda_stream)
+    full = _np(vf.decode(mode=capi.MODE_DOCIDS))
+    want = np.concatenate([full[s:s + n] for s, n in zip(src_off, lens)])
+    assert np.array_equal(_np(out), want)
+
+
+def _decode_lists(type_, dict_bytes, lists_vals, block_size=256, chunk_ints=0, mode=capi.MODE_RAW, **kw):
+    di = sb.DictImage(capi.KIND_OF_TYPE[type_], dict_bytes)
+    data = b"".join(sb.encode_vroom_list(di, v, block_size=block_size, **kw) for v in lists_vals)
+    vf = driver.VroomFile(type_, data, dict_bytes, chunk_ints=chunk_ints, block_size=block_size)
+    return _np(vf.decode(mode=mode)), data, vf
+
+
+EDGE_LISTS = [
+    [0, 1, 0, 1, 65536, 1, 0, 70000, 65537, 0, 0, 1],
+    [1 << 31, 0xFFFFFFFF, 65537, 65536, 1, 0] * 9,
+    [0] * 600 + [5] + [0] * 17,
+    [0] * 256, [0] * 255, [0] * 16, [7], [0], [1], [65535], [65536],
+    [3] * 31, [3] * 32, [3] * 33, [70000] * 31 + [1], [70000] * 32, [1, 0] * 40,
+]
+
+
+@pytest.mark.parametrize("type_", g.TYPES)
+@pytest.mark.parametrize("kw", ({}, {"use_dict": False}, {"use_runs": False, "use_dict": False}))
+def test_edge_case_streams(golden, oracle, type_, kw):
+    """32-bit exceptions, payload equal to 0/1, exceptions straddling 32-symbol tiles, runs,
+    single-integer lists, 8-bit blocks (multi): none of these occur in test_collection"""
+    rng = np.random.default_rng(9)
+    lists = EDGE_LISTS + [rng.integers(0, 3, 777).tolist(), rng.integers(0, 1 << 20, 300).tolist(),
+                          rng.integers(0, 70000, 1000).tolist()]
+    dict_bytes = golden.bytes(golden.dict_name(type_, "docs"))
+    want = np.concatenate([np.asarray(v, dtype=np.uint32) for v in lists])
+    for sels in ([0, 6, 3, 9, 1, 7], [8], [2]):
+        for chunk in (0, 1, 5):
+            out, data, vf = _decode_lists(type_, dict_bytes, lists, chunk_ints=chunk, selectors=sels, **kw)
+            assert np.array_equal(out, want), (sels, chunk)
+            ho = oracle.dict_parse(KINDS[type_], dict_bytes)
+            o, _ = oracle.vroom_decode_file(ho, data, len(want), len(lists))
+            assert np.array_equal(o, want)
+            # fused modes against numpy
+            docs = _np(vf.decode(mode=capi.MODE_DOCIDS))
+            exp = np.concatenate([(np.cumsum(np.asarray(v, dtype=np.uint64) + 1) - 1).astype(np.uint32) for v in lists])
+            assert np.array_equal(docs, exp)
+            assert np.array_equal(_np(vf.decode(mode=capi.MODE_FREQS)), want + np.uint32(1))
+
+
+def test_empty_batch_and_empty_file(golden):
+    dict_bytes = golden.bytes(golden.dict_name("single_packed_dint", "docs"))
+    vf = driver.VroomFile("single_packed_dint", b"", dict_bytes)
+    assert vf.n_ints == 0 and vf.decode().numel() == 0
+
+
+@pytest.mark.parametrize("type_", g.TYPES)
+def test_dict_copy_device_tables(golden, oracle, type_):
+    """Dictionary::copy through the device-resident tables"""
+    kind = KINDS[type_]
+    data = golden.bytes(golden.dict_name(type_, "freqs"))
+    d = capi.Dictionary(kind, data, device=0)
+    ho = oracle.dict_parse(kind, data)
+    rng = np.random.default_rng(2)
+    for cls in range(5 if kind == 2 else 1):
+        hi = 120 if kind == 2 else 65536
+        for i in [2, 3, 6, 7, 8] + rng.integers(7, hi, 40).tolist():
+            n, row = d.copy(cls, i)
+            wn, wrow = oracle.dict_copy(ho, cls, i)
+            assert n == wn and np.array_equal(row[:min(n, 16)], wrow[:min(n, 16)])
+
+
+@pytest.mark.parametrize("type_", g.TYPES)
+def test_decode_list_host_is_decoder_decode(golden, oracle, type_):
+    """the per-list drop-in: values AND the advanced input pointer"""
+    bin_ = golden.bytes(golden.vroom_name(type_, "docs"))
+    dict_bytes = golden.bytes(golden.dict_name(type_, "docs"))
+    d = capi.Dictionary(KINDS[type_], dict_bytes, device=0)
+    plan = capi.VroomPlan(d, bin_)
+    ho = oracle.dict_parse(KINDS[type_], dict_bytes)
+    raw = np.frombuffer(bin_, dtype=np.uint8)
+    lens = np.diff(plan.list_offsets.astype(np.int64))
+    rng = np.random.default_rng(4)
+    for i in sorted(set(rng.integers(0, plan.n_lists, 12).tolist()) | set(np.argsort(-lens)[:3].tolist())):
+        n = int(lens[i])
+        start = int(plan.list_byte_offsets[i])
+        hdr = np.zeros(2, dtype=np.uint32)
+        start += oracle.lib.oracle_vbyte_decode(raw[start:].ctypes.data, hdr.ctypes.data, 2)
+        vals, used = capi.decode_list_host(d, bin_[start:], n)
+        want, wused = oracle.vroom_decode_list(ho, np.frombuffer(bin_[start:] + b"\0" * 64, dtype=np.uint8), n)
+        assert used == wused == int(plan.list_byte_offsets[i + 1]) - start
+        assert np.array_equal(vals, want)
+
+
+def test_checksums_and_replicated_collection(golden, vroom_files):
+    """size-independent property for large inputs: decoding K back-to-back copies of the file
+    yields K identical per-list checksum vectors (checksum of checksums)"""
+    vf = vroom_files("single_packed_dint", "docs")
+    out = vf.decode()
+    sums = vf.checksums(out).cpu().numpy().view(np.uint64)
+    want = g.checksum_lists(_np(out), np.diff(vf.plan.list_offsets.astype(np.int64)))
+    assert np.array_equal(sums, want)
+    K = 3
+    bin_ = golden.bytes(golden.vroom_name("single_packed_dint", "docs"))
+    big = driver.VroomFile("single_packed_dint", bin_ * K, golden.bytes(golden.dict_name("single_packed_dint", "docs")))
+    bo = big.decode()
+    bs = big.checksums(bo).cpu().numpy().view(np.uint64).reshape(K, -1)
+    assert all(np.array_equal(bs[k], want) for k in range(K))
+    assert np.array_equal(_np(bo).reshape(K, -1)[K - 1], _np(out))
+
+
+@pytest.mark.parametrize("sum_known", (True, False))
+def test_interpolative_tail_blocks_random(golden, sum_known):
+    """partial blocks through the index path: hand-built m_lists with one tail block per list"""
+    rng = np.random.default_rng(13)
+    kind = 1
+    idxbin = golden.bytes(golden.index_name("single_packed_dint"))
+    plan0 = capi.IndexPlan(kind, idxbin)
+    dd = capi.Dictionary(kind, idxbin[plan0.docs_dict_off:plan0.freqs_dict_off], device=0, mapped=True)
+    fd = capi.Dictionary(kind, idxbin[plan0.freqs_dict_off:plan0.end_off], device=0, mapped=True)
+    lists = bytearray()
+    blocks, want_d, want_f = [], [], []
+    pos = 0
+    for n in [1, 2, 3, 16, 17, 31, 100, 254, 255] * 3:
+        for mag in (1, 2, 100, 100000):
+            gaps = rng.integers(0, mag, n).astype(np.uint32)
+            fm1 = rng.integers(0, mag, n).astype(np.uint32)
+            base = int(rng.integers(0, 1000))
+            docs = base + np.cumsum(gaps.astype(np.uint64) + 1) - 1
+            db, s = sb.encode_interpolative_block(gaps, True)
+            fb, _ = sb.encode_interpolative_block(fm1, False)
+            blocks.append((len(lists), pos, n, base, int(docs[-1]), 0))
+            lists += db + fb
+            want_d.append(docs.astype(np.uint32))
+            want_f.append(fm1 + 1)
+            pos += n
+    barr = np.array(blocks, dtype=capi.BLOCK_DTYPE)
+    d_lists = torch.frombuffer(bytearray(lists), dtype=torch.uint8).cuda()
+    d_blocks = torch.from_numpy(barr.view(np.uint8).reshape(-1)).cuda()
+    d_docs = torch.zeros(pos, dtype=torch.int32, device="cuda")
+    d_freqs = torch.zeros(pos, dtype=torch.int32, device="cuda")
+    capi.decode_index(dd, fd, d_lists.data_ptr(), len(lists), d_blocks.data_ptr(), len(barr), 256, d_docs.data_ptr(),
+                      d_freqs.data_ptr(), stream=torch.cuda.current_stream().cuda_stream)
+    assert np.array_equal(_np(d_docs), np.concatenate(want_d))
+    assert np.array_equal(_np(d_freqs), np.concatenate(want_f))

@@ -1,0 +1,129 @@
+"""Host format layer (dint_b200/csrc/dint_host.cpp) against the oracle: no GPU needed."""
+import numpy as np
+import pytest
+
+import golden_data as g
+import stream_builder as sb
+from dint_b200 import capi
+from oracle_lib import KINDS
+
+
+@pytest.mark.parametrize("type_", g.TYPES)
+@pytest.mark.parametrize("part", ("docs", "freqs"))
+def test_vroom_plan_matches_oracle_walk(oracle, golden, type_, part):
+    kind = KINDS[type_]
+    bin_ = golden.bytes(golden.vroom_name(type_, part))
+    d = capi.Dictionary(kind, golden.bytes(golden.dict_name(type_, part)))
+    plan = capi.VroomPlan(d, bin_, chunk_ints=300)
+    ho = oracle.dict_parse(kind, golden.bytes(golden.dict_name(type_, part)))
+    vals, ln = oracle.vroom_decode_file(ho, bin_, golden.n_postings, golden.n_lists)
+    assert plan.n_lists == golden.n_lists and plan.n_ints == golden.n_postings
+    assert np.array_equal(np.diff(plan.list_offsets.astype(np.int64)), ln.astype(np.int64))
+    assert int(plan.list_byte_offsets[-1]) == len(bin_)
+    segs = plan.segments
+    # segments tile the output exactly, in order
+    assert int(segs["out_off"][0]) == 0
+    assert np.array_equal(segs["out_off"][1:], (segs["out_off"] + segs["n"])[:-1])
+    assert int(segs["out_off"][-1] + segs["n"][-1]) == golden.n_postings
+    # doc_base of a segment = sum(v + 1) over the list's earlier postings (0 at a list start)
+    starts = plan.list_offsets[:-1]
+    first = np.isin(segs["out_off"], starts)
+    if type_ != "multi_packed_dint":
+        assert first.sum() == golden.n_lists
+    csum = np.concatenate([np.zeros(1, dtype=np.uint64), np.cumsum(vals.astype(np.uint64) + np.uint64(1))])
+    list_of = np.searchsorted(plan.list_offsets, segs["out_off"], side="right") - 1
+    want = (csum[segs["out_off"].astype(np.int64)] - csum[plan.list_offsets[list_of].astype(np.int64)]) & np.uint64(0xFFFFFFFF)
+    assert np.array_equal(segs["doc_base"].astype(np.uint64), want)
+    # every segment starts on a codeword boundary: decoding it alone reproduces its slice
+    raw = np.frombuffer(bin_ + b"\0" * 64, dtype=np.uint8)
+    rng = np.random.default_rng(5)
+    for i in rng.integers(0, len(segs), 200):
+        s = segs[i]
+        a, _ = oracle.vroom_decode_list(ho, raw[int(s["in_off"]):], int(s["n"])) if type_ != "multi_packed_dint" \
+            else oracle.block_decode(ho, raw[int(s["in_off"]):], 0, int(s["n"]), block_size=int(s["n"]))
+        assert np.array_equal(a, vals[int(s["out_off"]):int(s["out_off"]) + int(s["n"])])
+
+
+@pytest.mark.parametrize("type_", g.TYPES)
+def test_index_plan_matches_oracle(oracle, golden, type_):
+    kind = KINDS[type_]
+    bin_ = golden.bytes(golden.index_name(type_))
+    plan = capi.IndexPlan(kind, bin_)
+    ep, info = oracle.index_endpoints(kind, bin_)
+    assert plan.n_lists == info.n_lists == golden.n_lists
+    assert plan.num_docs == info.num_docs == 10000
+    assert (plan.lists_off, plan.lists_len) == (info.lists_off, info.lists_len)
+    assert (plan.docs_dict_off, plan.freqs_dict_off, plan.end_off) == (info.docs_dict_off, info.freqs_dict_off, len(bin_))
+    assert np.array_equal(plan.endpoints[:-1], ep) and int(plan.endpoints[-1]) == info.lists_len
+    assert plan.n_postings == golden.n_postings
+    d, f, ln = oracle.index_decode(kind, bin_, golden.n_postings)
+    assert np.array_equal(np.diff(plan.list_offsets.astype(np.int64)), ln.astype(np.int64))
+    b = plan.blocks
+    assert int(b["size"].astype(np.int64).sum()) == golden.n_postings
+    # block_max is the docid of the block's last posting; cur_base = previous block_max + 1
+    last = (b["out_off"] + b["size"] - 1).astype(np.int64)
+    assert np.array_equal(d[last], b["block_max"])
+    firsts = np.isin(b["out_off"], plan.list_offsets[:-1])
+    assert np.all(b["cur_base"][firsts] == 0)
+    assert np.array_equal(b["cur_base"][~firsts], b["block_max"][np.nonzero(~firsts)[0] - 1] + 1)
+
+
+def test_embedded_dictionaries_equal_dictionary_files(oracle, golden):
+    """the dictionaries frozen inside the index are the ones in the dict files"""
+    for type_ in g.TYPES:
+        kind = KINDS[type_]
+        bin_ = golden.bytes(golden.index_name(type_))
+        plan = capi.IndexPlan(kind, bin_)
+        a = oracle.lib.oracle_dict_parse_mapped(kind, np.frombuffer(bin_, dtype=np.uint8)[plan.docs_dict_off:].ctypes.data,
+                                                len(bin_) - plan.docs_dict_off, None)
+        b = oracle.dict_parse(kind, golden.bytes(golden.dict_name(type_, "docs")))
+        for cls in range(6 if kind == 2 else 1):
+            for i in (0, 1, 2, 6) + ((7, 8, 100, 130) if cls < 5 else ()):  # class 5 holds only the reserved 7
+                na, ra = oracle.dict_copy(a, cls, i)
+                nb, rb = oracle.dict_copy(b, cls, i)
+                assert na == nb and np.array_equal(ra[:min(na, 16)], rb[:min(nb, 16)])
+
+
+def test_malformed_inputs_are_rejected(golden):
+    kind = 1
+    dict_bytes = golden.bytes(golden.dict_name("single_packed_dint", "docs"))
+    with pytest.raises(capi.DintError) as e:
+        capi.Dictionary(kind, dict_bytes[:1000])
+    assert e.value.code == -2
+    with pytest.raises(capi.DintError):
+        capi.Dictionary(7, dict_bytes)
+    d = capi.Dictionary(kind, dict_bytes)
+    bin_ = golden.bytes(golden.vroom_name("single_packed_dint", "docs"))
+    with pytest.raises(capi.DintError) as e:
+        capi.VroomPlan(d, bin_[:len(bin_) - 3])  # truncated in the middle of the last list
+    assert e.value.code == -2
+    idx = golden.bytes(golden.index_name("single_packed_dint"))
+    with pytest.raises(capi.DintError):
+        capi.IndexPlan(kind, idx[:len(idx) - 8])
+    with pytest.raises(capi.DintError):
+        capi.IndexPlan(0, idx)  # wrong dictionary kind for this file
+
+
+def test_empty_vroom_file(golden):
+    d = capi.Dictionary(1, golden.bytes(golden.dict_name("single_packed_dint", "docs")))
+    plan = capi.VroomPlan(d, b"")
+    assert plan.n_lists == 0 and plan.n_ints == 0 and plan.n_segments == 0
+
+
+def test_chunking_respects_exception_payload(golden):
+    """chunk boundaries may never fall between an exception codeword and its payload"""
+    di = sb.DictImage(1, golden.bytes(golden.dict_name("single_packed_dint", "docs")))
+    d = capi.Dictionary(1, golden.bytes(golden.dict_name("single_packed_dint", "docs")))
+    vals = [70000, 1, 0, 65536] * 50
+    data = sb.encode_vroom_list(di, vals, use_dict=False, use_runs=False)
+    for chunk in (1, 2, 3, 7):
+        plan = capi.VroomPlan(d, data, chunk_ints=chunk)
+        assert plan.n_ints == len(vals)
+        # with only exceptions every integer costs 4 or 6 bytes: offsets must follow that grid
+        pos = len(sb.vbyte(len(vals))) + len(sb.vbyte(sum(vals) & 0xFFFFFFFF))
+        expect = {}
+        for j, v in enumerate(vals):
+            expect[j] = pos
+            pos += 4 if v < 65536 else 6
+        for s in plan.segments:
+            assert expect[int(s["out_off"])] == int(s["in_off"])
