@@ -34,6 +34,7 @@ SYMBOLS = [
     "dint_index_plan_num_postings", "dint_index_plan_num_blocks", "dint_index_plan_blocks",
     "dint_index_plan_list_offsets", "dint_index_plan_endpoints", "dint_index_plan_layout",
     "dint_decode_segments", "dint_decode_index", "dint_checksum_lists", "dint_decode_list_host",
+    "dint_vroom_ctx_create", "dint_vroom_ctx_destroy", "dint_vroom_ctx_device_output", "dint_vroom_decode_host",
 ]
 
 
@@ -88,6 +89,12 @@ def lib():
         L.dint_decode_index.argtypes = [vp, vp, vp, sz, vp, sz, u32, vp, vp, vp]
         L.dint_checksum_lists.argtypes = [vp, vp, sz, vp, vp]
         L.dint_decode_list_host.argtypes = [vp, vp, sz, vp, u32, u32, C.POINTER(sz)]
+        L.dint_vroom_ctx_create.argtypes = [vp, vp, u32, C.POINTER(vp)]
+        L.dint_vroom_ctx_destroy.argtypes = [vp]
+        L.dint_vroom_ctx_destroy.restype = None
+        L.dint_vroom_ctx_device_output.argtypes = [vp]
+        L.dint_vroom_ctx_device_output.restype = vp
+        L.dint_vroom_decode_host.argtypes = [vp, vp, sz, i32, vp, vp, vp]
         _lib = L
     return _lib
 
@@ -174,7 +181,48 @@ class VroomPlan:
         self.list_byte_offsets = _view(L.dint_vroom_plan_list_byte_offsets(h), self.n_lists + 1, np.uint64)
         self.block_size = block_size
         self.in_bytes = len(a)
-        L.dint_vroom_plan_destroy(h)
+        self.handle = h
+        self.dictionary = dictionary
+
+    def close(self):
+        if getattr(self, "handle", None):
+            lib().dint_vroom_plan_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class VroomHostDecoder:
+    """Host-buffer batch decode of whole vroom .bin files that share one plan
+    (vroom_env/decode.cpp:139-150 as one call): H2D, decode, checksums / output D2H."""
+
+    def __init__(self, plan, block_size=256):
+        self.plan = plan
+        h = C.c_void_p()
+        check(lib().dint_vroom_ctx_create(plan.dictionary.handle, plan.handle, block_size, C.byref(h)))
+        self.handle = h
+
+    def decode(self, h_bin_ptr, nbytes, mode=MODE_RAW, h_out_ptr=None, h_sums_ptr=None, stream=0):
+        check(lib().dint_vroom_decode_host(self.handle, h_bin_ptr, nbytes, mode, h_out_ptr, h_sums_ptr, stream))
+
+    @property
+    def device_output(self):
+        return lib().dint_vroom_ctx_device_output(self.handle)
+
+    def close(self):
+        if getattr(self, "handle", None):
+            lib().dint_vroom_ctx_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class IndexPlan:

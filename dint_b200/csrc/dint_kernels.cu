@@ -673,8 +673,10 @@ int dint_checksum_lists(const uint32_t* d_values, const uint64_t* d_list_offsets
                         void* stream) {
     if (n_lists == 0) return DINT_OK;
     if (!d_values || !d_list_offsets || !d_sums) return DINT_E_ARG;
-    int dev = 0;
-    CUDA_TRY(cudaGetDevice(&dev));
+    cudaPointerAttributes pa;
+    CUDA_TRY(cudaPointerGetAttributes(&pa, d_values));
+    int dev = pa.device;
+    device_guard g(dev);
     device_info di;
     int rc = get_device_info(dev, &di);
     if (rc) return rc;
@@ -683,6 +685,87 @@ int dint_checksum_lists(const uint32_t* d_values, const uint64_t* d_list_offsets
     checksum_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_values, d_list_offsets, n_lists, d_sums);
     ++g_launches;
     CUDA_TRY(cudaGetLastError());
+    return DINT_OK;
+}
+
+struct dint_vroom_ctx {
+    const dint_dict* dict = nullptr;
+    uint32_t block_size = 0;
+    uint64_t n_lists = 0, n_ints = 0, n_segs = 0, in_bytes = 0;
+    uint8_t* d_in = nullptr;
+    dint_segment* d_segs = nullptr;
+    uint64_t* d_list_offsets = nullptr;
+    uint32_t* d_out = nullptr;
+    uint64_t* d_sums = nullptr;
+};
+
+int dint_vroom_ctx_create(const dint_dict* d, const dint_vroom_plan* plan, uint32_t block_size, dint_vroom_ctx** out) {
+    if (!d || !plan || !out) return DINT_E_ARG;
+    if (!d->d_rows) {
+        dint::set_error("dictionary is not device resident (no CPU fallback)");
+        return DINT_E_NODEVICE;
+    }
+    device_guard g(d->device);
+    dint_vroom_ctx* c = new (std::nothrow) dint_vroom_ctx;
+    if (!c) return DINT_E_NOMEM;
+    c->dict = d;
+    c->block_size = block_size ? block_size : dint::kDefaultBlock;
+    c->n_lists = plan->list_offsets.size() - 1;
+    c->n_ints = plan->n_ints;
+    c->n_segs = plan->segments.size();
+    c->in_bytes = plan->list_byte_offsets.back();
+    auto fail = [&](cudaError_t e) {
+        dint::set_error(std::string("dint_vroom_ctx_create: ") + cudaGetErrorString(e));
+        dint_vroom_ctx_destroy(c);
+        return DINT_E_CUDA;
+    };
+    cudaError_t e;
+    if ((e = cudaMalloc(&c->d_in, c->in_bytes + 16)) != cudaSuccess) return fail(e);
+    if ((e = cudaMalloc(&c->d_segs, (c->n_segs + 1) * sizeof(dint_segment))) != cudaSuccess) return fail(e);
+    if ((e = cudaMalloc(&c->d_list_offsets, (c->n_lists + 1) * 8)) != cudaSuccess) return fail(e);
+    if ((e = cudaMalloc(&c->d_out, (c->n_ints + 1) * 4)) != cudaSuccess) return fail(e);
+    if ((e = cudaMalloc(&c->d_sums, (c->n_lists + 1) * 8)) != cudaSuccess) return fail(e);
+    if ((e = cudaMemcpy(c->d_segs, plan->segments.data(), c->n_segs * sizeof(dint_segment), cudaMemcpyHostToDevice)) !=
+        cudaSuccess)
+        return fail(e);
+    if ((e = cudaMemcpy(c->d_list_offsets, plan->list_offsets.data(), (c->n_lists + 1) * 8, cudaMemcpyHostToDevice)) !=
+        cudaSuccess)
+        return fail(e);
+    *out = c;
+    return DINT_OK;
+}
+
+void dint_vroom_ctx_destroy(dint_vroom_ctx* c) {
+    if (!c) return;
+    device_guard g(c->dict->device);
+    cudaFree(c->d_in);
+    cudaFree(c->d_segs);
+    cudaFree(c->d_list_offsets);
+    cudaFree(c->d_out);
+    cudaFree(c->d_sums);
+    delete c;
+}
+
+uint32_t* dint_vroom_ctx_device_output(const dint_vroom_ctx* c) { return c ? c->d_out : nullptr; }
+
+int dint_vroom_decode_host(dint_vroom_ctx* c, const void* h_bin, size_t len, int mode, uint32_t* h_out,
+                           uint64_t* h_sums, void* stream) {
+    if (!c || (!h_bin && len)) return DINT_E_ARG;
+    if (len != c->in_bytes) {
+        dint::set_error("dint_vroom_decode_host: .bin size differs from the plan's");
+        return DINT_E_ARG;
+    }
+    device_guard g(c->dict->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (len) CUDA_TRY(cudaMemcpyAsync(c->d_in, h_bin, len, cudaMemcpyHostToDevice, st));
+    int rc = dint_decode_segments(c->dict, c->d_in, len, c->d_segs, c->n_segs, c->block_size, c->d_out, mode, stream);
+    if (rc) return rc;
+    if (h_sums && c->n_lists) {
+        rc = dint_checksum_lists(c->d_out, c->d_list_offsets, c->n_lists, c->d_sums, stream);
+        if (rc) return rc;
+        CUDA_TRY(cudaMemcpyAsync(h_sums, c->d_sums, c->n_lists * 8, cudaMemcpyDeviceToHost, st));
+    }
+    if (h_out && c->n_ints) CUDA_TRY(cudaMemcpyAsync(h_out, c->d_out, c->n_ints * 4, cudaMemcpyDeviceToHost, st));
     return DINT_OK;
 }
 

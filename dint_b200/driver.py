@@ -26,7 +26,12 @@ def _require_cuda(device):
 
 
 def _to_device_bytes(data, dev, pinned=False):
-    t = torch.frombuffer(bytearray(data), dtype=torch.uint8) if not isinstance(data, torch.Tensor) else data
+    if isinstance(data, torch.Tensor):
+        t = data
+    elif len(data) == 0:
+        t = torch.empty(0, dtype=torch.uint8)
+    else:
+        t = torch.frombuffer(bytearray(data), dtype=torch.uint8)
     if pinned:
         t = t.pin_memory()
     return t.to(dev, non_blocking=pinned)

@@ -28,6 +28,8 @@
  *                            include/dint/dint_codecs.hpp:13-49, 269-274, 460-510
  *                            include/ds2i/block_codecs.hpp:130-150
  *   dint_decode_list_host  one Decoder::decode(dict, in, out, universe, n) call, host buffers
+ *   dint_vroom_ctx_* /     the whole decode_dint() loop of vroom_env/decode.cpp:139-150 on HOST
+ *   dint_vroom_decode_host   buffers: H2D of the .bin, batch decode, D2H of the result
  *   dint_checksum_lists    (new) per-list 64-bit checksums used for large-scale parity
  *
  * Ownership: the caller owns every device buffer; nothing is allocated on the decode
@@ -97,6 +99,7 @@ typedef struct dint_block {
 typedef struct dint_dict dint_dict;
 typedef struct dint_vroom_plan dint_vroom_plan;
 typedef struct dint_index_plan dint_index_plan;
+typedef struct dint_vroom_ctx dint_vroom_ctx;
 
 const char* dint_last_error(void);
 int dint_abi_version(void);
@@ -172,6 +175,21 @@ int dint_checksum_lists(const uint32_t* d_values, const uint64_t* d_list_offsets
  * the reference's returned pointer minus `in`. out receives exactly n integers (RAW). */
 int dint_decode_list_host(const dint_dict* d, const uint8_t* in, size_t in_avail, uint32_t* out, uint32_t n,
                           uint32_t block_size, size_t* consumed);
+
+/* ---- host-buffer batch decode of a whole vroom .bin --------------------------------------- */
+/* A ctx owns the device workspace for files that share `plan`'s layout (device copy of the
+ * segment table and list offsets, input / output / checksum buffers): create once, reuse for
+ * every call, so the call itself allocates nothing. */
+int dint_vroom_ctx_create(const dint_dict* d, const dint_vroom_plan* plan, uint32_t block_size, dint_vroom_ctx** out);
+void dint_vroom_ctx_destroy(dint_vroom_ctx* c);
+/* device pointer of the ctx's packed output (num_ints values, valid after a decode) */
+uint32_t* dint_vroom_ctx_device_output(const dint_vroom_ctx* c);
+/* h_bin: HOST pointer to the .bin image the plan was made from (pinned memory makes the
+ * copies asynchronous). Enqueues on `stream`: H2D of the bytes, the decode kernel in `mode`,
+ * then (h_sums != NULL) per-list checksums + D2H of num_lists uint64, and (h_out != NULL) D2H
+ * of all num_ints decoded integers. Returns without synchronising the stream. */
+int dint_vroom_decode_host(dint_vroom_ctx* c, const void* h_bin, size_t len, int mode, uint32_t* h_out,
+                           uint64_t* h_sums, void* stream);
 
 #ifdef __cplusplus
 }

@@ -129,8 +129,17 @@ long ref_vroom_decode_file(void* h, const uint8_t* bin, size_t len, uint32_t* ou
 // output buffer that is never re-zeroed, per-list chrono deltas summed. Decodes
 // the lists whose headers start in [bin, bin+len) `repeat` times. Returns the
 // summed seconds; *ints receives the number of integers decoded in one pass.
-double ref_vroom_time_file(void* h, const uint8_t* bin, size_t len, int repeat, uint64_t* ints) {
-    std::vector<uint32_t> decoded(constants::max_size, 0);
+//
+// scratch: optional caller-owned output buffer of >= constants::max_size (50 M) zeroed ints,
+// so that repeated calls do not pay the 200 MB allocation the reference pays once per process
+// (vroom_env/decode.cpp:128-129).
+double ref_vroom_time_file(void* h, const uint8_t* bin, size_t len, int repeat, uint64_t* ints, uint32_t* scratch) {
+    std::vector<uint32_t> own;
+    if (!scratch) {
+        own.assign(constants::max_size, 0);
+        scratch = own.data();
+    }
+    struct { uint32_t* p; uint32_t* data() { return p; } } decoded{scratch};
     double tot = 0;
     uint64_t cnt = 0;
     for (int r = 0; r < repeat; ++r) {

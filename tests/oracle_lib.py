@@ -160,7 +160,7 @@ class Reference:
         L.ref_vroom_decode_file.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
                                             C.POINTER(C.c_uint64)]
         L.ref_vroom_time_file.restype = C.c_double
-        L.ref_vroom_time_file.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_uint64)]
+        L.ref_vroom_time_file.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_uint64), C.c_void_p]
         assert L.ref_block_size() == block_size
 
     def dict_load(self, kind, path):
@@ -190,5 +190,5 @@ class Reference:
 
     def vroom_time(self, h, a, repeat=1):
         tot = C.c_uint64(0)
-        secs = self.lib.ref_vroom_time_file(h, _ptr(a), len(a), repeat, C.byref(tot))
+        secs = self.lib.ref_vroom_time_file(h, _ptr(a), len(a), repeat, C.byref(tot), None)
         return secs, tot.value
