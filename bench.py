@@ -261,12 +261,17 @@ class ReplicatedStream:
         self.n_segs = int(self.plan.n_segments)
         base = torch.frombuffer(bytearray(bin_bytes), dtype=torch.uint8).to(dev)
         self.d_in = base.repeat(replicas)
-        segs = torch.from_numpy(self.plan.segments.view(np.int64).reshape(-1, 3).copy()).to(dev)
-        shift = torch.zeros(replicas, 1, 3, dtype=torch.int64, device=dev)
+        segs = torch.from_numpy(self.plan.segments.view(np.int64).reshape(-1, 4).copy()).to(dev)
+        shift = torch.zeros(replicas, 1, 4, dtype=torch.int64, device=dev)
         r = torch.arange(replicas, dtype=torch.int64, device=dev)
         shift[:, 0, 0] = r * self.in_bytes
         shift[:, 0, 1] = r * self.n_ints
-        self.d_segs = (segs[None, :, :] + shift).reshape(-1, 3).contiguous()
+        self.d_segs = (segs[None, :, :] + shift).reshape(-1, 4).contiguous()
+        self.n_units = int(self.plan.n_units)
+        uf = torch.from_numpy(self.plan.unit_first.astype(np.int64)).to(dev)
+        self.d_unit_first = torch.cat([(uf[:-1][None, :] + (r * self.n_segs)[:, None]).reshape(-1),
+                                       torch.tensor([replicas * self.n_segs], dtype=torch.int64, device=dev)]
+                                      ).to(torch.int32)
         lo = torch.from_numpy(self.plan.list_offsets.astype(np.int64)).to(dev)
         self.d_list_offsets = torch.cat([(lo[:-1][None, :] + (r * self.n_ints)[:, None]).reshape(-1),
                                          torch.tensor([replicas * self.n_ints], dtype=torch.int64, device=dev)])
@@ -274,8 +279,9 @@ class ReplicatedStream:
         self.algo_bytes = replicas * (self.in_bytes + 4 * self.n_ints)
 
     def launch(self, mode, stream):
-        self.capi.decode_segments(self.dict, self.d_in.data_ptr(), self.R * self.in_bytes, self.d_segs.data_ptr(),
-                                  self.R * self.n_segs, self.out.data_ptr(), mode, stream=stream)
+        self.capi.decode_units(self.dict, self.d_in.data_ptr(), self.R * self.in_bytes, self.d_segs.data_ptr(),
+                               self.R * self.n_segs, self.d_unit_first.data_ptr(), self.R * self.n_units,
+                               self.out.data_ptr(), mode, stream=stream)
 
 
 def run_gpu(args):

@@ -17,10 +17,11 @@ E_NODEVICE = -5
 
 KIND_OF_TYPE = {"single_rect_dint": DICT_RECT, "single_packed_dint": DICT_PACKED, "multi_packed_dint": DICT_MULTI}
 
-SEGMENT_DTYPE = np.dtype([("in_off", "<u8"), ("out_off", "<u8"), ("n", "<u4"), ("doc_base", "<u4")])
+SEGMENT_DTYPE = np.dtype([("in_off", "<u8"), ("out_off", "<u8"), ("n", "<u4"), ("doc_base", "<u4"),
+                          ("in_len", "<u4"), ("doc_sum", "<u4")])
 BLOCK_DTYPE = np.dtype([("in_off", "<u8"), ("out_off", "<u8"), ("size", "<u4"), ("cur_base", "<u4"),
                         ("block_max", "<u4"), ("reserved", "<u4")])
-assert SEGMENT_DTYPE.itemsize == 24 and BLOCK_DTYPE.itemsize == 32
+assert SEGMENT_DTYPE.itemsize == 32 and BLOCK_DTYPE.itemsize == 32
 
 # every symbol include/dint_b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
@@ -28,12 +29,12 @@ SYMBOLS = [
     "dint_dict_create", "dint_dict_create_mapped", "dint_dict_destroy", "dint_dict_kind", "dint_dict_num_rows",
     "dint_dict_device_bytes", "dint_dict_copy",
     "dint_vroom_plan_create", "dint_vroom_plan_destroy", "dint_vroom_plan_num_lists", "dint_vroom_plan_num_ints",
-    "dint_vroom_plan_num_segments", "dint_vroom_plan_segments", "dint_vroom_plan_list_offsets",
-    "dint_vroom_plan_list_byte_offsets",
+    "dint_vroom_plan_num_segments", "dint_vroom_plan_segments", "dint_vroom_plan_num_units",
+    "dint_vroom_plan_unit_first", "dint_vroom_plan_list_offsets", "dint_vroom_plan_list_byte_offsets",
     "dint_index_plan_create", "dint_index_plan_destroy", "dint_index_plan_num_lists", "dint_index_plan_num_docs",
     "dint_index_plan_num_postings", "dint_index_plan_num_blocks", "dint_index_plan_blocks",
     "dint_index_plan_list_offsets", "dint_index_plan_endpoints", "dint_index_plan_layout",
-    "dint_decode_segments", "dint_decode_index", "dint_checksum_lists", "dint_decode_list_host",
+    "dint_decode_segments", "dint_decode_units", "dint_decode_index", "dint_checksum_lists", "dint_decode_list_host",
     "dint_vroom_ctx_create", "dint_vroom_ctx_destroy", "dint_vroom_ctx_device_output", "dint_vroom_decode_host",
 ]
 
@@ -69,10 +70,10 @@ def lib():
         L.dint_vroom_plan_create.argtypes = [vp, vp, sz, u32, u32, C.POINTER(vp)]
         L.dint_vroom_plan_destroy.argtypes = [vp]
         L.dint_vroom_plan_destroy.restype = None
-        for f in ("num_lists", "num_ints", "num_segments"):
+        for f in ("num_lists", "num_ints", "num_segments", "num_units"):
             getattr(L, "dint_vroom_plan_" + f).argtypes = [vp]
             getattr(L, "dint_vroom_plan_" + f).restype = u64
-        for f in ("segments", "list_offsets", "list_byte_offsets"):
+        for f in ("segments", "unit_first", "list_offsets", "list_byte_offsets"):
             getattr(L, "dint_vroom_plan_" + f).argtypes = [vp]
             getattr(L, "dint_vroom_plan_" + f).restype = vp
         L.dint_index_plan_create.argtypes = [i32, vp, sz, u32, C.POINTER(vp)]
@@ -86,6 +87,7 @@ def lib():
             getattr(L, "dint_index_plan_" + f).restype = vp
         L.dint_index_plan_layout.argtypes = [vp] + [C.POINTER(u64)] * 5
         L.dint_decode_segments.argtypes = [vp, vp, sz, vp, sz, u32, vp, i32, vp]
+        L.dint_decode_units.argtypes = [vp, vp, sz, vp, sz, vp, sz, vp, i32, vp]
         L.dint_decode_index.argtypes = [vp, vp, vp, sz, vp, sz, u32, vp, vp, vp]
         L.dint_checksum_lists.argtypes = [vp, vp, sz, vp, vp]
         L.dint_decode_list_host.argtypes = [vp, vp, sz, vp, u32, u32, C.POINTER(sz)]
@@ -177,6 +179,8 @@ class VroomPlan:
         self.n_ints = L.dint_vroom_plan_num_ints(h)
         self.n_segments = L.dint_vroom_plan_num_segments(h)
         self.segments = _view(L.dint_vroom_plan_segments(h), self.n_segments, SEGMENT_DTYPE)
+        self.n_units = L.dint_vroom_plan_num_units(h)
+        self.unit_first = _view(L.dint_vroom_plan_unit_first(h), self.n_units + 1, np.uint32)
         self.list_offsets = _view(L.dint_vroom_plan_list_offsets(h), self.n_lists + 1, np.uint64)
         self.list_byte_offsets = _view(L.dint_vroom_plan_list_byte_offsets(h), self.n_lists + 1, np.uint64)
         self.block_size = block_size
@@ -251,6 +255,11 @@ class IndexPlan:
 def decode_segments(dictionary, d_in_ptr, in_bytes, d_segs_ptr, n_segs, d_out_ptr, mode, stream=0, block_size=256):
     check(lib().dint_decode_segments(dictionary.handle, d_in_ptr, in_bytes, d_segs_ptr, n_segs, block_size, d_out_ptr,
                                      mode, stream))
+
+
+def decode_units(dictionary, d_in_ptr, in_bytes, d_segs_ptr, n_segs, d_unit_first_ptr, n_units, d_out_ptr, mode, stream=0):
+    check(lib().dint_decode_units(dictionary.handle, d_in_ptr, in_bytes, d_segs_ptr, n_segs, d_unit_first_ptr, n_units,
+                                  d_out_ptr, mode, stream))
 
 
 def decode_index(docs_dict, freqs_dict, d_lists_ptr, lists_bytes, d_blocks_ptr, n_blocks, block_size, d_docids_ptr,

@@ -341,7 +341,8 @@ int dint_vroom_plan_create(const dint_dict* d, const void* bin_, size_t len, uin
             uint32_t seg_base = 0;
             auto cut = [&](const uint8_t* q, uint64_t i, uint32_t a) {
                 if (i - seg_i >= chunk_ints && i < n) {
-                    plan->segments.push_back({uint64_t(seg_p - bin), out_off + seg_i, uint32_t(i - seg_i), seg_base});
+                    plan->segments.push_back({uint64_t(seg_p - bin), out_off + seg_i, uint32_t(i - seg_i), seg_base,
+                                              uint32_t(q - seg_p), a - seg_base});
                     seg_p = q;
                     seg_i = i;
                     seg_base = a;
@@ -352,7 +353,9 @@ int dint_vroom_plan_create(const dint_dict* d, const void* bin_, size_t len, uin
                 set_error("vroom .bin: codeword stream does not tile the list");
                 return DINT_E_FORMAT;
             }
-            if (n > seg_i) plan->segments.push_back({uint64_t(seg_p - bin), out_off + seg_i, uint32_t(n - seg_i), seg_base});
+            if (n > seg_i)
+                plan->segments.push_back({uint64_t(seg_p - bin), out_off + seg_i, uint32_t(n - seg_i), seg_base,
+                                          uint32_t(p - seg_p), acc - seg_base});
         } else {
             // multi_opt_dint::decode (vroom_env/dint_codecs.hpp:521-619): ceil(n / block_size) blocks,
             // each = selector byte + u16 stream (selector < 6) or u8 stream (selector - 6)
@@ -368,13 +371,14 @@ int dint_vroom_plan_create(const dint_dict* d, const void* bin_, size_t len, uin
                     set_error("vroom .bin: bad selector byte");
                     return DINT_E_FORMAT;
                 }
-                plan->segments.push_back({uint64_t(p - bin), out_off + done, size, acc});
+                const uint32_t acc0 = acc;
                 const uint8_t* q = sel < kSelectors ? wk.walk16(p + 1, sel, size, acc, [](const uint8_t*, uint64_t, uint32_t) {})
                                                     : wk.walk8(p + 1, sel - kSelectors, size, acc);
                 if (!q) {
                     set_error("vroom .bin: codeword stream does not tile the block");
                     return DINT_E_FORMAT;
                 }
+                plan->segments.push_back({uint64_t(p - bin), out_off + done, size, acc0, uint32_t(q - p), acc - acc0});
                 p = q;
                 done += size;
             }
@@ -384,6 +388,21 @@ int dint_vroom_plan_create(const dint_dict* d, const void* bin_, size_t len, uin
     }
     plan->list_byte_offsets.push_back(len);
     plan->n_ints = out_off;
+    if (plan->segments.size() > 0xFFFFFFF0ull) {
+        set_error("vroom .bin: more than 2^32 segments");
+        return DINT_E_ARG;
+    }
+    // work units: runs of consecutive segments (contiguous input and output) of ~kUnitInts integers
+    plan->unit_first.push_back(0);
+    uint64_t unit_ints = 0;
+    for (size_t i = 0; i < plan->segments.size(); ++i) {
+        unit_ints += plan->segments[i].n;
+        if (unit_ints >= kUnitInts || i + 1 - plan->unit_first.back() >= kUnitSegments) {
+            plan->unit_first.push_back(uint32_t(i + 1));
+            unit_ints = 0;
+        }
+    }
+    if (plan->unit_first.back() != plan->segments.size()) plan->unit_first.push_back(uint32_t(plan->segments.size()));
     *out = plan.release();
     return DINT_OK;
 }
@@ -393,6 +412,8 @@ uint64_t dint_vroom_plan_num_lists(const dint_vroom_plan* p) { return p ? p->lis
 uint64_t dint_vroom_plan_num_ints(const dint_vroom_plan* p) { return p ? p->n_ints : 0; }
 uint64_t dint_vroom_plan_num_segments(const dint_vroom_plan* p) { return p ? p->segments.size() : 0; }
 const dint_segment* dint_vroom_plan_segments(const dint_vroom_plan* p) { return p ? p->segments.data() : nullptr; }
+uint64_t dint_vroom_plan_num_units(const dint_vroom_plan* p) { return p ? p->unit_first.size() - 1 : 0; }
+const uint32_t* dint_vroom_plan_unit_first(const dint_vroom_plan* p) { return p ? p->unit_first.data() : nullptr; }
 const uint64_t* dint_vroom_plan_list_offsets(const dint_vroom_plan* p) { return p ? p->list_offsets.data() : nullptr; }
 const uint64_t* dint_vroom_plan_list_byte_offsets(const dint_vroom_plan* p) {
     return p ? p->list_byte_offsets.data() : nullptr;

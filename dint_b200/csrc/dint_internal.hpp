@@ -18,6 +18,8 @@ constexpr uint32_t kSelectors = 6;     // constants::num_selectors  (dint_config
 constexpr uint32_t kReserved = 7;      // EXCEPTIONS + 5 run codewords (single_dictionary.hpp:22)
 constexpr uint32_t kDefaultBlock = 256;  // constants::block_size    (include/util.hpp:35)
 constexpr uint32_t kDefaultChunk = 1024;
+constexpr uint32_t kUnitInts = 2048;     // a work unit closes once it holds this many integers ...
+constexpr uint32_t kUnitSegments = 256;  // ... or this many segments
 
 void set_error(const std::string& msg);
 
@@ -30,7 +32,7 @@ inline uint64_t rd64(const uint8_t* p) { uint64_t v; std::memcpy(&v, p, 8); retu
 // Device-side view of a dictionary, passed by value to kernels.
 struct dint_dict_view {
     const uint32_t* rows;   // [n_rows] x 16 words, 64-byte aligned rows: entry payload, zero padded
-    const uint8_t* lens;    // [n_rows] entry length - 1
+    const uint8_t* lens;    // 4-bit log2(entry length) per row, two rows per byte
     uint32_t class_base[8]; // first row of each class (single kinds: one class at 0)
     uint32_t n_rows;
     uint32_t n_classes;
@@ -62,6 +64,7 @@ struct dint_dict {
 struct dint_vroom_plan {
     uint64_t n_ints = 0;
     std::vector<dint_segment> segments;
+    std::vector<uint32_t> unit_first;         // n_units + 1
     std::vector<uint64_t> list_offsets;       // n_lists + 1
     std::vector<uint64_t> list_byte_offsets;  // n_lists + 1
 };

@@ -1,23 +1,9 @@
 // dint_b200 — sm_100a kernels and the device half of the C ABI.
 //
-// Work unit: a "segment" = contiguous codeword stream starting on a codeword boundary
-// and producing exactly n integers (include/dint_b200.h). One warp decodes one segment,
-// 32 codeword symbols (u16 or u8) per step:
-//
-//   1. lanes load one symbol each (coalesced; byte-wise when the stream is odd-aligned);
-//   2. __ballot_sync masks of the symbols equal to 0 / 1 resolve which symbols are
-//      codewords and which are exception payload (a 0 is followed by 1 payload symbol,
-//      a 1 by 2; payload may itself be 0/1, so the masks are walked in stream order —
-//      a warp-uniform loop with one trip per 0/1 symbol, i.e. ~0.25 % of symbols);
-//   3. entry lengths come from the (len-1) byte table staged in shared memory;
-//   4. a __shfl_up_sync inclusive scan turns lengths into output offsets; codewords past
-//      the segment's n-th integer (bytes of the next list) are dropped;
-//   5. the output is produced 32 integers at a time in OUTPUT order: a __reduce_or_sync
-//      "head flag" mask + popc tells every lane which codeword covers its position, the
-//      value is one 4-byte load from the 64-byte-aligned dictionary row (L1/L2 resident),
-//      runs produce zeros without touching memory, exceptions carry their value;
-//   6. DOCIDS mode fuses the d-gap prefix sum (second warp scan + running carry), FREQS
-//      mode the +1 shift; stores are fully coalesced 128-byte lines.
+// The stream decoder itself (tiles, staging ring, fused flush) is in dint_decoder.cuh; this
+// file holds the kernels that drive it (work units of a vroom .bin, blocks of a frozen
+// dict_freq_index), the interpolative tail-block kernel, the checksum kernel, and the
+// extern "C" entry points.
 //
 // Reference semantics reproduced (paths relative to the reference root):
 //   vroom_env/dint_codecs.hpp:37-107 (u16 loop), :574-609 (u8 loop), :521-536 (selector),
@@ -31,16 +17,16 @@
 #include <mutex>
 #include <string>
 
+#include "dint_decoder.cuh"
 #include "dint_internal.hpp"
 
 namespace {
 
-constexpr unsigned FULL = 0xffffffffu;
+using namespace dintk;
+
 constexpr int kWarpsPerCta = 16;
 constexpr int kThreads = kWarpsPerCta * 32;
-
-enum { KIND_DICT = 0, KIND_RUN = 1, KIND_EXC = 2 };
-enum { OUT_RAW = 0, OUT_DOCIDS = 1, OUT_FREQS = 2, OUT_SKIP = 3 };
+constexpr uint32_t kImplicitUnit = 8;  // segments per work unit when the caller passes no unit table
 
 std::atomic<uint64_t> g_launches{0};
 
@@ -53,216 +39,96 @@ std::atomic<uint64_t> g_launches{0};
         }                                                                                 \
     } while (0)
 
-__device__ __forceinline__ unsigned lane_id() {
-    unsigned l;
-    asm("mov.u32 %0, %%laneid;" : "=r"(l));
-    return l;
-}
-__device__ __forceinline__ unsigned lanemask_lt() {
-    unsigned m;
-    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
-    return m;
-}
-__device__ __forceinline__ unsigned lanemask_le() {
-    unsigned m;
-    asm("mov.u32 %0, %%lanemask_le;" : "=r"(m));
-    return m;
-}
-
-// streaming loads of the compressed bytes: read once, do not pollute L1
-__device__ __forceinline__ uint32_t ldg_u8(const uint8_t* p) {
-    uint32_t v;
-    asm volatile("ld.global.nc.L1::no_allocate.u8 %0, [%1];" : "=r"(v) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ uint32_t ldg_u16(const uint8_t* p) {
-    uint16_t v;
-    asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(v) : "l"(p));
-    return v;
-}
-
-// symbol `lane` of the 32-symbol tile that starts at byte `pos`
-template <int SYM>
-__device__ __forceinline__ uint32_t load_symbol(const uint8_t* __restrict__ in, uint64_t in_bytes, uint64_t pos,
-                                                unsigned lane) {
-    uint64_t a = pos + uint64_t(SYM) * lane;
-    if (SYM == 1) return a < in_bytes ? ldg_u8(in + a) : 0u;
-    if (a + 2 > in_bytes) return 0u;
-    if (((reinterpret_cast<uintptr_t>(in) + pos) & 1) == 0) return ldg_u16(in + a);  // warp-uniform
-    return ldg_u8(in + a) | (ldg_u8(in + a + 1) << 8);
-}
-
-// symbol (lane + d) of the concatenation cur | nxt, 1 <= d <= 4
-__device__ __forceinline__ uint32_t peek(uint32_t cur, uint32_t nxt, unsigned lane, unsigned d) {
-    uint32_t a = __shfl_sync(FULL, cur, (lane + d) & 31);
-    uint32_t b = __shfl_sync(FULL, nxt, (lane + d) & 31);
-    return (lane + d < 32) ? a : b;
-}
-
-__device__ __forceinline__ uint32_t warp_inclusive_scan(uint32_t v, unsigned lane) {
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        uint32_t t = __shfl_up_sync(FULL, v, o);
-        if (lane >= unsigned(o)) v += t;
-    }
-    return v;
-}
-
-// Decodes one segment with the calling warp. Returns the byte offset one past the last
-// consumed symbol (the reference's returned pointer). SYM = bytes per codeword symbol.
-//   lut       shared-memory (len-1) table of the segment's class
-//   row_base  first dictionary row of the class, class_rows its number of rows
-//   out       first output integer of the segment (ignored for OUT_SKIP)
-template <int SYM, int MODE>
-__device__ __forceinline__ uint64_t decode_stream(const uint32_t* __restrict__ rows, const uint8_t* __restrict__ lut,
-                                                  uint32_t row_base, uint32_t class_rows,
-                                                  const uint8_t* __restrict__ in, uint64_t in_bytes, uint64_t pos,
-                                                  uint32_t n, uint32_t* __restrict__ out, uint32_t doc_base,
-                                                  uint2* __restrict__ cwbuf, unsigned lane) {
-    constexpr int PZ = SYM == 2 ? 1 : 2;  // payload symbols after a 0 codeword (u16 value)
-    constexpr int PO = SYM == 2 ? 2 : 4;  // payload symbols after a 1 codeword (u32 value)
-    uint32_t remaining = n;
-    uint32_t produced = 0;
-    uint32_t acc = doc_base - 1u;  // docid[i] = acc + sum_{j<=i} (v_j + 1)
-    uint32_t carry = 0;            // payload symbols spilling in from the previous tile (low bits)
-    uint64_t tile_pos = pos;
-    uint64_t end_off = pos;
-    uint32_t cur = load_symbol<SYM>(in, in_bytes, tile_pos, lane);
-    while (remaining) {
-        uint32_t nxt = load_symbol<SYM>(in, in_bytes, tile_pos + 32 * SYM, lane);  // prefetch
-
-        // -- which symbols are codewords ---------------------------------------------------
-        const unsigned Z = __ballot_sync(FULL, cur == 0u);
-        const unsigned O = __ballot_sync(FULL, cur == 1u);
-        uint64_t P = carry;
-        uint32_t excval = 0;
-        if (Z | O) {
-            unsigned m = Z | O;
-            while (m) {
-                int j = __ffs(m) - 1;
-                m &= m - 1;
-                if (!((P >> j) & 1ull)) {
-                    int cnt = ((Z >> j) & 1u) ? PZ : PO;
-                    P |= ((1ull << cnt) - 1ull) << (j + 1);
-                }
-            }
-            uint32_t n1 = peek(cur, nxt, lane, 1), n2 = peek(cur, nxt, lane, 2);
-            if (SYM == 2) {
-                excval = (cur == 0u) ? n1 : (n1 | (n2 << 16));
-            } else {
-                uint32_t n3 = peek(cur, nxt, lane, 3), n4 = peek(cur, nxt, lane, 4);
-                excval = (cur == 0u) ? (n1 | (n2 << 8)) : (n1 | (n2 << 8) | (n3 << 16) | (n4 << 24));
-            }
-        }
-        carry = uint32_t(P >> 32);
-        const bool iscw = !((uint32_t(P) >> lane) & 1u);
-
-        // -- lengths and offsets -----------------------------------------------------------
-        uint32_t len = 0, kind = KIND_EXC, data = excval;
-        if (iscw) {
-            if (cur >= 2u) {
-                uint32_t idx = min(cur, class_rows - 1u);
-                len = uint32_t(lut[idx]) + 1u;
-                data = row_base + idx;
-                kind = cur < dint::kReserved ? KIND_RUN : KIND_DICT;
-            } else {
-                len = 1;
-            }
-        }
-        const uint32_t e = warp_inclusive_scan(len, lane);
-        const uint32_t s = e - len;
-        const bool valid = iscw && (s < remaining);
-        const unsigned V = __ballot_sync(FULL, valid);
-        const uint32_t T = min(__shfl_sync(FULL, e, 31), remaining);
-
-        if (MODE != OUT_SKIP) {
-            if (valid) cwbuf[__popc(V & lanemask_lt())] = make_uint2(data, s | (kind << 16));
-            __syncwarp();
-            // -- expansion, 32 outputs per round, in output order ---------------------------
-            uint32_t kbase = 0;
-            for (uint32_t w0 = 0; w0 < T; w0 += 32) {
-                const uint32_t rel = s - w0;
-                const unsigned heads = __reduce_or_sync(FULL, (valid && rel < 32u) ? (1u << rel) : 0u);
-                const uint32_t p = w0 + lane;
-                const uint32_t k = kbase + __popc(heads & lanemask_le()) - 1u;
-                kbase += __popc(heads);
-                uint32_t v = 0;
-                const bool act = p < T;
-                if (act) {
-                    const uint2 info = cwbuf[k];
-                    const uint32_t kd = info.y >> 16;
-                    if (kd == KIND_DICT) v = __ldg(rows + (size_t(info.x) * dint::kEntry + (p - (info.y & 0xffffu))));
-                    else if (kd == KIND_EXC) v = info.x;
-                }
-                if (MODE == OUT_DOCIDS) {
-                    const uint32_t xs = warp_inclusive_scan(act ? v + 1u : 0u, lane);
-                    v = acc + xs;
-                    acc += __shfl_sync(FULL, xs, 31);
-                } else if (MODE == OUT_FREQS) {
-                    v += 1u;
-                }
-                if (act) out[produced + p] = v;
-            }
-            __syncwarp();
-        }
-        produced += T;
-        remaining -= T;
-        if (remaining == 0) {
-            // the last codeword of the segment and its payload are the last consumed symbols
-            const int kl = 31 - __clz(V);
-            const uint32_t lastsym = __shfl_sync(FULL, cur, kl);
-            const uint32_t extra = lastsym == 0u ? PZ : (lastsym == 1u ? PO : 0);
-            end_off = tile_pos + uint64_t(SYM) * (kl + 1 + extra);
-        }
-        tile_pos += 32 * SYM;
-        cur = nxt;
-    }
-    return end_off;
-}
-
-// single kinds: u16 stream at `pos`. multi: selector byte at `pos`, then u16 (sel < 6) or
-// u8 (sel - 6) stream into class sel % 6 (vroom_env/dint_codecs.hpp:536-575).
-template <int MODE>
-__device__ __forceinline__ uint64_t decode_segment(const dint_dict_view& dv, const uint8_t* __restrict__ lut,
-                                                   bool multi, const uint8_t* __restrict__ in, uint64_t in_bytes,
-                                                   uint64_t pos, uint32_t n, uint32_t* out, uint32_t doc_base,
-                                                   uint2* cwbuf, unsigned lane) {
-    const uint32_t* rows = dv.rows;
-    if (!multi) return decode_stream<2, MODE>(rows, lut, 0, dv.n_rows, in, in_bytes, pos, n, out, doc_base, cwbuf, lane);
-    uint32_t sel = pos < in_bytes ? ldg_u8(in + pos) : 0u;
-    const bool wide = sel < dint::kSelectors;
-    uint32_t cls = wide ? sel : sel - dint::kSelectors;
-    cls = min(cls, dv.n_classes - 1u);
-    const uint32_t base = dv.class_base[cls];
-    const uint32_t crows = (cls + 1 < dv.n_classes ? dv.class_base[cls + 1] : dv.n_rows) - base;
-    if (wide) return decode_stream<2, MODE>(rows, lut + base, base, crows, in, in_bytes, pos + 1, n, out, doc_base, cwbuf, lane);
-    return decode_stream<1, MODE>(rows, lut + base, base, min(crows, 256u), in, in_bytes, pos + 1, n, out, doc_base, cwbuf, lane);
-}
-
 extern __shared__ __align__(16) uint8_t g_smem[];
 
-// stage the (len-1) table into shared memory; returns the per-warp codeword buffer
-__device__ __forceinline__ uint2* stage_lut(const dint_dict_view& dv, uint32_t lut_bytes) {
+// Stages the 4-bit log2(length) table into shared memory and carves the calling warp's rings.
+__device__ __forceinline__ void cta_setup(const dint_dict_view& dv, uint32_t lut_bytes, const uint8_t* in,
+                                          uint64_t in_bytes, uint32_t* out, warp_state& ws) {
     const uint4* src = reinterpret_cast<const uint4*>(dv.lens);
     uint4* dst = reinterpret_cast<uint4*>(g_smem);
     for (uint32_t i = threadIdx.x; i < lut_bytes / 16; i += blockDim.x) dst[i] = __ldg(src + i);
+    uint8_t* mine = g_smem + lut_bytes + (threadIdx.x >> 5) * kWarpSmem;
+    ws.stage = reinterpret_cast<uint32_t*>(mine);
+    ws.inb = mine + kStageInts * 4;
+    for (uint32_t i = lane_id(); i < kStageInts / 4; i += 32) reinterpret_cast<uint4*>(ws.stage)[i] = make_uint4(0, 0, 0, 0);
+    ws.out = out;
+    ws.flushed = 0;
+    ws.staged = 0;
+    ws.acc = 0;
+    ws.win_end = 0;
+    ws.safe_end = 0;
+    const uint64_t a = reinterpret_cast<uint64_t>(in);
+    ws.in_lo = a & ~uint64_t(15);
+    ws.in_hi = (a + in_bytes + 15) & ~uint64_t(15);
+    ws.vec_ok = (reinterpret_cast<uint64_t>(out) & 15) == 0;
     __syncthreads();
-    return reinterpret_cast<uint2*>(g_smem + lut_bytes) + (threadIdx.x >> 5) * 32;
 }
 
+__device__ __forceinline__ uint64_t shfl64(uint64_t v, int src) {
+    const uint32_t lo = __shfl_sync(FULL, uint32_t(v), src), hi = __shfl_sync(FULL, uint32_t(v >> 32), src);
+    return (uint64_t(hi) << 32) | lo;
+}
+
+// vroom path: one warp per work unit (a run of consecutive segments with contiguous output).
 template <int MODE>
-__global__ void __launch_bounds__(kThreads)
-decode_segments_kernel(dint_dict_view dv, uint32_t lut_bytes, int multi, const uint8_t* __restrict__ in,
-                       uint64_t in_bytes, const dint_segment* __restrict__ segs, uint64_t n_segs,
-                       uint32_t* __restrict__ out) {
-    uint2* cwbuf = stage_lut(dv, lut_bytes);
+__global__ void __launch_bounds__(kThreads, 2)
+decode_units_kernel(dint_dict_view dv, uint32_t lut_bytes, int multi, const uint8_t* __restrict__ in, uint64_t in_bytes,
+                    const dint_segment* __restrict__ segs, uint64_t n_segs, const uint32_t* __restrict__ unit_first,
+                    uint64_t n_units, uint32_t* __restrict__ out) {
+    warp_state ws;
+    cta_setup(dv, lut_bytes, in, in_bytes, out, ws);
     const unsigned lane = lane_id();
+    const uint64_t in_base = reinterpret_cast<uint64_t>(in);
+    const uint64_t hard_hi = ws.in_hi;
     const uint64_t gwarp = uint64_t(blockIdx.x) * kWarpsPerCta + (threadIdx.x >> 5);
     const uint64_t nwarps = uint64_t(gridDim.x) * kWarpsPerCta;
-    for (uint64_t i = gwarp; i < n_segs; i += nwarps) {
-        const dint_segment sg = segs[i];
-        decode_segment<MODE>(dv, g_smem, multi != 0, in, in_bytes, sg.in_off, sg.n, out + sg.out_off, sg.doc_base, cwbuf,
-                             lane);
+    for (uint64_t u = gwarp; u < n_units; u += nwarps) {
+        uint64_t s0, s1;
+        if (unit_first) {
+            s0 = unit_first[u];
+            s1 = unit_first[u + 1];
+        } else {
+            s0 = u * kImplicitUnit;
+            s1 = min(n_segs, s0 + kImplicitUnit);
+        }
+        ws.staged = 0;
+        ws.in_hi = 0;
+        uint32_t tail = 0;  // docid of the last integer of the previous segment
+        for (uint64_t sb = s0; sb < s1; sb += 32) {
+            const uint32_t cnt = uint32_t(min(uint64_t(32), s1 - sb));
+            dint_segment sg = {0, 0, 0, 0, 0, 0};
+            if (lane < cnt) sg = segs[sb + lane];
+            // bytes this batch can touch: lets the input ring stop at the end of the unit
+            uint64_t endb = 0;
+            if (lane < cnt) endb = sg.in_len ? sg.in_off + sg.in_len + 8 : in_bytes;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) endb = max(endb, shfl64(endb, lane ^ o));
+            const uint64_t want_hi = min(hard_hi, (in_base + endb + 15) & ~uint64_t(15));
+            if (want_hi > ws.in_hi) {
+                ws.in_hi = want_hi;
+                ws.win_end = 0;  // chunks loaded under the smaller bound are incomplete
+            }
+            for (uint32_t k = 0; k < cnt; ++k) {
+                const uint64_t in_off = shfl64(sg.in_off, k), out_off = shfl64(sg.out_off, k);
+                const uint32_t n = __shfl_sync(FULL, sg.n, k), doc_base = __shfl_sync(FULL, sg.doc_base, k);
+                const uint32_t doc_sum = __shfl_sync(FULL, sg.doc_sum, k);
+                if (ws.staged && out_off != ws.flushed + ws.staged) {  // output not contiguous: start over
+                    ws.flush_all<MODE>(lane);
+                    __syncwarp();
+                }
+                uint32_t corr = 0;
+                if (!ws.staged) {
+                    ws.flushed = out_off;
+                    ws.acc = doc_base - 1u;  // docid[i] = acc + sum_{j<=i} (v_j + 1)
+                } else if (MODE == OUT_DOCIDS) {
+                    corr = doc_base - 1u - tail;  // re-base the running prefix sum at the list boundary
+                }
+                tail = doc_base - 1u + doc_sum;
+                decode_one<MODE>(ws, dv, g_smem, multi != 0, in_base + in_off, n, corr, lane);
+            }
+        }
+        ws.flush_all<MODE>(lane);
+        __syncwarp();
     }
 }
 
@@ -270,31 +136,40 @@ decode_segments_kernel(dint_dict_view dv, uint32_t lut_bytes, int multi, const u
 // The block's docs byte length (= where its freqs bytes start) is left in the first slot of
 // the block's freqs output for pass 2.
 template <int MODE>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 index_docs_kernel(dint_dict_view dv, uint32_t lut_bytes, int multi, const uint8_t* __restrict__ lists,
                   uint64_t lists_bytes, const dint_block* __restrict__ blocks, uint64_t n_blocks, uint32_t block_size,
                   uint32_t* __restrict__ docids, uint32_t* __restrict__ freqs) {
-    uint2* cwbuf = stage_lut(dv, lut_bytes);
+    warp_state ws;
+    cta_setup(dv, lut_bytes, lists, lists_bytes, docids, ws);
     const unsigned lane = lane_id();
+    const uint64_t base = reinterpret_cast<uint64_t>(lists);
     const uint64_t gwarp = uint64_t(blockIdx.x) * kWarpsPerCta + (threadIdx.x >> 5);
     const uint64_t nwarps = uint64_t(gridDim.x) * kWarpsPerCta;
     for (uint64_t i = gwarp; i < n_blocks; i += nwarps) {
         const dint_block b = blocks[i];
         if (b.size != block_size) continue;  // partial block: interpolative, index_tails_kernel
-        // docid[0] = buf[0] + cur_base (dict_posting_list.hpp:304)
-        uint64_t end = decode_segment<MODE>(dv, g_smem, multi != 0, lists, lists_bytes, b.in_off, b.size,
-                                            MODE == OUT_SKIP ? nullptr : docids + b.out_off, b.cur_base, cwbuf, lane);
-        if (freqs && lane == 0) freqs[b.out_off] = uint32_t(end - b.in_off);
+        ws.staged = 0;
+        ws.flushed = b.out_off;
+        ws.acc = b.cur_base - 1u;  // docid[0] = buf[0] + cur_base (dict_posting_list.hpp:304)
+        const uint64_t end = decode_one<MODE>(ws, dv, g_smem, multi != 0, base + b.in_off, b.size, 0, lane);
+        if (MODE != OUT_SKIP) {
+            ws.flush_all<MODE>(lane);
+            __syncwarp();
+        }
+        if (freqs && lane == 0) freqs[b.out_off] = uint32_t(end - base - b.in_off);
     }
 }
 
 // pass 2 (freqs): decode_freqs_block (dict_posting_list.hpp:311-318), freq() = buf[i] + 1 (:168)
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 index_freqs_kernel(dint_dict_view dv, uint32_t lut_bytes, int multi, const uint8_t* __restrict__ lists,
                    uint64_t lists_bytes, const dint_block* __restrict__ blocks, uint64_t n_blocks, uint32_t block_size,
                    uint32_t* __restrict__ freqs) {
-    uint2* cwbuf = stage_lut(dv, lut_bytes);
+    warp_state ws;
+    cta_setup(dv, lut_bytes, lists, lists_bytes, freqs, ws);
     const unsigned lane = lane_id();
+    const uint64_t base = reinterpret_cast<uint64_t>(lists);
     const uint64_t gwarp = uint64_t(blockIdx.x) * kWarpsPerCta + (threadIdx.x >> 5);
     const uint64_t nwarps = uint64_t(gridDim.x) * kWarpsPerCta;
     for (uint64_t i = gwarp; i < n_blocks; i += nwarps) {
@@ -302,8 +177,11 @@ index_freqs_kernel(dint_dict_view dv, uint32_t lut_bytes, int multi, const uint8
         if (b.size != block_size) continue;
         const uint32_t docs_len = freqs[b.out_off];
         __syncwarp();
-        decode_segment<OUT_FREQS>(dv, g_smem, multi != 0, lists, lists_bytes, b.in_off + docs_len, b.size,
-                                  freqs + b.out_off, 0, cwbuf, lane);
+        ws.staged = 0;
+        ws.flushed = b.out_off;
+        decode_one<OUT_FREQS>(ws, dv, g_smem, multi != 0, base + b.in_off + docs_len, b.size, 0, lane);
+        ws.flush_all<OUT_FREQS>(lane);
+        __syncwarp();
     }
 }
 
@@ -461,17 +339,20 @@ checksum_kernel(const uint32_t* __restrict__ values, const uint64_t* __restrict_
 __global__ void __launch_bounds__(32)
 decode_list_kernel(dint_dict_view dv, uint32_t lut_bytes, int multi, const uint8_t* __restrict__ in, uint64_t in_bytes,
                    uint32_t n, uint32_t block_size, uint32_t* __restrict__ out, uint64_t* __restrict__ consumed) {
-    uint2* cwbuf = stage_lut(dv, lut_bytes);
+    warp_state ws;
+    cta_setup(dv, lut_bytes, in, in_bytes, out, ws);
     const unsigned lane = lane_id();
-    uint64_t pos = 0;
+    const uint64_t base = reinterpret_cast<uint64_t>(in);
+    uint64_t addr = base;
+    ws.flushed = 0;
     if (!multi) {
-        pos = decode_segment<OUT_RAW>(dv, g_smem, false, in, in_bytes, 0, n, out, 0, cwbuf, lane);
+        addr = decode_one<OUT_RAW>(ws, dv, g_smem, false, addr, n, 0, lane);
     } else {
         for (uint32_t done = 0; done < n; done += block_size)  // vroom_env/dint_codecs.hpp:525-534
-            pos = decode_segment<OUT_RAW>(dv, g_smem, true, in, in_bytes, pos, min(block_size, n - done), out + done, 0,
-                                          cwbuf, lane);
+            addr = decode_one<OUT_RAW>(ws, dv, g_smem, true, addr, min(block_size, n - done), 0, lane);
     }
-    if (lane == 0) *consumed = pos;
+    ws.flush_all<OUT_RAW>(lane);
+    if (lane == 0) *consumed = addr - base;
 }
 
 // ---- launch helpers -------------------------------------------------------------------------
@@ -495,8 +376,9 @@ int get_device_info(int device, device_info* di) {
     return DINT_OK;
 }
 
-uint32_t lut_bytes_of(const dint_dict* d) { return (d->n_rows + 15u) & ~15u; }
-size_t smem_bytes_of(const dint_dict* d, int warps) { return size_t(lut_bytes_of(d)) + size_t(warps) * 32 * sizeof(uint2); }
+// 4-bit log2(length) per dictionary row, padded to 16 bytes
+uint32_t lut_bytes_of(const dint_dict* d) { return ((d->n_rows + 1u) / 2u + 15u) & ~15u; }
+size_t smem_bytes_of(const dint_dict* d, int warps) { return size_t(lut_bytes_of(d)) + size_t(warps) * kWarpSmem; }
 
 // persistent grid: as many CTAs as fit (shared memory bound), never more than the work needs
 template <typename K>
@@ -551,7 +433,14 @@ int dint_dict_upload(dint_dict* d) {
     CUDA_TRY(cudaMalloc(&d->d_lens, lens_bytes));
     CUDA_TRY(cudaMemset(d->d_lens, 0, lens_bytes));
     CUDA_TRY(cudaMemcpy(d->d_rows, d->h_rows.data(), rows_bytes, cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(d->d_lens, d->h_lens.data(), d->n_rows, cudaMemcpyHostToDevice));
+    // lengths are powers of two (1..256): 4 bits of log2 per row, two rows per byte
+    std::vector<uint8_t> lut(lens_bytes, 0);
+    for (uint32_t r = 0; r < d->n_rows; ++r) {
+        uint32_t len = uint32_t(d->h_lens[r]) + 1, code = 0;
+        while ((1u << code) < len) ++code;
+        lut[r >> 1] |= uint8_t(code << ((r & 1u) * 4u));
+    }
+    CUDA_TRY(cudaMemcpy(d->d_lens, lut.data(), lens_bytes, cudaMemcpyHostToDevice));
     return DINT_OK;
 }
 
@@ -580,21 +469,22 @@ int dint_dict_copy(const dint_dict* d, uint32_t cls, uint32_t i, uint32_t* out16
     device_guard g(d->device);
     uint8_t l = 0;
     CUDA_TRY(cudaMemcpy(out16, d->d_rows + size_t(r) * dint::kEntry, dint::kEntry * 4, cudaMemcpyDeviceToHost));
-    CUDA_TRY(cudaMemcpy(&l, d->d_lens + r, 1, cudaMemcpyDeviceToHost));
-    *len = uint32_t(l) + 1;
+    CUDA_TRY(cudaMemcpy(&l, d->d_lens + (r >> 1), 1, cudaMemcpyDeviceToHost));
+    *len = 1u << ((l >> ((r & 1u) * 4u)) & 15u);
     return DINT_OK;
 }
 
-int dint_decode_segments(const dint_dict* d, const uint8_t* d_in, size_t in_bytes, const dint_segment* d_segs,
-                         size_t n_segs, uint32_t block_size, uint32_t* d_out, int mode, void* stream) {
-    (void)block_size;
+int dint_decode_units(const dint_dict* d, const uint8_t* d_in, size_t in_bytes, const dint_segment* d_segs, size_t n_segs,
+                      const uint32_t* d_unit_first, size_t n_units, uint32_t* d_out, int mode, void* stream) {
     if (!d || mode < DINT_MODE_RAW || mode > DINT_MODE_FREQS) return DINT_E_ARG;
     if (!d->d_rows) {
         dint::set_error("dictionary is not device resident (no CPU fallback)");
         return DINT_E_NODEVICE;
     }
     if (n_segs == 0) return DINT_OK;
-    if (!d_in || !d_segs || !d_out) return DINT_E_ARG;
+    if (!d_in || !d_segs || !d_out || n_segs > 0xFFFFFFF0ull) return DINT_E_ARG;
+    if (!d_unit_first) n_units = (n_segs + kImplicitUnit - 1) / kImplicitUnit;
+    if (n_units == 0) return DINT_OK;
     device_guard g(d->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int multi = d->kind == DINT_DICT_MULTI;
@@ -602,10 +492,10 @@ int dint_decode_segments(const dint_dict* d, const uint8_t* d_in, size_t in_byte
     size_t smem = 0;
     int rc;
 #define LAUNCH_SEG(M)                                                                                              \
-    rc = plan_grid(decode_segments_kernel<M>, d, n_segs, &grid, &smem);                                            \
+    rc = plan_grid(decode_units_kernel<M>, d, n_units, &grid, &smem);                                              \
     if (rc) return rc;                                                                                             \
-    decode_segments_kernel<M><<<grid, kThreads, smem, st>>>(d->view(), lut_bytes_of(d), multi, d_in, in_bytes, d_segs, \
-                                                           n_segs, d_out);
+    decode_units_kernel<M><<<grid, kThreads, smem, st>>>(d->view(), lut_bytes_of(d), multi, d_in, in_bytes, d_segs,    \
+                                                        n_segs, d_unit_first, n_units, d_out);
     if (mode == DINT_MODE_RAW) { LAUNCH_SEG(OUT_RAW) }
     else if (mode == DINT_MODE_DOCIDS) { LAUNCH_SEG(OUT_DOCIDS) }
     else { LAUNCH_SEG(OUT_FREQS) }
@@ -613,6 +503,12 @@ int dint_decode_segments(const dint_dict* d, const uint8_t* d_in, size_t in_byte
     ++g_launches;
     CUDA_TRY(cudaGetLastError());
     return DINT_OK;
+}
+
+int dint_decode_segments(const dint_dict* d, const uint8_t* d_in, size_t in_bytes, const dint_segment* d_segs,
+                         size_t n_segs, uint32_t block_size, uint32_t* d_out, int mode, void* stream) {
+    (void)block_size;
+    return dint_decode_units(d, d_in, in_bytes, d_segs, n_segs, nullptr, 0, d_out, mode, stream);
 }
 
 int dint_decode_index(const dint_dict* docs_dict, const dint_dict* freqs_dict, const uint8_t* d_lists,
@@ -691,9 +587,10 @@ int dint_checksum_lists(const uint32_t* d_values, const uint64_t* d_list_offsets
 struct dint_vroom_ctx {
     const dint_dict* dict = nullptr;
     uint32_t block_size = 0;
-    uint64_t n_lists = 0, n_ints = 0, n_segs = 0, in_bytes = 0;
+    uint64_t n_lists = 0, n_ints = 0, n_segs = 0, n_units = 0, in_bytes = 0;
     uint8_t* d_in = nullptr;
     dint_segment* d_segs = nullptr;
+    uint32_t* d_unit_first = nullptr;
     uint64_t* d_list_offsets = nullptr;
     uint32_t* d_out = nullptr;
     uint64_t* d_sums = nullptr;
@@ -713,6 +610,7 @@ int dint_vroom_ctx_create(const dint_dict* d, const dint_vroom_plan* plan, uint3
     c->n_lists = plan->list_offsets.size() - 1;
     c->n_ints = plan->n_ints;
     c->n_segs = plan->segments.size();
+    c->n_units = plan->unit_first.empty() ? 0 : plan->unit_first.size() - 1;
     c->in_bytes = plan->list_byte_offsets.back();
     auto fail = [&](cudaError_t e) {
         dint::set_error(std::string("dint_vroom_ctx_create: ") + cudaGetErrorString(e));
@@ -722,6 +620,7 @@ int dint_vroom_ctx_create(const dint_dict* d, const dint_vroom_plan* plan, uint3
     cudaError_t e;
     if ((e = cudaMalloc(&c->d_in, c->in_bytes + 16)) != cudaSuccess) return fail(e);
     if ((e = cudaMalloc(&c->d_segs, (c->n_segs + 1) * sizeof(dint_segment))) != cudaSuccess) return fail(e);
+    if ((e = cudaMalloc(&c->d_unit_first, (c->n_units + 1) * 4)) != cudaSuccess) return fail(e);
     if ((e = cudaMalloc(&c->d_list_offsets, (c->n_lists + 1) * 8)) != cudaSuccess) return fail(e);
     if ((e = cudaMalloc(&c->d_out, (c->n_ints + 1) * 4)) != cudaSuccess) return fail(e);
     if ((e = cudaMalloc(&c->d_sums, (c->n_lists + 1) * 8)) != cudaSuccess) return fail(e);
@@ -730,6 +629,9 @@ int dint_vroom_ctx_create(const dint_dict* d, const dint_vroom_plan* plan, uint3
         return fail(e);
     if ((e = cudaMemcpy(c->d_list_offsets, plan->list_offsets.data(), (c->n_lists + 1) * 8, cudaMemcpyHostToDevice)) !=
         cudaSuccess)
+        return fail(e);
+    if (c->n_units && (e = cudaMemcpy(c->d_unit_first, plan->unit_first.data(), (c->n_units + 1) * 4,
+                                      cudaMemcpyHostToDevice)) != cudaSuccess)
         return fail(e);
     *out = c;
     return DINT_OK;
@@ -740,6 +642,7 @@ void dint_vroom_ctx_destroy(dint_vroom_ctx* c) {
     device_guard g(c->dict->device);
     cudaFree(c->d_in);
     cudaFree(c->d_segs);
+    cudaFree(c->d_unit_first);
     cudaFree(c->d_list_offsets);
     cudaFree(c->d_out);
     cudaFree(c->d_sums);
@@ -758,7 +661,8 @@ int dint_vroom_decode_host(dint_vroom_ctx* c, const void* h_bin, size_t len, int
     device_guard g(c->dict->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (len) CUDA_TRY(cudaMemcpyAsync(c->d_in, h_bin, len, cudaMemcpyHostToDevice, st));
-    int rc = dint_decode_segments(c->dict, c->d_in, len, c->d_segs, c->n_segs, c->block_size, c->d_out, mode, stream);
+    int rc = dint_decode_units(c->dict, c->d_in, len, c->d_segs, c->n_segs, c->n_units ? c->d_unit_first : nullptr,
+                               c->n_units, c->d_out, mode, stream);
     if (rc) return rc;
     if (h_sums && c->n_lists) {
         rc = dint_checksum_lists(c->d_out, c->d_list_offsets, c->n_lists, c->d_sums, stream);

@@ -55,6 +55,7 @@ class VroomFile:
         self.plan = capi.VroomPlan(self.dict, bin_bytes, block_size=block_size, chunk_ints=chunk_ints)
         self.d_in = _to_device_bytes(bin_bytes, self.dev)
         self.d_segs = _structured_to_device(self.plan.segments, self.dev)
+        self.d_unit_first = torch.from_numpy(self.plan.unit_first.astype(np.int64)).to(torch.int32).to(self.dev)
         self.d_list_offsets = torch.from_numpy(self.plan.list_offsets.astype(np.int64)).to(self.dev)
         self.n_ints = int(self.plan.n_ints)
         self.n_lists = int(self.plan.n_lists)
@@ -64,8 +65,9 @@ class VroomFile:
         if out is None:
             out = torch.empty(self.n_ints, dtype=torch.int32, device=self.dev)
         st = (stream or torch.cuda.current_stream(self.dev)).cuda_stream
-        capi.decode_segments(self.dict, self.d_in.data_ptr(), self.plan.in_bytes, self.d_segs.data_ptr(),
-                             int(self.plan.n_segments), out.data_ptr(), mode, stream=st, block_size=self.block_size)
+        capi.decode_units(self.dict, self.d_in.data_ptr(), self.plan.in_bytes, self.d_segs.data_ptr(),
+                          int(self.plan.n_segments), self.d_unit_first.data_ptr(), int(self.plan.n_units),
+                          out.data_ptr(), mode, stream=st)
         return out
 
     def checksums(self, values, stream=None):

@@ -50,7 +50,7 @@
 extern "C" {
 #endif
 
-#define DINT_B200_ABI_VERSION 1
+#define DINT_B200_ABI_VERSION 2
 
 /* dictionary kinds == the reference's three dictionary types */
 enum {
@@ -77,12 +77,18 @@ enum {
 
 /* One contiguous codeword stream that starts on a codeword boundary and produces
  * exactly n integers: a whole vroom list, a chunk of a long list, or one 256-int
- * block of a multi_packed vroom list. 24 bytes. */
+ * block of a multi_packed vroom list. 32 bytes. */
 typedef struct dint_segment {
     uint64_t in_off;   /* byte offset of the first codeword (multi: of the selector byte)  */
     uint64_t out_off;  /* index of the first output integer                                */
     uint32_t n;        /* integers produced                                                */
     uint32_t doc_base; /* DOCIDS mode: docid[first] = doc_base + v[first]                  */
+    uint32_t in_len;   /* bytes of the stream (0 = unknown: the decoder may read ahead up
+                          to in_bytes)                                                      */
+    uint32_t doc_sum;  /* DOCIDS mode: sum of (v + 1) over the segment, mod 2^32, so that
+                          doc_base + doc_sum - 1 is its last docid. Needed only when the
+                          next segment of the same work unit continues the output
+                          (out_off == this out_off + n)                                     */
 } dint_segment;
 
 /* One block of a dict_freq_index posting list (docs bytes immediately followed by the
@@ -133,6 +139,11 @@ uint64_t dint_vroom_plan_num_lists(const dint_vroom_plan* p);
 uint64_t dint_vroom_plan_num_ints(const dint_vroom_plan* p);
 uint64_t dint_vroom_plan_num_segments(const dint_vroom_plan* p);
 const dint_segment* dint_vroom_plan_segments(const dint_vroom_plan* p);
+/* Work units: unit u = segments [unit_first[u], unit_first[u+1]), consecutive segments with
+ * contiguous output holding about 2 K integers; one warp decodes one unit at a time.
+ * num_units + 1 entries. */
+uint64_t dint_vroom_plan_num_units(const dint_vroom_plan* p);
+const uint32_t* dint_vroom_plan_unit_first(const dint_vroom_plan* p);
 /* n_lists + 1 offsets into the packed output; list i is [off[i], off[i+1]) */
 const uint64_t* dint_vroom_plan_list_offsets(const dint_vroom_plan* p);
 /* n_lists + 1 byte offsets of the list headers; the last one is the file size */
@@ -158,6 +169,10 @@ int dint_index_plan_layout(const dint_index_plan* p, uint64_t* lists_off, uint64
  * stream: a cudaStream_t (0 = default stream). */
 int dint_decode_segments(const dint_dict* d, const uint8_t* d_in, size_t in_bytes, const dint_segment* d_segs,
                          size_t n_segs, uint32_t block_size, uint32_t* d_out, int mode, void* stream);
+/* Same with an explicit work-unit table (d_unit_first: n_units + 1 DEVICE uint32, see
+ * dint_vroom_plan_unit_first). dint_decode_segments groups every 8 consecutive segments. */
+int dint_decode_units(const dint_dict* d, const uint8_t* d_in, size_t in_bytes, const dint_segment* d_segs, size_t n_segs,
+                      const uint32_t* d_unit_first, size_t n_units, uint32_t* d_out, int mode, void* stream);
 
 /* d_lists: the m_lists bytes of the index. Writes docids and freqs (enumerator
  * semantics: docid(), freq()) of every block into the packed arrays. Either output

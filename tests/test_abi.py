@@ -25,11 +25,11 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), f"{n} declared in include/dint_b200.h but not exported"
     assert sorted(capi.SYMBOLS) == names
-    assert L.dint_abi_version() == 1
+    assert L.dint_abi_version() == 2
 
 
 def test_struct_layouts_match_header():
-    assert capi.SEGMENT_DTYPE.itemsize == 24
+    assert capi.SEGMENT_DTYPE.itemsize == 32
     assert capi.BLOCK_DTYPE.itemsize == 32
     assert capi.SEGMENT_DTYPE.fields["n"][1] == 16 and capi.BLOCK_DTYPE.fields["block_max"][1] == 24
 
@@ -59,7 +59,7 @@ def test_product_does_not_reference_the_oracle():
     """the product sources never include, link or import anything under oracle/"""
     for dirpath, _, files in os.walk(os.path.join(ROOT, "dint_b200")):
         for f in files:
-            if f.endswith((".py", ".cu", ".cpp", ".hpp", ".h")):
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
                 txt = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "oracle" not in txt.lower().replace("no cpu fallback", ""), os.path.join(dirpath, f)
     assert "oracle" not in open(os.path.join(ROOT, "include", "dint_b200.h")).read().lower()

@@ -34,6 +34,16 @@ def test_vroom_plan_matches_oracle_walk(oracle, golden, type_, part):
     list_of = np.searchsorted(plan.list_offsets, segs["out_off"], side="right") - 1
     want = (csum[segs["out_off"].astype(np.int64)] - csum[plan.list_offsets[list_of].astype(np.int64)]) & np.uint64(0xFFFFFFFF)
     assert np.array_equal(segs["doc_base"].astype(np.uint64), want)
+    # doc_sum = sum(v + 1) over the segment; in_len = its bytes (segments of one list are back to back)
+    ends = (segs["out_off"] + segs["n"]).astype(np.int64)
+    assert np.array_equal(segs["doc_sum"].astype(np.uint64),
+                          (csum[ends] - csum[segs["out_off"].astype(np.int64)]) & np.uint64(0xFFFFFFFF))
+    same_list = list_of[1:] == list_of[:-1]
+    assert np.array_equal((segs["in_off"] + segs["in_len"])[:-1][same_list], segs["in_off"][1:][same_list])
+    assert int(segs["in_off"][-1] + segs["in_len"][-1]) == len(bin_)
+    # work units tile the segment table, in order, none empty
+    uf = plan.unit_first.astype(np.int64)
+    assert uf[0] == 0 and uf[-1] == len(segs) and np.all(np.diff(uf) > 0) and len(uf) == plan.n_units + 1
     # every segment starts on a codeword boundary: decoding it alone reproduces its slice
     raw = np.frombuffer(bin_ + b"\0" * 64, dtype=np.uint8)
     rng = np.random.default_rng(5)
