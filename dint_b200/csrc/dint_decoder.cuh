@@ -1,25 +1,29 @@
 // dint_b200 — the warp-level DINT stream decoder (device code, sm_100a).
 //
-// One warp owns a WORK UNIT: a run of consecutive segments (whole short lists and/or
-// ~1 K-integer chunks of long lists, include/dint_b200.h) whose outputs are contiguous in the
-// packed output array. The warp streams through the unit tile by tile:
+// One warp decodes a RUN of up to 32 consecutive segments (whole short lists, ~1 K-integer
+// chunks of long lists, 256-integer blocks of multi_packed lists — include/dint_b200.h) whose
+// compressed bytes are (nearly) adjacent and whose outputs are contiguous in the packed output
+// array. The codeword symbols of the run form one FLAT symbol space; the warp walks it tile by
+// tile, so tiles stay full even when a list holds a single posting:
 //
 //   input ring   1 KB of shared memory per warp, filled 512 bytes at a time with 16-byte
 //                cp.async (LDGSTS) from the compressed stream; the copy for the next chunk
 //                is in flight while the current one is parsed. Ring offsets are the low bits
 //                of the global byte address, so any stream alignment works.
-//   tile         32 consecutive codeword symbols (u16, or u8 in multi_packed's narrow blocks),
-//                one per lane, always starting on a codeword boundary:
+//   tile         32 consecutive flat symbols (u16, or u8 in multi_packed's narrow blocks), one
+//                per lane, always starting on a codeword boundary. A __reduce_or_sync mask of
+//                the segment starts inside the tile + popc tells every lane which segment its
+//                symbol belongs to (lane k holds segment k's parameters, fetched by shuffle).
 //                  * __ballot_sync masks of the symbols equal to 0 / 1 decide which symbols are
-//                    codewords and which are exception payload. Candidates with no other
-//                    candidate in the preceding 2 (u16) / 4 (u8) symbols are codewords for
-//                    sure and are resolved bit-parallel; only the rest (payload that happens
-//                    to equal 0/1) is walked in stream order, warp-uniformly;
+//                    codewords and which are exception payload. Candidates that no earlier
+//                    candidate can reach are codewords for sure and are resolved bit-parallel;
+//                    only real exception codewords hiding behind such payload cost one
+//                    warp-uniform loop trip each;
 //                  * entry lengths come from a 4-bit log2(length) table in shared memory
 //                    (32 KB for a single dictionary);
 //                  * a __shfl_up_sync inclusive scan of the lengths gives every codeword its
-//                    output offset; codewords that would overflow the staging ring or the
-//                    segment are left for the next tile.
+//                    output offset; codewords that would overflow the staging ring are left
+//                    for the next tile.
 //   scatter      every codeword lane copies its entry from the L2-resident dictionary (64-byte
 //                aligned rows, 16-byte vector loads) / its exception value into the warp's
 //                OUTPUT STAGING RING (512 ints of shared memory, indexed by the low bits of
@@ -50,6 +54,8 @@ constexpr int kInBytes = 1024;   // input ring per warp (two chunks)
 constexpr int kChunk = 512;      // bytes per cp.async round (32 lanes x 16 bytes)
 constexpr int kGroup = 128;      // integers per flush round (one uint4 per lane)
 constexpr int kWarpSmem = kStageInts * 4 + kInBytes;
+constexpr uint32_t kMaxRunBytes = 1u << 30;  // input span of one run (32-bit relative offsets)
+constexpr uint32_t kUnknownLen = 0xFFFFFFFFu;
 
 enum { OUT_RAW = 0, OUT_DOCIDS = 1, OUT_FREQS = 2, OUT_SKIP = 3 };
 
@@ -58,9 +64,9 @@ __device__ __forceinline__ unsigned lane_id() {
     asm("mov.u32 %0, %%laneid;" : "=r"(l));
     return l;
 }
-__device__ __forceinline__ unsigned lanemask_lt() {
+__device__ __forceinline__ unsigned lanemask_le() {
     unsigned m;
-    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    asm("mov.u32 %0, %%lanemask_le;" : "=r"(m));
     return m;
 }
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
@@ -68,7 +74,6 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, uint64_t src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-__device__ __forceinline__ uint4 ldg_row(const uint4* p) { return __ldg(p); }
 __device__ __forceinline__ void st_stream(uint32_t* p, uint32_t v) { __stcs(p, v); }
 __device__ __forceinline__ void st_stream4(uint32_t* p, uint4 v) { __stcs(reinterpret_cast<uint4*>(p), v); }
 
@@ -80,43 +85,66 @@ __device__ __forceinline__ uint32_t warp_inclusive_scan(uint32_t v, unsigned lan
     }
     return v;
 }
+__device__ __forceinline__ uint64_t shfl64(uint64_t v, int src) {
+    const uint32_t lo = __shfl_sync(FULL, uint32_t(v), src), hi = __shfl_sync(FULL, uint32_t(v >> 32), src);
+    return (uint64_t(hi) << 32) | lo;
+}
 
 // Per-warp decoder state. Lives in registers; everything is warp-uniform.
 struct warp_state {
     uint32_t* stage;    // [kStageInts] shared
     uint8_t* inb;       // [kInBytes] shared
     uint32_t* out;      // packed output array (global)
-    uint64_t flushed;   // output index: everything below it (of this unit) is in global memory
+    uint64_t flushed;   // output index: everything below it (of this run) is in global memory
     uint32_t staged;    // integers sitting in the ring: [flushed, flushed + staged)
     uint32_t acc;       // DOCIDS: docid of element flushed-1 (doc_base - 1 at a list start)
-    uint64_t win_end;   // input ring holds global addresses [win_end - kInBytes, win_end)
-    uint64_t safe_end;  // ... of which everything below safe_end has landed
-    uint64_t in_lo;     // 16-byte aligned bounds of the bytes this warp may read
-    uint64_t in_hi;
     bool vec_ok;        // output base is 16-byte aligned
+    // input: global byte address = anchor + rel; anchor is a multiple of kInBytes so that the
+    // ring offset of an address is rel & (kInBytes - 1)
+    uint64_t anchor;
+    uint32_t win_end;   // ring holds rel addresses [win_end - kInBytes, win_end); 0 = nothing
+    uint32_t safe_end;  // ... of which everything below safe_end has landed
+    uint32_t lo_rel;    // 16-byte aligned bounds of the bytes this warp may read, rel
+    uint32_t hi_rel;
+    uint64_t in_lo;     // the same bounds as absolute addresses (whole input buffer)
+    uint64_t in_hi;
 
-    __device__ __forceinline__ void load_chunk(uint64_t base, unsigned lane) {
-        const uint64_t x = base + 16u * lane;
-        const uint32_t so = smem_u32(inb) + (uint32_t(x) & (kInBytes - 1));
-        if (x >= in_lo && x < in_hi) cp_async16(so, x);
+    // Re-anchors the input side at global address g (start of a run); returns g's rel offset.
+    // Bytes at or beyond `end` (absolute) are not fetched.
+    __device__ __forceinline__ uint32_t set_anchor(uint64_t g, uint64_t end) {
+        cp_async_wait_all();
+        __syncwarp();
+        anchor = g & ~uint64_t(kInBytes - 1);
+        lo_rel = in_lo > anchor ? uint32_t(in_lo - anchor) : 0u;
+        const uint64_t hi = end >= in_hi ? in_hi : (end + 15) & ~uint64_t(15);
+        hi_rel = uint32_t(min(hi > anchor ? hi - anchor : uint64_t(0), uint64_t(0xFFFFFFF0u)));
+        win_end = 0;
+        safe_end = 0;
+        return uint32_t(g - anchor);
+    }
+    __device__ __forceinline__ void load_chunk(uint32_t base, unsigned lane) {
+        const uint32_t x = base + 16u * lane;
+        const uint32_t so = smem_u32(inb) + (x & (kInBytes - 1));
+        if (x >= lo_rel && x < hi_rel) cp_async16(so, anchor + x);
         else asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(so), "r"(0u) : "memory");
     }
-    // make [addr, addr + look) readable from the ring
-    __device__ __forceinline__ void ensure_input(uint64_t addr, uint32_t look, unsigned lane) {
-        if (win_end == 0 || addr + kInBytes < win_end || addr >= win_end) {
+    // make rel addresses [a, a + look) readable from the ring (look <= kChunk)
+    __device__ __forceinline__ void ensure_input(uint32_t a, uint32_t look, unsigned lane) {
+        if (a + look <= safe_end && a + kChunk <= win_end) return;  // the common case: one compare pair
+        if (win_end == 0 || a + kInBytes < win_end || a >= win_end) {
             cp_async_wait_all();
             __syncwarp();
-            const uint64_t b = addr & ~uint64_t(kChunk - 1);
+            const uint32_t b = a & ~uint32_t(kChunk - 1);
             load_chunk(b, lane);
             load_chunk(b + kChunk, lane);
             win_end = b + 2 * kChunk;
             safe_end = b;
-        } else if (addr + kChunk > win_end) {
+        } else if (a + kChunk > win_end) {
             // the warp has moved into the newest chunk: the other slot is dead, refill it
             load_chunk(win_end, lane);
             win_end += kChunk;
         }
-        if (addr + look > safe_end) {
+        if (a + look > safe_end) {
             cp_async_wait_all();
             __syncwarp();
             safe_end = win_end;
@@ -195,73 +223,95 @@ struct warp_state {
     }
 };
 
-// Decodes the codeword stream that starts at global address `addr` and produces exactly n
-// integers, appending them to the staging ring. Returns the address one past the last consumed
-// symbol (the reference's returned pointer). SYM = bytes per codeword symbol.
-//   lut       4-bit log2(length) table, indexed by dictionary row
-//   row_base  first row of the stream's class, class_rows its number of rows
-//   corr      DOCIDS re-basing term folded into the first integer (0 for a fresh ring)
-template <int SYM, int MODE>
-__device__ __forceinline__ uint64_t decode_tiles(warp_state& ws, const uint32_t* __restrict__ rows,
-                                                 const uint8_t* __restrict__ lut, uint32_t row_base, uint32_t class_rows,
-                                                 uint64_t addr, uint32_t n, uint32_t corr, unsigned lane) {
-    constexpr int PZ = 2 / SYM;  // payload symbols after a 0 codeword (u16 value)
-    constexpr int PO = 4 / SYM;  // payload symbols after a 1 codeword (u32 value)
-    constexpr uint32_t LOOK = 32 * SYM + 4;
-    uint32_t remaining = n;
-    while (remaining) {
-        ws.ensure_input(addr, LOOK, lane);
-        const uint32_t a = uint32_t(addr) + SYM * lane;
-        uint32_t sym;
-        if (SYM == 1) sym = ws.rb(a);
-        else if ((uint32_t(addr) & 1u) == 0) sym = *reinterpret_cast<const uint16_t*>(ws.inb + (a & (kInBytes - 1)));
-        else sym = ws.rb(a) | (ws.rb(a + 1) << 8);
+// What lane k knows about segment k of the run.
+struct seg_lane {
+    uint32_t cs;    // first flat symbol of the segment
+    uint32_t ab;    // rel address of its first symbol
+    uint32_t pk;    // row_base | narrow << 31   (narrow: u8 symbols, multi_packed selector >= 6)
+    uint32_t rows;  // addressable rows of its class
+    uint32_t corr;  // DOCIDS: added to the segment's first integer (re-bases the running prefix sum)
+};
+
+// Decodes a run of `cnt` (<= 32) segments whose parameters sit in lanes 0..cnt-1 of `sl`.
+//   S  flat symbols in the run (kUnknownLen: a single segment of unknown byte length; the walk
+//      then stops after exactly N integers, like the reference's `i != n` loop)
+//   N  integers the run produces (never exceeded, whatever the bytes say)
+// Appends to the staging ring. Returns the flat symbol position one past the last consumed symbol.
+template <bool MULTI, int MODE>
+__device__ __forceinline__ uint32_t decode_run(warp_state& ws, const uint32_t* __restrict__ rows,
+                                               const uint8_t* __restrict__ lut, const seg_lane& sl, uint32_t cnt,
+                                               uint32_t S, uint32_t N, unsigned lane) {
+    uint32_t F = 0, produced = 0;
+    const bool has = lane < cnt;
+    const unsigned le = lanemask_le();
+    while (produced < N && F < S) {
+        // ---- which segment does each lane's symbol belong to ------------------------------------
+        const uint32_t kcur = __popc(__ballot_sync(FULL, has && sl.cs <= F)) - 1u;
+        const uint32_t rel = sl.cs - F;
+        const uint32_t H = __reduce_or_sync(FULL, (has && rel - 1u < 31u) ? (1u << rel) : 0u);
+        const uint32_t kl = kcur + __popc(H & le) - ((H & 1u) ? 1u : 0u);
+        const uint32_t my_cs = __shfl_sync(FULL, sl.cs, kl), my_ab = __shfl_sync(FULL, sl.ab, kl);
+        const uint32_t my_pk = __shfl_sync(FULL, sl.pk, kl), my_rows = __shfl_sync(FULL, sl.rows, kl);
+        const bool narrow = MULTI && (my_pk >> 31);
+        const uint32_t fi = F + lane;
+        const uint32_t a = my_ab + (narrow ? 1u : 2u) * (fi - my_cs);
+        // bytes the tile can touch: from lane 0's symbol to lane 31's symbol + the widest payload
+        const uint32_t a0 = __shfl_sync(FULL, a, 0), a31 = __shfl_sync(FULL, a, 31);
+        ws.ensure_input(a0, min(a31 - a0 + 8u, uint32_t(kChunk)), lane);
+        uint32_t sym = ws.rb(a);
+        if (!narrow) sym |= ws.rb(a + 1) << 8;
 
         // ---- which symbols are codewords ----------------------------------------------------
-        const uint32_t Z = __ballot_sync(FULL, sym == 0u);
-        const uint32_t O = __ballot_sync(FULL, sym == 1u);
+        const uint32_t live = S - F >= 32u ? FULL : ((1u << (S - F)) - 1u);  // symbols inside the run
+        const uint32_t Z = __ballot_sync(FULL, sym == 0u) & live;
+        const uint32_t O = __ballot_sync(FULL, sym == 1u) & live;
         const uint32_t E = Z | O;
         uint32_t P = 0;  // payload symbols of this tile
         if (E) {
-            uint32_t prev = 0;
-#pragma unroll
-            for (int d = 1; d <= PO; ++d) prev |= E << d;
-            const uint32_t A = E & ~prev;  // certainly codewords
-            const uint32_t az = A & Z, ao = A & O;
-#pragma unroll
-            for (int d = 1; d <= PZ; ++d) P |= az << d;
-#pragma unroll
-            for (int d = 1; d <= PO; ++d) P |= ao << d;
-            uint32_t U = E & ~A;
-            while (U) {  // warp-uniform: payload that happens to look like an exception codeword
-                const int j = __ffs(U) - 1;
-                U &= U - 1;
-                if (!((P >> j) & 1u)) {
-                    const uint32_t cnt = ((Z >> j) & 1u) ? PZ : PO;
-                    P |= (((1u << cnt) - 1u) << j) << 1;
-                }
+            // a 0 codeword is followed by a u16 value, a 1 codeword by a u32 value
+            const uint32_t Nm = MULTI ? __ballot_sync(FULL, narrow) : 0u;
+            const uint32_t zw = Z & ~Nm, ow = O & ~Nm, zn = Z & Nm, on = O & Nm;
+            const uint32_t starts = H | 1u;  // a segment always starts with a codeword
+            uint32_t reach = (zw << 1) | (ow << 1) | (ow << 2);
+            if (MULTI) reach |= (zn << 1) | (zn << 2) | (on << 1) | (on << 2) | (on << 3) | (on << 4);
+            const uint32_t A = E & (~reach | starts);  // certainly codewords
+            const uint32_t azw = A & zw, aow = A & ow;
+            P = (azw << 1) | (aow << 1) | (aow << 2);
+            if (MULTI) {
+                const uint32_t azn = A & zn, aon = A & on;
+                P |= (azn << 1) | (azn << 2) | (aon << 1) | (aon << 2) | (aon << 3) | (aon << 4);
+            }
+            P &= ~starts;
+            uint32_t c = E & ~A & ~P;
+            while (c) {  // warp-uniform: a real exception codeword right behind 0/1-valued payload
+                const int j = __ffs(c) - 1;
+                const bool jn = MULTI && ((Nm >> j) & 1u);
+                const uint32_t pcnt = ((Z >> j) & 1u) ? (jn ? 2u : 1u) : (jn ? 4u : 2u);
+                P |= ((((1u << pcnt) - 1u) << j) << 1) & ~starts;
+                c = E & ~A & ~P & ~((2u << j) - 1u);
             }
         }
-        const bool iscw = !((P >> lane) & 1u);
+        const bool iscw = (((live & ~P) >> lane) & 1u) != 0u;
 
         // ---- lengths, offsets, how much of the tile is taken ----------------------------------
         uint32_t len = iscw ? 1u : 0u;
         uint32_t row = 0;
         if (iscw && sym >= 2u) {
-            row = row_base + min(sym, class_rows - 1u);
+            row = (my_pk & 0x7FFFFFFFu) + min(sym, my_rows - 1u);
             len = 1u << ((uint32_t(lut[row >> 1]) >> ((row & 1u) * 4u)) & 15u);
         }
         const uint32_t e = warp_inclusive_scan(len, lane);
         const uint32_t s = e - len;
-        const uint32_t room = kStageInts - ((uint32_t(ws.flushed) & (kGroup - 1)) + ws.staged);
-        const uint32_t limit = MODE == OUT_SKIP ? remaining : min(remaining, room);
+        uint32_t limit = N - produced;
+        if (MODE != OUT_SKIP) limit = min(limit, kStageInts - ((uint32_t(ws.flushed) & (kGroup - 1)) + ws.staged));
         const bool valid = iscw && e <= limit;
         const uint32_t V = __ballot_sync(FULL, valid);
-        if (V == 0) break;  // malformed stream (a codeword straddles the end of the segment)
+        if (V == 0) break;  // malformed stream (a codeword straddles the end of the run)
         const int last = 31 - __clz(V);
         const uint32_t T = __shfl_sync(FULL, e, last);
         const uint32_t lastsym = __shfl_sync(FULL, sym, last);
-        const uint32_t extra = lastsym == 0u ? PZ : (lastsym == 1u ? PO : 0);
+        const bool lastn = MULTI && __shfl_sync(FULL, narrow ? 1u : 0u, last);
+        const uint32_t extra = lastsym == 0u ? (lastn ? 2u : 1u) : (lastsym == 1u ? (lastn ? 4u : 2u) : 0u);
 
         // ---- scatter into the staging ring ------------------------------------------------------
         if (MODE != OUT_SKIP) {
@@ -270,16 +320,17 @@ __device__ __forceinline__ uint64_t decode_tiles(warp_state& ws, const uint32_t*
             const uint32_t L = (valid && sym >= dint::kReserved) ? len : 0u;
             const uint4* rp = reinterpret_cast<const uint4*>(rows + size_t(row) * dint::kEntry);
             uint4 r0 = make_uint4(0, 0, 0, 0);
-            if (L) r0 = ldg_row(rp);
+            if (L) r0 = __ldg(rp);
             if (valid && sym < 2u) {
-                const uint32_t pa = a + SYM;
+                const uint32_t pa = a + (narrow ? 1u : 2u);
                 r0.x = ws.rb(pa) | (ws.rb(pa + 1) << 8);
                 if (sym == 1u) r0.x |= (ws.rb(pa + 2) << 16) | (ws.rb(pa + 3) << 24);
             }
-            if (valid) {
-                if (s == 0) r0.x += corr;
-                st[base & (kStageInts - 1)] = r0.x;
+            if (MODE == OUT_DOCIDS) {
+                const uint32_t my_corr = __shfl_sync(FULL, sl.corr, kl);
+                if (fi == my_cs) r0.x += my_corr;
             }
+            if (valid) st[base & (kStageInts - 1)] = r0.x;
             if (L > 1) st[(base + 1) & (kStageInts - 1)] = r0.y;
             if (L > 2) {
                 st[(base + 2) & (kStageInts - 1)] = r0.z;
@@ -287,7 +338,7 @@ __device__ __forceinline__ uint64_t decode_tiles(warp_state& ws, const uint32_t*
             }
             if (__any_sync(FULL, L > 4)) {
                 if (L > 4) {
-                    const uint4 r1 = ldg_row(rp + 1);
+                    const uint4 r1 = __ldg(rp + 1);
                     st[(base + 4) & (kStageInts - 1)] = r1.x;
                     st[(base + 5) & (kStageInts - 1)] = r1.y;
                     st[(base + 6) & (kStageInts - 1)] = r1.z;
@@ -295,8 +346,8 @@ __device__ __forceinline__ uint64_t decode_tiles(warp_state& ws, const uint32_t*
                 }
                 if (__any_sync(FULL, L > 8)) {
                     if (L > 8) {
-                        const uint4 r2 = ldg_row(rp + 2);
-                        const uint4 r3 = ldg_row(rp + 3);
+                        const uint4 r2 = __ldg(rp + 2);
+                        const uint4 r3 = __ldg(rp + 3);
                         st[(base + 8) & (kStageInts - 1)] = r2.x;
                         st[(base + 9) & (kStageInts - 1)] = r2.y;
                         st[(base + 10) & (kStageInts - 1)] = r2.z;
@@ -308,34 +359,54 @@ __device__ __forceinline__ uint64_t decode_tiles(warp_state& ws, const uint32_t*
                     }
                 }
             }
-            corr = 0;
             ws.staged += T;
             __syncwarp();
             ws.flush_full<MODE>(lane);
             __syncwarp();
         }
-        remaining -= T;
-        addr += uint64_t(SYM) * (last + 1 + extra);
+        produced += T;
+        F += uint32_t(last) + 1u + extra;
     }
-    return addr;
+    return F;
 }
 
-// One segment. single kinds: u16 stream at `addr`. multi: selector byte at `addr`, then a u16
-// (selector < 6) or u8 (selector - 6) stream into class selector % 6
-// (vroom_env/dint_codecs.hpp:536-575, include/dint/dint_codecs.hpp:466-505).
+// Per-class parameters of a dictionary, staged in shared memory next to the length table.
+struct class_info {
+    uint32_t row_base;
+    uint32_t rows;
+};
+
+// One segment of unknown byte length that starts at global address g and produces n integers
+// (a dict_freq_index block, or a whole list for the host convenience call). single kinds: u16
+// stream at g. multi: selector byte at g, then a u16 (selector < 6) or u8 (selector - 6)
+// stream into class selector % 6 (vroom_env/dint_codecs.hpp:536-575,
+// include/dint/dint_codecs.hpp:466-505). Returns the global address one past the last consumed
+// byte (the reference's returned pointer).
 template <int MODE>
-__device__ __forceinline__ uint64_t decode_one(warp_state& ws, const dint_dict_view& dv, const uint8_t* __restrict__ lut,
-                                               bool multi, uint64_t addr, uint32_t n, uint32_t corr, unsigned lane) {
-    if (n == 0) return addr;
-    if (!multi) return decode_tiles<2, MODE>(ws, dv.rows, lut, 0, dv.n_rows, addr, n, corr, lane);
-    ws.ensure_input(addr, 1, lane);
-    const uint32_t sel = ws.rb(uint32_t(addr));
+__device__ __forceinline__ uint64_t decode_one(warp_state& ws, const uint32_t* __restrict__ rows,
+                                               const uint8_t* __restrict__ lut, const class_info* __restrict__ classes,
+                                               uint32_t n_classes, bool multi, uint64_t g, uint32_t n, unsigned lane) {
+    if (n == 0) return g;
+    uint32_t a = ws.set_anchor(g, ~uint64_t(0));
+    seg_lane sl;
+    sl.cs = 0;
+    sl.corr = 0;
+    if (!multi) {
+        sl.ab = a;
+        sl.pk = 0;
+        sl.rows = classes[0].rows;
+        const uint32_t F = decode_run<false, MODE>(ws, rows, lut, sl, 1, kUnknownLen, n, lane);
+        return ws.anchor + a + 2ull * F;
+    }
+    ws.ensure_input(a, 1, lane);
+    const uint32_t sel = ws.rb(a);
     const bool wide = sel < dint::kSelectors;
-    const uint32_t cls = min(wide ? sel : sel - dint::kSelectors, dv.n_classes - 1u);
-    const uint32_t base = dv.class_base[cls];
-    const uint32_t crows = (cls + 1 < dv.n_classes ? dv.class_base[cls + 1] : dv.n_rows) - base;
-    if (wide) return decode_tiles<2, MODE>(ws, dv.rows, lut, base, crows, addr + 1, n, corr, lane);
-    return decode_tiles<1, MODE>(ws, dv.rows, lut, base, min(crows, 256u), addr + 1, n, corr, lane);
+    const class_info ci = classes[min(wide ? sel : sel - dint::kSelectors, n_classes - 1u)];
+    sl.ab = a + 1;
+    sl.pk = ci.row_base | (wide ? 0u : 0x80000000u);
+    sl.rows = wide ? ci.rows : min(ci.rows, 256u);
+    const uint32_t F = decode_run<true, MODE>(ws, rows, lut, sl, 1, kUnknownLen, n, lane);
+    return ws.anchor + a + 1ull + (wide ? 2ull : 1ull) * F;
 }
 
 }  // namespace dintk

@@ -19,7 +19,7 @@ constexpr uint32_t kReserved = 7;      // EXCEPTIONS + 5 run codewords (single_d
 constexpr uint32_t kDefaultBlock = 256;  // constants::block_size    (include/util.hpp:35)
 constexpr uint32_t kDefaultChunk = 1024;
 constexpr uint32_t kUnitInts = 2048;     // a work unit closes once it holds this many integers ...
-constexpr uint32_t kUnitSegments = 256;  // ... or this many segments
+constexpr uint32_t kUnitSegments = 32;   // ... or this many segments (one per lane of the decoding warp)
 
 void set_error(const std::string& msg);
 

@@ -41,13 +41,26 @@ std::atomic<uint64_t> g_launches{0};
 
 extern __shared__ __align__(16) uint8_t g_smem[];
 
-// Stages the 4-bit log2(length) table into shared memory and carves the calling warp's rings.
-__device__ __forceinline__ void cta_setup(const dint_dict_view& dv, uint32_t lut_bytes, const uint8_t* in,
-                                          uint64_t in_bytes, uint32_t* out, warp_state& ws) {
+constexpr uint32_t kClassBytes = 64;  // class_info[8] between the length table and the rings
+
+// Stages the 4-bit log2(length) table and the class table into shared memory and carves the
+// calling warp's rings. Returns the class table.
+__device__ __forceinline__ const class_info* cta_setup(const dint_dict_view& dv, uint32_t lut_bytes, const uint8_t* in,
+                                                       uint64_t in_bytes, uint32_t* out, warp_state& ws) {
     const uint4* src = reinterpret_cast<const uint4*>(dv.lens);
     uint4* dst = reinterpret_cast<uint4*>(g_smem);
     for (uint32_t i = threadIdx.x; i < lut_bytes / 16; i += blockDim.x) dst[i] = __ldg(src + i);
-    uint8_t* mine = g_smem + lut_bytes + (threadIdx.x >> 5) * kWarpSmem;
+    class_info* classes = reinterpret_cast<class_info*>(g_smem + lut_bytes);
+    if (threadIdx.x < 8) {
+        const uint32_t c = threadIdx.x;
+        class_info ci = {0, 0};
+        if (c < dv.n_classes) {
+            ci.row_base = dv.class_base[c];
+            ci.rows = (c + 1 < dv.n_classes ? dv.class_base[c + 1] : dv.n_rows) - ci.row_base;
+        }
+        classes[c] = ci;
+    }
+    uint8_t* mine = g_smem + lut_bytes + kClassBytes + (threadIdx.x >> 5) * kWarpSmem;
     ws.stage = reinterpret_cast<uint32_t*>(mine);
     ws.inb = mine + kStageInts * 4;
     for (uint32_t i = lane_id(); i < kStageInts / 4; i += 32) reinterpret_cast<uint4*>(ws.stage)[i] = make_uint4(0, 0, 0, 0);
@@ -55,31 +68,30 @@ __device__ __forceinline__ void cta_setup(const dint_dict_view& dv, uint32_t lut
     ws.flushed = 0;
     ws.staged = 0;
     ws.acc = 0;
+    ws.anchor = 0;
     ws.win_end = 0;
     ws.safe_end = 0;
+    ws.lo_rel = 0;
+    ws.hi_rel = 0;
     const uint64_t a = reinterpret_cast<uint64_t>(in);
     ws.in_lo = a & ~uint64_t(15);
     ws.in_hi = (a + in_bytes + 15) & ~uint64_t(15);
     ws.vec_ok = (reinterpret_cast<uint64_t>(out) & 15) == 0;
     __syncthreads();
+    return classes;
 }
 
-__device__ __forceinline__ uint64_t shfl64(uint64_t v, int src) {
-    const uint32_t lo = __shfl_sync(FULL, uint32_t(v), src), hi = __shfl_sync(FULL, uint32_t(v >> 32), src);
-    return (uint64_t(hi) << 32) | lo;
-}
-
-// vroom path: one warp per work unit (a run of consecutive segments with contiguous output).
-template <int MODE>
+// vroom path: one warp per work unit (<= 32 consecutive segments, normally contiguous in the
+// file and in the output, which makes the whole unit one flat run).
+template <bool MULTI, int MODE>
 __global__ void __launch_bounds__(kThreads, 2)
-decode_units_kernel(dint_dict_view dv, uint32_t lut_bytes, int multi, const uint8_t* __restrict__ in, uint64_t in_bytes,
+decode_units_kernel(dint_dict_view dv, uint32_t lut_bytes, const uint8_t* __restrict__ in, uint64_t in_bytes,
                     const dint_segment* __restrict__ segs, uint64_t n_segs, const uint32_t* __restrict__ unit_first,
                     uint64_t n_units, uint32_t* __restrict__ out) {
     warp_state ws;
-    cta_setup(dv, lut_bytes, in, in_bytes, out, ws);
+    const class_info* classes = cta_setup(dv, lut_bytes, in, in_bytes, out, ws);
     const unsigned lane = lane_id();
     const uint64_t in_base = reinterpret_cast<uint64_t>(in);
-    const uint64_t hard_hi = ws.in_hi;
     const uint64_t gwarp = uint64_t(blockIdx.x) * kWarpsPerCta + (threadIdx.x >> 5);
     const uint64_t nwarps = uint64_t(gridDim.x) * kWarpsPerCta;
     for (uint64_t u = gwarp; u < n_units; u += nwarps) {
@@ -92,39 +104,87 @@ decode_units_kernel(dint_dict_view dv, uint32_t lut_bytes, int multi, const uint
             s1 = min(n_segs, s0 + kImplicitUnit);
         }
         ws.staged = 0;
-        ws.in_hi = 0;
-        uint32_t tail = 0;  // docid of the last integer of the previous segment
+        uint32_t tail = 0;  // docid of the last integer decoded so far
         for (uint64_t sb = s0; sb < s1; sb += 32) {
-            const uint32_t cnt = uint32_t(min(uint64_t(32), s1 - sb));
+            uint32_t cnt = uint32_t(min(uint64_t(32), s1 - sb));
             dint_segment sg = {0, 0, 0, 0, 0, 0};
             if (lane < cnt) sg = segs[sb + lane];
-            // bytes this batch can touch: lets the input ring stop at the end of the unit
-            uint64_t endb = 0;
-            if (lane < cnt) endb = sg.in_len ? sg.in_off + sg.in_len + 8 : in_bytes;
-#pragma unroll
-            for (int o = 16; o; o >>= 1) endb = max(endb, shfl64(endb, lane ^ o));
-            const uint64_t want_hi = min(hard_hi, (in_base + endb + 15) & ~uint64_t(15));
-            if (want_hi > ws.in_hi) {
-                ws.in_hi = want_hi;
-                ws.win_end = 0;  // chunks loaded under the smaller bound are incomplete
-            }
-            for (uint32_t k = 0; k < cnt; ++k) {
-                const uint64_t in_off = shfl64(sg.in_off, k), out_off = shfl64(sg.out_off, k);
-                const uint32_t n = __shfl_sync(FULL, sg.n, k), doc_base = __shfl_sync(FULL, sg.doc_base, k);
-                const uint32_t doc_sum = __shfl_sync(FULL, sg.doc_sum, k);
-                if (ws.staged && out_off != ws.flushed + ws.staged) {  // output not contiguous: start over
+            while (cnt) {
+                // ---- the longest prefix of the batch that forms one flat run -----------------------
+                const bool has = lane < cnt;
+                const uint64_t out0 = shfl64(sg.out_off, 0), in0 = shfl64(sg.in_off, 0);
+                const uint32_t n_incl = warp_inclusive_scan(has ? sg.n : 0u, lane);
+                const uint64_t my_end = sg.in_off + sg.in_len;
+                const uint64_t prev_end = shfl64(my_end, lane ? int(lane) - 1 : 0);
+                bool ok = sg.in_len != 0 && sg.n != 0 && my_end <= in_bytes && my_end - in0 < kMaxRunBytes &&
+                          sg.out_off == out0 + (n_incl - sg.n);
+                if (lane) ok = ok && sg.in_off >= prev_end && sg.in_off - prev_end <= 12;  // vroom list headers only
+                const uint32_t bad = __ballot_sync(FULL, has && !ok);
+                const uint32_t r = bad ? uint32_t(__ffs(bad) - 1) : cnt;
+                const uint32_t doc_base0 = __shfl_sync(FULL, sg.doc_base, 0);
+                if (ws.staged && out0 != ws.flushed + ws.staged) {  // output not contiguous: start over
                     ws.flush_all<MODE>(lane);
                     __syncwarp();
                 }
-                uint32_t corr = 0;
+                uint32_t corr0 = 0;
                 if (!ws.staged) {
-                    ws.flushed = out_off;
-                    ws.acc = doc_base - 1u;  // docid[i] = acc + sum_{j<=i} (v_j + 1)
-                } else if (MODE == OUT_DOCIDS) {
-                    corr = doc_base - 1u - tail;  // re-base the running prefix sum at the list boundary
+                    ws.flushed = out0;
+                    ws.acc = doc_base0 - 1u;  // docid[i] = acc + sum_{j<=i} (v_j + 1)
+                } else {
+                    corr0 = doc_base0 - 1u - tail;  // re-base the running prefix sum at the list boundary
                 }
-                tail = doc_base - 1u + doc_sum;
-                decode_one<MODE>(ws, dv, g_smem, multi != 0, in_base + in_off, n, corr, lane);
+                if (r == 0) {
+                    // segment 0 has no usable byte length (or is empty): walk it alone, like the reference
+                    const uint32_t n0 = __shfl_sync(FULL, sg.n, 0);
+                    if (corr0) {  // keep it simple: no carried prefix into a segment of unknown length
+                        ws.flush_all<MODE>(lane);
+                        __syncwarp();
+                        ws.flushed = out0;
+                        ws.acc = doc_base0 - 1u;
+                    }
+                    if (in0 < in_bytes) decode_one<MODE>(ws, dv.rows, g_smem, classes, dv.n_classes, MULTI, in_base + in0, n0, lane);
+                    ws.flush_all<MODE>(lane);
+                    __syncwarp();
+                } else {
+                    const bool hasr = lane < r;
+                    seg_lane sl;
+                    uint32_t hdr = 0, narrow = 0;
+                    sl.pk = 0;
+                    sl.rows = dv.n_rows;
+                    if (MULTI) {
+                        const uint32_t sel = hasr ? uint32_t(__ldg(in + sg.in_off)) : 0u;
+                        const bool wide = sel < dint::kSelectors;
+                        const class_info ci = classes[min(wide ? sel : sel - dint::kSelectors, dv.n_classes - 1u)];
+                        narrow = wide ? 0u : 1u;
+                        hdr = 1;
+                        sl.pk = ci.row_base | (narrow << 31);
+                        sl.rows = wide ? ci.rows : min(ci.rows, 256u);
+                    }
+                    const uint32_t ns = hasr ? (sg.in_len - hdr) >> (narrow ? 0 : 1) : 0u;
+                    const uint32_t cs_incl = warp_inclusive_scan(ns, lane);
+                    sl.cs = cs_incl - ns;
+                    const uint32_t S = __shfl_sync(FULL, cs_incl, 31);
+                    const uint32_t N = __shfl_sync(FULL, n_incl, r - 1);
+                    const uint64_t run_end = shfl64(my_end, r - 1);
+                    const uint32_t a0 = ws.set_anchor(in_base + in0, in_base + run_end + 8);
+                    sl.ab = a0 + uint32_t(sg.in_off - in0) + hdr;
+                    const uint32_t my_tail = sg.doc_base - 1u + sg.doc_sum;
+                    const uint32_t prev_tail = __shfl_up_sync(FULL, my_tail, 1);
+                    sl.corr = lane ? sg.doc_base - 1u - prev_tail : corr0;
+                    decode_run<MULTI, MODE>(ws, dv.rows, g_smem, sl, r, S, N, lane);
+                    tail = __shfl_sync(FULL, my_tail, r - 1);
+                }
+                // ---- drop the segments just decoded ---------------------------------------------------
+                const uint32_t drop = r ? r : 1;
+                cnt -= drop;
+                if (cnt) {
+                    sg.in_off = shfl64(sg.in_off, (lane + drop) & 31);
+                    sg.out_off = shfl64(sg.out_off, (lane + drop) & 31);
+                    sg.n = __shfl_sync(FULL, sg.n, (lane + drop) & 31);
+                    sg.doc_base = __shfl_sync(FULL, sg.doc_base, (lane + drop) & 31);
+                    sg.in_len = __shfl_sync(FULL, sg.in_len, (lane + drop) & 31);
+                    sg.doc_sum = __shfl_sync(FULL, sg.doc_sum, (lane + drop) & 31);
+                }
             }
         }
         ws.flush_all<MODE>(lane);
@@ -141,7 +201,7 @@ index_docs_kernel(dint_dict_view dv, uint32_t lut_bytes, int multi, const uint8_
                   uint64_t lists_bytes, const dint_block* __restrict__ blocks, uint64_t n_blocks, uint32_t block_size,
                   uint32_t* __restrict__ docids, uint32_t* __restrict__ freqs) {
     warp_state ws;
-    cta_setup(dv, lut_bytes, lists, lists_bytes, docids, ws);
+    const class_info* classes = cta_setup(dv, lut_bytes, lists, lists_bytes, docids, ws);
     const unsigned lane = lane_id();
     const uint64_t base = reinterpret_cast<uint64_t>(lists);
     const uint64_t gwarp = uint64_t(blockIdx.x) * kWarpsPerCta + (threadIdx.x >> 5);
@@ -152,7 +212,8 @@ index_docs_kernel(dint_dict_view dv, uint32_t lut_bytes, int multi, const uint8_
         ws.staged = 0;
         ws.flushed = b.out_off;
         ws.acc = b.cur_base - 1u;  // docid[0] = buf[0] + cur_base (dict_posting_list.hpp:304)
-        const uint64_t end = decode_one<MODE>(ws, dv, g_smem, multi != 0, base + b.in_off, b.size, 0, lane);
+        const uint64_t end = decode_one<MODE>(ws, dv.rows, g_smem, classes, dv.n_classes, multi != 0, base + b.in_off,
+                                              b.size, lane);
         if (MODE != OUT_SKIP) {
             ws.flush_all<MODE>(lane);
             __syncwarp();
@@ -167,7 +228,7 @@ index_freqs_kernel(dint_dict_view dv, uint32_t lut_bytes, int multi, const uint8
                    uint64_t lists_bytes, const dint_block* __restrict__ blocks, uint64_t n_blocks, uint32_t block_size,
                    uint32_t* __restrict__ freqs) {
     warp_state ws;
-    cta_setup(dv, lut_bytes, lists, lists_bytes, freqs, ws);
+    const class_info* classes = cta_setup(dv, lut_bytes, lists, lists_bytes, freqs, ws);
     const unsigned lane = lane_id();
     const uint64_t base = reinterpret_cast<uint64_t>(lists);
     const uint64_t gwarp = uint64_t(blockIdx.x) * kWarpsPerCta + (threadIdx.x >> 5);
@@ -179,7 +240,8 @@ index_freqs_kernel(dint_dict_view dv, uint32_t lut_bytes, int multi, const uint8
         __syncwarp();
         ws.staged = 0;
         ws.flushed = b.out_off;
-        decode_one<OUT_FREQS>(ws, dv, g_smem, multi != 0, base + b.in_off + docs_len, b.size, 0, lane);
+        decode_one<OUT_FREQS>(ws, dv.rows, g_smem, classes, dv.n_classes, multi != 0, base + b.in_off + docs_len, b.size,
+                              lane);
         ws.flush_all<OUT_FREQS>(lane);
         __syncwarp();
     }
@@ -340,16 +402,16 @@ __global__ void __launch_bounds__(32)
 decode_list_kernel(dint_dict_view dv, uint32_t lut_bytes, int multi, const uint8_t* __restrict__ in, uint64_t in_bytes,
                    uint32_t n, uint32_t block_size, uint32_t* __restrict__ out, uint64_t* __restrict__ consumed) {
     warp_state ws;
-    cta_setup(dv, lut_bytes, in, in_bytes, out, ws);
+    const class_info* classes = cta_setup(dv, lut_bytes, in, in_bytes, out, ws);
     const unsigned lane = lane_id();
     const uint64_t base = reinterpret_cast<uint64_t>(in);
     uint64_t addr = base;
     ws.flushed = 0;
     if (!multi) {
-        addr = decode_one<OUT_RAW>(ws, dv, g_smem, false, addr, n, 0, lane);
+        addr = decode_one<OUT_RAW>(ws, dv.rows, g_smem, classes, dv.n_classes, false, addr, n, lane);
     } else {
         for (uint32_t done = 0; done < n; done += block_size)  // vroom_env/dint_codecs.hpp:525-534
-            addr = decode_one<OUT_RAW>(ws, dv, g_smem, true, addr, min(block_size, n - done), 0, lane);
+            addr = decode_one<OUT_RAW>(ws, dv.rows, g_smem, classes, dv.n_classes, true, addr, min(block_size, n - done), lane);
     }
     ws.flush_all<OUT_RAW>(lane);
     if (lane == 0) *consumed = addr - base;
@@ -378,7 +440,9 @@ int get_device_info(int device, device_info* di) {
 
 // 4-bit log2(length) per dictionary row, padded to 16 bytes
 uint32_t lut_bytes_of(const dint_dict* d) { return ((d->n_rows + 1u) / 2u + 15u) & ~15u; }
-size_t smem_bytes_of(const dint_dict* d, int warps) { return size_t(lut_bytes_of(d)) + size_t(warps) * kWarpSmem; }
+size_t smem_bytes_of(const dint_dict* d, int warps) {
+    return size_t(lut_bytes_of(d)) + kClassBytes + size_t(warps) * kWarpSmem;
+}
 
 // persistent grid: as many CTAs as fit (shared memory bound), never more than the work needs
 template <typename K>
@@ -487,18 +551,24 @@ int dint_decode_units(const dint_dict* d, const uint8_t* d_in, size_t in_bytes, 
     if (n_units == 0) return DINT_OK;
     device_guard g(d->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int multi = d->kind == DINT_DICT_MULTI;
+    const bool multi = d->kind == DINT_DICT_MULTI;
     int grid = 0;
     size_t smem = 0;
     int rc;
-#define LAUNCH_SEG(M)                                                                                              \
-    rc = plan_grid(decode_units_kernel<M>, d, n_units, &grid, &smem);                                              \
+#define LAUNCH_SEG(MU, M)                                                                                          \
+    rc = plan_grid(decode_units_kernel<MU, M>, d, n_units, &grid, &smem);                                          \
     if (rc) return rc;                                                                                             \
-    decode_units_kernel<M><<<grid, kThreads, smem, st>>>(d->view(), lut_bytes_of(d), multi, d_in, in_bytes, d_segs,    \
-                                                        n_segs, d_unit_first, n_units, d_out);
-    if (mode == DINT_MODE_RAW) { LAUNCH_SEG(OUT_RAW) }
-    else if (mode == DINT_MODE_DOCIDS) { LAUNCH_SEG(OUT_DOCIDS) }
-    else { LAUNCH_SEG(OUT_FREQS) }
+    decode_units_kernel<MU, M><<<grid, kThreads, smem, st>>>(d->view(), lut_bytes_of(d), d_in, in_bytes, d_segs,      \
+                                                            n_segs, d_unit_first, n_units, d_out);
+    if (multi) {
+        if (mode == DINT_MODE_RAW) { LAUNCH_SEG(true, OUT_RAW) }
+        else if (mode == DINT_MODE_DOCIDS) { LAUNCH_SEG(true, OUT_DOCIDS) }
+        else { LAUNCH_SEG(true, OUT_FREQS) }
+    } else {
+        if (mode == DINT_MODE_RAW) { LAUNCH_SEG(false, OUT_RAW) }
+        else if (mode == DINT_MODE_DOCIDS) { LAUNCH_SEG(false, OUT_DOCIDS) }
+        else { LAUNCH_SEG(false, OUT_FREQS) }
+    }
 #undef LAUNCH_SEG
     ++g_launches;
     CUDA_TRY(cudaGetLastError());
