@@ -232,6 +232,36 @@ struct seg_lane {
     uint32_t corr;  // DOCIDS: added to the segment's first integer (re-bases the running prefix sum)
 };
 
+// Which of a tile's symbols are exception payload. Z / O: symbols equal to 0 / 1; a 0 codeword is
+// followed by PZ payload symbols (a u16 value), a 1 codeword by PO (a u32 value); payload may
+// itself look like 0 / 1. `starts`: symbols known to be codewords (bit 0, segment starts).
+template <int PZ, int PO>
+__device__ __forceinline__ uint32_t payload_mask(uint32_t Z, uint32_t O, uint32_t starts) {
+    constexpr uint32_t MZ = (1u << PZ) - 1u, MO = (1u << PO) - 1u;
+    const uint32_t E = Z | O;
+    uint32_t reach = 0;
+#pragma unroll
+    for (int d = 1; d <= PZ; ++d) reach |= Z << d;
+#pragma unroll
+    for (int d = 1; d <= PO; ++d) reach |= O << d;
+    const uint32_t A = E & (~reach | starts);  // candidates no other candidate can reach: codewords
+    const uint32_t az = A & Z, ao = A & O;
+    uint32_t P = 0;
+#pragma unroll
+    for (int d = 1; d <= PZ; ++d) P |= az << d;
+#pragma unroll
+    for (int d = 1; d <= PO; ++d) P |= ao << d;
+    P &= ~starts;
+    uint32_t c = E & ~A & ~P;
+    while (c) {  // warp-uniform: a real exception codeword right behind 0/1-valued payload
+        const uint32_t bit = c & (0u - c);
+        const uint32_t m = (Z & bit) ? MZ : MO;
+        P |= (m * bit * 2u) & ~starts;
+        c = E & ~A & ~P & ~(bit * 2u - 1u);
+    }
+    return P;
+}
+
 // Decodes a run of `cnt` (<= 32) segments whose parameters sit in lanes 0..cnt-1 of `sl`.
 //   S  flat symbols in the run (kUnknownLen: a single segment of unknown byte length; the walk
 //      then stops after exactly N integers, like the reference's `i != n` loop)
@@ -244,74 +274,83 @@ __device__ __forceinline__ uint32_t decode_run(warp_state& ws, const uint32_t* _
     uint32_t F = 0, produced = 0;
     const bool has = lane < cnt;
     const unsigned le = lanemask_le();
+    // parameters of the segment the tile starts in, broadcast to every lane
+    uint32_t ck = 0;
+    uint32_t c_cs = __shfl_sync(FULL, sl.cs, 0), c_ab = __shfl_sync(FULL, sl.ab, 0);
+    uint32_t c_pk = __shfl_sync(FULL, sl.pk, 0), c_rows = __shfl_sync(FULL, sl.rows, 0);
     while (produced < N && F < S) {
         // ---- which segment does each lane's symbol belong to ------------------------------------
-        const uint32_t kcur = __popc(__ballot_sync(FULL, has && sl.cs <= F)) - 1u;
-        const uint32_t rel = sl.cs - F;
-        const uint32_t H = __reduce_or_sync(FULL, (has && rel - 1u < 31u) ? (1u << rel) : 0u);
-        const uint32_t kl = kcur + __popc(H & le) - ((H & 1u) ? 1u : 0u);
-        const uint32_t my_cs = __shfl_sync(FULL, sl.cs, kl), my_ab = __shfl_sync(FULL, sl.ab, kl);
-        const uint32_t my_pk = __shfl_sync(FULL, sl.pk, kl), my_rows = __shfl_sync(FULL, sl.rows, kl);
-        const bool narrow = MULTI && (my_pk >> 31);
-        const uint32_t fi = F + lane;
-        const uint32_t a = my_ab + (narrow ? 1u : 2u) * (fi - my_cs);
-        // bytes the tile can touch: from lane 0's symbol to lane 31's symbol + the widest payload
-        const uint32_t a0 = __shfl_sync(FULL, a, 0), a31 = __shfl_sync(FULL, a, 31);
-        ws.ensure_input(a0, min(a31 - a0 + 8u, uint32_t(kChunk)), lane);
-        uint32_t sym = ws.rb(a);
-        if (!narrow) sym |= ws.rb(a + 1) << 8;
-
-        // ---- which symbols are codewords ----------------------------------------------------
-        const uint32_t live = S - F >= 32u ? FULL : ((1u << (S - F)) - 1u);  // symbols inside the run
-        const uint32_t Z = __ballot_sync(FULL, sym == 0u) & live;
-        const uint32_t O = __ballot_sync(FULL, sym == 1u) & live;
-        const uint32_t E = Z | O;
-        uint32_t P = 0;  // payload symbols of this tile
-        if (E) {
-            // a 0 codeword is followed by a u16 value, a 1 codeword by a u32 value
-            const uint32_t Nm = MULTI ? __ballot_sync(FULL, narrow) : 0u;
-            const uint32_t zw = Z & ~Nm, ow = O & ~Nm, zn = Z & Nm, on = O & Nm;
-            const uint32_t starts = H | 1u;  // a segment always starts with a codeword
-            uint32_t reach = (zw << 1) | (ow << 1) | (ow << 2);
-            if (MULTI) reach |= (zn << 1) | (zn << 2) | (on << 1) | (on << 2) | (on << 3) | (on << 4);
-            const uint32_t A = E & (~reach | starts);  // certainly codewords
-            const uint32_t azw = A & zw, aow = A & ow;
-            P = (azw << 1) | (aow << 1) | (aow << 2);
-            if (MULTI) {
-                const uint32_t azn = A & zn, aon = A & on;
-                P |= (azn << 1) | (azn << 2) | (aon << 1) | (aon << 2) | (aon << 3) | (aon << 4);
-            }
-            P &= ~starts;
-            uint32_t c = E & ~A & ~P;
-            while (c) {  // warp-uniform: a real exception codeword right behind 0/1-valued payload
-                const int j = __ffs(c) - 1;
-                const bool jn = MULTI && ((Nm >> j) & 1u);
-                const uint32_t pcnt = ((Z >> j) & 1u) ? (jn ? 2u : 1u) : (jn ? 4u : 2u);
-                P |= ((((1u << pcnt) - 1u) << j) << 1) & ~starts;
-                c = E & ~A & ~P & ~((2u << j) - 1u);
+        uint32_t H = 0;  // segments that start inside the tile (not at its first symbol)
+        if (cnt > 1) {
+            const uint32_t kcur = __popc(__ballot_sync(FULL, has && sl.cs <= F)) - 1u;
+            const uint32_t rel = sl.cs - F;
+            H = __reduce_or_sync(FULL, (has && rel - 1u < 31u) ? (1u << rel) : 0u);
+            if (kcur != ck) {
+                ck = kcur;
+                c_cs = __shfl_sync(FULL, sl.cs, ck);
+                c_ab = __shfl_sync(FULL, sl.ab, ck);
+                c_pk = __shfl_sync(FULL, sl.pk, ck);
+                c_rows = __shfl_sync(FULL, sl.rows, ck);
             }
         }
+        uint32_t my_cs = c_cs, my_ab = c_ab, my_pk = c_pk, my_rows = c_rows, kl = ck;
+        uint32_t live = S - F >= 32u ? FULL : ((1u << (S - F)) - 1u);  // symbols inside the run
+        const bool nar = MULTI && (c_pk >> 31);  // the tile's symbol size (uniform)
+        const uint32_t sz = nar ? 1u : 2u;
+        const uint32_t fi = F + lane;
+        uint32_t a, sym;
+        if (H == 0) {
+            a = c_ab + sz * (fi - c_cs);
+            const uint32_t a0 = c_ab + sz * (F - c_cs);
+            ws.ensure_input(a0, 32u * sz + 8u, lane);
+            if (nar) sym = ws.rb(a);
+            else if ((a0 & 1u) == 0) sym = *reinterpret_cast<const uint16_t*>(ws.inb + (a & (kInBytes - 1)));
+            else sym = ws.rb(a) | (ws.rb(a + 1) << 8);
+        } else {
+            kl = ck + __popc(H & le);
+            my_cs = __shfl_sync(FULL, sl.cs, kl);
+            my_ab = __shfl_sync(FULL, sl.ab, kl);
+            my_pk = __shfl_sync(FULL, sl.pk, kl);
+            my_rows = __shfl_sync(FULL, sl.rows, kl);
+            if (MULTI) {
+                // one symbol size per tile: stop in front of the first segment of the other size
+                const uint32_t other = __ballot_sync(FULL, (my_pk >> 31) != (c_pk >> 31));
+                if (other) live &= (1u << (__ffs(other) - 1)) - 1u;
+            }
+            a = my_ab + sz * (fi - my_cs);
+            // bytes the tile can touch: from lane 0's symbol to lane 31's symbol + the widest payload
+            const uint32_t a0 = __shfl_sync(FULL, a, 0), a31 = __shfl_sync(FULL, a, 31);
+            ws.ensure_input(a0, min(a31 - a0 + 8u, uint32_t(kChunk)), lane);
+            sym = ws.rb(a);
+            if (!nar) sym |= ws.rb(a + 1) << 8;
+        }
+
+        // ---- which symbols are codewords ----------------------------------------------------
+        const uint32_t Z = __ballot_sync(FULL, sym == 0u) & live;
+        const uint32_t O = __ballot_sync(FULL, sym == 1u) & live;
+        uint32_t P = 0;  // payload symbols of this tile
+        if (Z | O) P = nar ? payload_mask<2, 4>(Z, O, H | 1u) : payload_mask<1, 2>(Z, O, H | 1u);
         const bool iscw = (((live & ~P) >> lane) & 1u) != 0u;
 
         // ---- lengths, offsets, how much of the tile is taken ----------------------------------
-        uint32_t len = iscw ? 1u : 0u;
-        uint32_t row = 0;
-        if (iscw && sym >= 2u) {
-            row = (my_pk & 0x7FFFFFFFu) + min(sym, my_rows - 1u);
-            len = 1u << ((uint32_t(lut[row >> 1]) >> ((row & 1u) * 4u)) & 15u);
+        uint32_t len = 0, row = 0, step = 1;
+        if (iscw) {
+            len = 1;
+            if (sym >= 2u) {
+                row = (my_pk & 0x7FFFFFFFu) + min(sym, my_rows - 1u);
+                len = 1u << ((uint32_t(lut[row >> 1]) >> ((row & 1u) * 4u)) & 15u);
+            } else {
+                step = 1u + (4u >> (sym == 0u ? 1 : 0) >> (nar ? 0 : 1));  // + payload symbols
+            }
         }
         const uint32_t e = warp_inclusive_scan(len, lane);
         const uint32_t s = e - len;
         uint32_t limit = N - produced;
         if (MODE != OUT_SKIP) limit = min(limit, kStageInts - ((uint32_t(ws.flushed) & (kGroup - 1)) + ws.staged));
         const bool valid = iscw && e <= limit;
-        const uint32_t V = __ballot_sync(FULL, valid);
-        if (V == 0) break;  // malformed stream (a codeword straddles the end of the run)
-        const int last = 31 - __clz(V);
-        const uint32_t T = __shfl_sync(FULL, e, last);
-        const uint32_t lastsym = __shfl_sync(FULL, sym, last);
-        const bool lastn = MULTI && __shfl_sync(FULL, narrow ? 1u : 0u, last);
-        const uint32_t extra = lastsym == 0u ? (lastn ? 2u : 1u) : (lastsym == 1u ? (lastn ? 4u : 2u) : 0u);
+        const uint32_t T = __reduce_max_sync(FULL, valid ? e : 0u);
+        if (T == 0) break;  // malformed stream (a codeword straddles the end of the run)
+        const uint32_t adv = __reduce_max_sync(FULL, valid ? lane + step : 0u);  // symbols consumed
 
         // ---- scatter into the staging ring ------------------------------------------------------
         if (MODE != OUT_SKIP) {
@@ -322,11 +361,11 @@ __device__ __forceinline__ uint32_t decode_run(warp_state& ws, const uint32_t* _
             uint4 r0 = make_uint4(0, 0, 0, 0);
             if (L) r0 = __ldg(rp);
             if (valid && sym < 2u) {
-                const uint32_t pa = a + (narrow ? 1u : 2u);
+                const uint32_t pa = a + sz;
                 r0.x = ws.rb(pa) | (ws.rb(pa + 1) << 8);
                 if (sym == 1u) r0.x |= (ws.rb(pa + 2) << 16) | (ws.rb(pa + 3) << 24);
             }
-            if (MODE == OUT_DOCIDS) {
+            if (MODE == OUT_DOCIDS && (H || F == c_cs)) {  // a segment starts in this tile: re-base
                 const uint32_t my_corr = __shfl_sync(FULL, sl.corr, kl);
                 if (fi == my_cs) r0.x += my_corr;
             }
@@ -361,11 +400,13 @@ __device__ __forceinline__ uint32_t decode_run(warp_state& ws, const uint32_t* _
             }
             ws.staged += T;
             __syncwarp();
-            ws.flush_full<MODE>(lane);
-            __syncwarp();
+            if ((uint32_t(ws.flushed) & (kGroup - 1)) + ws.staged >= uint32_t(kGroup)) {
+                ws.flush_full<MODE>(lane);
+                __syncwarp();
+            }
         }
         produced += T;
-        F += uint32_t(last) + 1u + extra;
+        F += adv;
     }
     return F;
 }

@@ -83,8 +83,8 @@ __device__ __forceinline__ const class_info* cta_setup(const dint_dict_view& dv,
 
 // vroom path: one warp per work unit (<= 32 consecutive segments, normally contiguous in the
 // file and in the output, which makes the whole unit one flat run).
-template <bool MULTI, int MODE>
-__global__ void __launch_bounds__(kThreads, 2)
+template <bool MULTI, int MODE, int W>
+__global__ void __launch_bounds__(W * 32, W == 16 ? 2 : 1)
 decode_units_kernel(dint_dict_view dv, uint32_t lut_bytes, const uint8_t* __restrict__ in, uint64_t in_bytes,
                     const dint_segment* __restrict__ segs, uint64_t n_segs, const uint32_t* __restrict__ unit_first,
                     uint64_t n_units, uint32_t* __restrict__ out) {
@@ -92,8 +92,8 @@ decode_units_kernel(dint_dict_view dv, uint32_t lut_bytes, const uint8_t* __rest
     const class_info* classes = cta_setup(dv, lut_bytes, in, in_bytes, out, ws);
     const unsigned lane = lane_id();
     const uint64_t in_base = reinterpret_cast<uint64_t>(in);
-    const uint64_t gwarp = uint64_t(blockIdx.x) * kWarpsPerCta + (threadIdx.x >> 5);
-    const uint64_t nwarps = uint64_t(gridDim.x) * kWarpsPerCta;
+    const uint64_t gwarp = uint64_t(blockIdx.x) * W + (threadIdx.x >> 5);
+    const uint64_t nwarps = uint64_t(gridDim.x) * W;
     for (uint64_t u = gwarp; u < n_units; u += nwarps) {
         uint64_t s0, s1;
         if (unit_first) {
@@ -446,20 +446,20 @@ size_t smem_bytes_of(const dint_dict* d, int warps) {
 
 // persistent grid: as many CTAs as fit (shared memory bound), never more than the work needs
 template <typename K>
-int plan_grid(K kernel, const dint_dict* d, uint64_t n_units, int* grid, size_t* smem) {
+int plan_grid(K kernel, const dint_dict* d, uint64_t n_units, int* grid, size_t* smem, int warps = kWarpsPerCta) {
     device_info di;
     int rc = get_device_info(d->device, &di);
     if (rc) return rc;
-    *smem = smem_bytes_of(d, kWarpsPerCta);
+    *smem = smem_bytes_of(d, warps);
     if (*smem > size_t(di.max_smem_optin)) {
         dint::set_error("dictionary length table does not fit in shared memory");
         return DINT_E_ARG;
     }
     CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(*smem)));
     int per_sm = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, *smem));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, warps * 32, *smem));
     if (per_sm < 1) per_sm = 1;
-    uint64_t want = (n_units + kWarpsPerCta - 1) / kWarpsPerCta;
+    uint64_t want = (n_units + warps - 1) / warps;
     uint64_t cap = uint64_t(di.sms) * per_sm;
     *grid = int(std::max<uint64_t>(1, std::min(want, cap)));
     return DINT_OK;
@@ -555,19 +555,21 @@ int dint_decode_units(const dint_dict* d, const uint8_t* d_in, size_t in_bytes, 
     int grid = 0;
     size_t smem = 0;
     int rc;
-#define LAUNCH_SEG(MU, M)                                                                                          \
-    rc = plan_grid(decode_units_kernel<MU, M>, d, n_units, &grid, &smem);                                          \
+    // single dictionaries: 32 KB table, two 16-warp CTAs per SM; multi_packed: ~70 KB table shared by
+    // one 32-warp CTA per SM
+#define LAUNCH_SEG(MU, M, W)                                                                                       \
+    rc = plan_grid(decode_units_kernel<MU, M, W>, d, n_units, &grid, &smem, W);                                    \
     if (rc) return rc;                                                                                             \
-    decode_units_kernel<MU, M><<<grid, kThreads, smem, st>>>(d->view(), lut_bytes_of(d), d_in, in_bytes, d_segs,      \
-                                                            n_segs, d_unit_first, n_units, d_out);
+    decode_units_kernel<MU, M, W><<<grid, W * 32, smem, st>>>(d->view(), lut_bytes_of(d), d_in, in_bytes, d_segs,    \
+                                                             n_segs, d_unit_first, n_units, d_out);
     if (multi) {
-        if (mode == DINT_MODE_RAW) { LAUNCH_SEG(true, OUT_RAW) }
-        else if (mode == DINT_MODE_DOCIDS) { LAUNCH_SEG(true, OUT_DOCIDS) }
-        else { LAUNCH_SEG(true, OUT_FREQS) }
+        if (mode == DINT_MODE_RAW) { LAUNCH_SEG(true, OUT_RAW, 32) }
+        else if (mode == DINT_MODE_DOCIDS) { LAUNCH_SEG(true, OUT_DOCIDS, 32) }
+        else { LAUNCH_SEG(true, OUT_FREQS, 32) }
     } else {
-        if (mode == DINT_MODE_RAW) { LAUNCH_SEG(false, OUT_RAW) }
-        else if (mode == DINT_MODE_DOCIDS) { LAUNCH_SEG(false, OUT_DOCIDS) }
-        else { LAUNCH_SEG(false, OUT_FREQS) }
+        if (mode == DINT_MODE_RAW) { LAUNCH_SEG(false, OUT_RAW, 16) }
+        else if (mode == DINT_MODE_DOCIDS) { LAUNCH_SEG(false, OUT_DOCIDS, 16) }
+        else { LAUNCH_SEG(false, OUT_FREQS, 16) }
     }
 #undef LAUNCH_SEG
     ++g_launches;

@@ -37,7 +37,8 @@ def main():
     launch = int(sys.argv[4]) if len(sys.argv) > 4 else 0
     rows = list(csv.reader(open(sass)))
     secs = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
-    secs = [i for i in secs if want in rows[i][1].replace("(int)", "")]
+    norm = lambda t: re.sub(r"\((int|bool)\)", "", t)
+    secs = [i for i in secs if want in norm(rows[i][1])]
     s = secs[launch]
     nxt = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name" and i > s]
     e = nxt[0] if nxt else len(rows)
@@ -47,7 +48,7 @@ def main():
     a0 = int(body[0][ia], 16)
     funcs = parse_dis(dis, want)
     name = re.sub(r"[^A-Za-z0-9]", "", rows[s][1].split("(")[0])
-    cand = [f for f in funcs if all(tok in f for tok in re.findall(r"[a-z_]{4,}", want))]
+    cand = [f for f in funcs if all(tok in f for tok in re.findall(r"[a-z_]{4,}", want.split("<")[0]))]
     # pick the function with the same instruction count
     f = [c for c in cand if len(funcs[c]) == len(body)]
     if not f:
