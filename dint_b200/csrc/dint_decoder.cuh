@@ -11,9 +11,11 @@
 //                is in flight while the current one is parsed. Ring offsets are the low bits
 //                of the global byte address, so any stream alignment works.
 //   tile         32 consecutive flat symbols (u16, or u8 in multi_packed's narrow blocks), one
-//                per lane, always starting on a codeword boundary. A __reduce_or_sync mask of
-//                the segment starts inside the tile + popc tells every lane which segment its
-//                symbol belongs to (lane k holds segment k's parameters, fetched by shuffle).
+//                per lane, always starting on a codeword boundary. While the tile lies inside
+//                one segment its parameters are warp-uniform; when a segment starts inside
+//                the tile, a __reduce_or_sync mask of the segment starts + popc tells every
+//                lane which segment its symbol belongs to (lane k holds segment k's
+//                parameters, fetched by shuffle).
 //                  * __ballot_sync masks of the symbols equal to 0 / 1 decide which symbols are
 //                    codewords and which are exception payload. Candidates that no earlier
 //                    candidate can reach are codewords for sure and are resolved bit-parallel;
@@ -37,6 +39,10 @@
 //                re-based by folding (next doc_base - previous list's last docid) into the
 //                first staged value, so the scan itself never has to be segmented.
 //
+// The kernel is bound by instruction issue, not by HBM (profiles/): the hot loop is written to
+// keep the per-tile instruction count down — 32-bit shared-memory addresses, predicated stores,
+// shuffle-with-predicate scans, warp-uniform control flow.
+//
 // Reference semantics reproduced (paths relative to the reference root):
 //   vroom_env/dint_codecs.hpp:37-107 (u16 loop), :574-609 (u8 loop), :521-536 (selector),
 //   include/dint/dint_codecs.hpp:13-49, 460-510, include/dint/*_dictionary.hpp copy().
@@ -56,6 +62,8 @@ constexpr int kGroup = 128;      // integers per flush round (one uint4 per lane
 constexpr int kWarpSmem = kStageInts * 4 + kInBytes;
 constexpr uint32_t kMaxRunBytes = 1u << 30;  // input span of one run (32-bit relative offsets)
 constexpr uint32_t kUnknownLen = 0xFFFFFFFFu;
+constexpr uint32_t kNoSegment = 0xFFFFFFFFu;
+constexpr uint32_t kTileLook = 80;  // bytes a single-segment tile may touch: 32 u16 symbols + payload, rounded up
 
 enum { OUT_RAW = 0, OUT_DOCIDS = 1, OUT_FREQS = 2, OUT_SKIP = 3 };
 
@@ -77,23 +85,73 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 __device__ __forceinline__ void st_stream(uint32_t* p, uint32_t v) { __stcs(p, v); }
 __device__ __forceinline__ void st_stream4(uint32_t* p, uint4 v) { __stcs(reinterpret_cast<uint4*>(p), v); }
 
-__device__ __forceinline__ uint32_t warp_inclusive_scan(uint32_t v, unsigned lane) {
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        uint32_t t = __shfl_up_sync(FULL, v, o);
-        if (lane >= unsigned(o)) v += t;
-    }
+// shared-memory accesses through 32-bit addresses (no generic-pointer arithmetic in the hot loop)
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
     return v;
 }
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
+    uint16_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+// words 1..3 of an entry of length L (1, 2 or >= 4) to consecutive ring slots
+__device__ __forceinline__ void sts_tail3(uint32_t a, uint32_t L, uint32_t y, uint32_t z, uint32_t w) {
+    asm volatile(
+        "{\n\t.reg .pred p1, p2;\n\t"
+        "setp.gt.u32 p1, %1, 1;\n\t"
+        "setp.gt.u32 p2, %1, 2;\n\t"
+        "@p1 st.shared.u32 [%0+4], %2;\n\t"
+        "@p2 st.shared.u32 [%0+8], %3;\n\t"
+        "@p2 st.shared.u32 [%0+12], %4;\n\t}" ::"r"(a),
+        "r"(L), "r"(y), "r"(z), "r"(w)
+        : "memory");
+}
+__device__ __forceinline__ void sts_4(uint32_t a, uint4 v) {
+    asm volatile(
+        "st.shared.u32 [%0], %1;\n\tst.shared.u32 [%0+4], %2;\n\tst.shared.u32 [%0+8], %3;\n\tst.shared.u32 [%0+12], %4;" ::"r"(a),
+        "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+        : "memory");
+}
+
+// inclusive warp scan: shfl.up hands back a predicate that is false for the lanes without a source
+#define DINT_SCAN_STEP(v, o)                                                        \
+    asm volatile(                                                                   \
+        "{\n\t.reg .pred p;\n\t.reg .u32 t;\n\t"                                    \
+        "shfl.sync.up.b32 t|p, %0, " #o ", 0, 0xffffffff;\n\t"                      \
+        "@p add.u32 %0, %0, t;\n\t}"                                                \
+        : "+r"(v))
+__device__ __forceinline__ uint32_t warp_inclusive_scan(uint32_t v) {
+    DINT_SCAN_STEP(v, 1);
+    DINT_SCAN_STEP(v, 2);
+    DINT_SCAN_STEP(v, 4);
+    DINT_SCAN_STEP(v, 8);
+    DINT_SCAN_STEP(v, 16);
+    return v;
+}
+#undef DINT_SCAN_STEP
 __device__ __forceinline__ uint64_t shfl64(uint64_t v, int src) {
     const uint32_t lo = __shfl_sync(FULL, uint32_t(v), src), hi = __shfl_sync(FULL, uint32_t(v >> 32), src);
     return (uint64_t(hi) << 32) | lo;
 }
+// tells the compiler a warp-uniform value is uniform (a REDUX result lives in a uniform register),
+// so that branches on it need no divergence guards around the warp-level instructions inside
+__device__ __forceinline__ uint32_t uniform(uint32_t v) { return __reduce_max_sync(FULL, v); }
 
 // Per-warp decoder state. Lives in registers; everything is warp-uniform.
 struct warp_state {
-    uint32_t* stage;    // [kStageInts] shared
-    uint8_t* inb;       // [kInBytes] shared
+    uint32_t stage_s;   // shared address of the output staging ring [kStageInts]
+    uint32_t inb_s;     // shared address of the input ring [kInBytes]
+    uint32_t lut_s;     // shared address of the 4-bit length table
     uint32_t* out;      // packed output array (global)
     uint64_t flushed;   // output index: everything below it (of this run) is in global memory
     uint32_t staged;    // integers sitting in the ring: [flushed, flushed + staged)
@@ -104,6 +162,7 @@ struct warp_state {
     uint64_t anchor;
     uint32_t win_end;   // ring holds rel addresses [win_end - kInBytes, win_end); 0 = nothing
     uint32_t safe_end;  // ... of which everything below safe_end has landed
+    uint32_t fast_end;  // single-segment tiles starting below this rel address need no housekeeping
     uint32_t lo_rel;    // 16-byte aligned bounds of the bytes this warp may read, rel
     uint32_t hi_rel;
     uint64_t in_lo;     // the same bounds as absolute addresses (whole input buffer)
@@ -120,17 +179,17 @@ struct warp_state {
         hi_rel = uint32_t(min(hi > anchor ? hi - anchor : uint64_t(0), uint64_t(0xFFFFFFF0u)));
         win_end = 0;
         safe_end = 0;
+        fast_end = 0;
         return uint32_t(g - anchor);
     }
     __device__ __forceinline__ void load_chunk(uint32_t base, unsigned lane) {
         const uint32_t x = base + 16u * lane;
-        const uint32_t so = smem_u32(inb) + (x & (kInBytes - 1));
+        const uint32_t so = inb_s + (x & (kInBytes - 1));
         if (x >= lo_rel && x < hi_rel) cp_async16(so, anchor + x);
         else asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(so), "r"(0u) : "memory");
     }
-    // make rel addresses [a, a + look) readable from the ring (look <= kChunk)
-    __device__ __forceinline__ void ensure_input(uint32_t a, uint32_t look, unsigned lane) {
-        if (a + look <= safe_end && a + kChunk <= win_end) return;  // the common case: one compare pair
+    // Input housekeeping: make rel addresses [a, a + look) readable from the ring (look <= kChunk).
+    __device__ __forceinline__ void refill(uint32_t a, uint32_t look, unsigned lane) {
         if (win_end == 0 || a + kInBytes < win_end || a >= win_end) {
             cp_async_wait_all();
             __syncwarp();
@@ -149,8 +208,21 @@ struct warp_state {
             __syncwarp();
             safe_end = win_end;
         }
+        // a single-segment tile at a' < fast_end has [a', a' + kTileLook) landed and is not yet in
+        // the newest chunk
+        const uint32_t f = min(safe_end - kTileLook, win_end - uint32_t(kChunk));
+        fast_end = safe_end > kTileLook ? f + 1u : 0u;
     }
-    __device__ __forceinline__ uint32_t rb(uint32_t a) const { return inb[a & (kInBytes - 1)]; }
+    __device__ __forceinline__ void ensure_input(uint32_t a, uint32_t look, unsigned lane) {
+        if (look > kTileLook || a >= fast_end) refill(a, look, lane);
+    }
+    __device__ __forceinline__ uint32_t rb(uint32_t a) const { return lds_u8(inb_s + (a & (kInBytes - 1))); }
+    // the little-endian u32 at ring address a (any alignment)
+    __device__ __forceinline__ uint32_t r32(uint32_t a) const {
+        const uint32_t w0 = lds_u32(inb_s + (a & (kInBytes - 4)));
+        const uint32_t w1 = lds_u32(inb_s + ((a + 4) & (kInBytes - 4)));
+        return __funnelshift_r(w0, w1, (a & 3u) * 8u);
+    }
 
     // ---- output side ---------------------------------------------------------------------
     // Flushes the (possibly partial) 128-aligned group that starts the staged data.
@@ -160,9 +232,10 @@ struct warp_state {
         const uint32_t hi = min(uint32_t(kGroup), lo + staged);
         const uint64_t gbase = flushed - lo;
         const uint32_t q = 4u * lane;
-        uint32_t* sp = stage + ((uint32_t(gbase) + q) & (kStageInts - 1));
-        uint4 v = *reinterpret_cast<uint4*>(sp);
-        *reinterpret_cast<uint4*>(sp) = make_uint4(0, 0, 0, 0);  // keep the ring zeroed behind us
+        const uint32_t sp = stage_s + (((uint32_t(gbase) + q) & (kStageInts - 1)) << 2);
+        uint4 v;
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(sp));
+        asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(sp), "r"(0u) : "memory");  // keep the ring zeroed
         uint32_t* gp = out + gbase + q;
         if (lo == 0 && hi == kGroup && vec_ok) {
             if (MODE == OUT_DOCIDS) {
@@ -170,7 +243,7 @@ struct warp_state {
                 v.y += v.x + 1u;
                 v.z += v.y + 1u;
                 v.w += v.z + 1u;
-                const uint32_t incl = warp_inclusive_scan(v.w, lane);
+                const uint32_t incl = warp_inclusive_scan(v.w);
                 const uint32_t base = acc + (incl - v.w);
                 acc += __shfl_sync(FULL, incl, 31);
                 v.x += base;
@@ -192,7 +265,7 @@ struct warp_state {
                 v.y = v.x + (l1 ? v.y + 1u : 0u);
                 v.z = v.y + (l2 ? v.z + 1u : 0u);
                 v.w = v.z + (l3 ? v.w + 1u : 0u);
-                const uint32_t incl = warp_inclusive_scan(v.w, lane);
+                const uint32_t incl = warp_inclusive_scan(v.w);
                 const uint32_t base = acc + (incl - v.w);
                 acc += __shfl_sync(FULL, incl, 31);
                 v.x += base;
@@ -268,135 +341,108 @@ __device__ __forceinline__ uint32_t payload_mask(uint32_t Z, uint32_t O, uint32_
 //   N  integers the run produces (never exceeded, whatever the bytes say)
 // Appends to the staging ring. Returns the flat symbol position one past the last consumed symbol.
 template <bool MULTI, int MODE>
-__device__ __forceinline__ uint32_t decode_run(warp_state& ws, const uint32_t* __restrict__ rows,
-                                               const uint8_t* __restrict__ lut, const seg_lane& sl, uint32_t cnt,
-                                               uint32_t S, uint32_t N, unsigned lane) {
-    uint32_t F = 0, produced = 0;
+__device__ __forceinline__ uint32_t decode_run(warp_state& ws, const uint32_t* __restrict__ rows, const seg_lane& sl,
+                                               uint32_t cnt_, uint32_t S_, uint32_t N_, unsigned lane) {
+    const uint32_t cnt = uniform(cnt_), S = uniform(S_);
+    uint32_t F = 0, remaining = uniform(N_);
     const bool has = lane < cnt;
-    const unsigned le = lanemask_le();
-    // parameters of the segment the tile starts in, broadcast to every lane
+    // parameters of the segment the tile starts in (segment ck), broadcast to every lane
     uint32_t ck = 0;
-    uint32_t c_cs = __shfl_sync(FULL, sl.cs, 0), c_ab = __shfl_sync(FULL, sl.ab, 0);
-    uint32_t c_pk = __shfl_sync(FULL, sl.pk, 0), c_rows = __shfl_sync(FULL, sl.rows, 0);
-    while (produced < N && F < S) {
-        // ---- which segment does each lane's symbol belong to ------------------------------------
-        uint32_t H = 0;  // segments that start inside the tile (not at its first symbol)
-        if (cnt > 1) {
-            const uint32_t kcur = __popc(__ballot_sync(FULL, has && sl.cs <= F)) - 1u;
-            const uint32_t rel = sl.cs - F;
-            H = __reduce_or_sync(FULL, (has && rel - 1u < 31u) ? (1u << rel) : 0u);
-            if (kcur != ck) {
-                ck = kcur;
-                c_cs = __shfl_sync(FULL, sl.cs, ck);
-                c_ab = __shfl_sync(FULL, sl.ab, ck);
-                c_pk = __shfl_sync(FULL, sl.pk, ck);
-                c_rows = __shfl_sync(FULL, sl.rows, ck);
-            }
-        }
-        uint32_t my_cs = c_cs, my_ab = c_ab, my_pk = c_pk, my_rows = c_rows, kl = ck;
-        uint32_t live = S - F >= 32u ? FULL : ((1u << (S - F)) - 1u);  // symbols inside the run
-        const bool nar = MULTI && (c_pk >> 31);  // the tile's symbol size (uniform)
-        const uint32_t sz = nar ? 1u : 2u;
-        const uint32_t fi = F + lane;
+    uint32_t c_cs = 0, c_ab = uniform(__shfl_sync(FULL, sl.ab, 0));
+    uint32_t c_pk = uniform(__shfl_sync(FULL, sl.pk, 0)), c_rows = uniform(__shfl_sync(FULL, sl.rows, 0));
+    uint32_t next_start = cnt > 1 ? uniform(__shfl_sync(FULL, sl.cs, 1)) : kNoSegment;  // first symbol of segment ck+1
+    while (remaining && F < S) {
+        const uint32_t szsh = (MULTI && (c_pk >> 31)) ? 0u : 1u;  // log2(bytes per symbol), uniform per tile
+        uint32_t nlive = min(S - F, 32u);                         // symbols of the run in this tile
+        uint32_t H = 0, kl = ck;
+        uint32_t my_cs = c_cs, my_pk = c_pk, my_rows = c_rows;
         uint32_t a, sym;
-        if (H == 0) {
-            a = c_ab + sz * (fi - c_cs);
-            const uint32_t a0 = c_ab + sz * (F - c_cs);
-            ws.ensure_input(a0, 32u * sz + 8u, lane);
-            if (nar) sym = ws.rb(a);
-            else if ((a0 & 1u) == 0) sym = *reinterpret_cast<const uint16_t*>(ws.inb + (a & (kInBytes - 1)));
+        if (next_start - F >= 32u) {
+            // ---- the whole tile lies in segment ck -----------------------------------------------------
+            const uint32_t a0 = c_ab + ((F - c_cs) << szsh);
+            ws.ensure_input(a0, kTileLook, lane);
+            a = a0 + (lane << szsh);
+            if (szsh == 0) sym = ws.rb(a);
+            else if ((a0 & 1u) == 0) sym = lds_u16(ws.inb_s + (a & (kInBytes - 1)));
             else sym = ws.rb(a) | (ws.rb(a + 1) << 8);
         } else {
-            kl = ck + __popc(H & le);
+            // ---- segments start inside the tile: which one does each lane's symbol belong to -----------
+            const uint32_t rel = sl.cs - F;
+            H = __reduce_or_sync(FULL, (has && rel - 1u < 31u) ? (1u << rel) : 0u);
+            kl = ck + __popc(H & lanemask_le());
             my_cs = __shfl_sync(FULL, sl.cs, kl);
-            my_ab = __shfl_sync(FULL, sl.ab, kl);
             my_pk = __shfl_sync(FULL, sl.pk, kl);
             my_rows = __shfl_sync(FULL, sl.rows, kl);
+            const uint32_t my_ab = __shfl_sync(FULL, sl.ab, kl);
             if (MULTI) {
                 // one symbol size per tile: stop in front of the first segment of the other size
                 const uint32_t other = __ballot_sync(FULL, (my_pk >> 31) != (c_pk >> 31));
-                if (other) live &= (1u << (__ffs(other) - 1)) - 1u;
+                if (other) nlive = min(nlive, uint32_t(__ffs(other) - 1));
             }
-            a = my_ab + sz * (fi - my_cs);
+            a = my_ab + ((F + lane - my_cs) << szsh);
             // bytes the tile can touch: from lane 0's symbol to lane 31's symbol + the widest payload
             const uint32_t a0 = __shfl_sync(FULL, a, 0), a31 = __shfl_sync(FULL, a, 31);
-            ws.ensure_input(a0, min(a31 - a0 + 8u, uint32_t(kChunk)), lane);
+            ws.ensure_input(a0, max(kTileLook + 1u, min(a31 - a0 + 8u, uint32_t(kChunk))), lane);
             sym = ws.rb(a);
-            if (!nar) sym |= ws.rb(a + 1) << 8;
+            if (szsh) sym |= ws.rb(a + 1) << 8;
         }
 
         // ---- which symbols are codewords ----------------------------------------------------
-        const uint32_t Z = __ballot_sync(FULL, sym == 0u) & live;
-        const uint32_t O = __ballot_sync(FULL, sym == 1u) & live;
-        uint32_t P = 0;  // payload symbols of this tile
-        if (Z | O) P = nar ? payload_mask<2, 4>(Z, O, H | 1u) : payload_mask<1, 2>(Z, O, H | 1u);
-        const bool iscw = (((live & ~P) >> lane) & 1u) != 0u;
+        const bool inlive = lane < nlive;
+        const uint32_t Z = __ballot_sync(FULL, inlive && sym == 0u);
+        const uint32_t O = __ballot_sync(FULL, inlive && sym == 1u);
+        bool iscw = inlive;
+        if (Z | O) {
+            const uint32_t P = szsh ? payload_mask<1, 2>(Z, O, H | 1u) : payload_mask<2, 4>(Z, O, H | 1u);
+            iscw = inlive && !((P >> lane) & 1u);
+        }
 
         // ---- lengths, offsets, how much of the tile is taken ----------------------------------
-        uint32_t len = 0, row = 0, step = 1;
-        if (iscw) {
-            len = 1;
-            if (sym >= 2u) {
-                row = (my_pk & 0x7FFFFFFFu) + min(sym, my_rows - 1u);
-                len = 1u << ((uint32_t(lut[row >> 1]) >> ((row & 1u) * 4u)) & 15u);
-            } else {
-                step = 1u + (4u >> (sym == 0u ? 1 : 0) >> (nar ? 0 : 1));  // + payload symbols
-            }
-        }
-        const uint32_t e = warp_inclusive_scan(len, lane);
-        const uint32_t s = e - len;
-        uint32_t limit = N - produced;
-        if (MODE != OUT_SKIP) limit = min(limit, kStageInts - ((uint32_t(ws.flushed) & (kGroup - 1)) + ws.staged));
+        // (rows 0 and 1 of every class are the exception codewords: the table holds length 1 for them)
+        const uint32_t row = (my_pk & 0x7FFFFFFFu) + min(sym, my_rows - 1u);
+        const uint32_t nib = (lds_u8(ws.lut_s + (row >> 1)) >> ((row & 1u) * 4u)) & 15u;
+        const uint32_t len = iscw ? (1u << nib) : 0u;
+        const uint32_t e = warp_inclusive_scan(len);
+        uint32_t limit = remaining;
+        if (MODE != OUT_SKIP) limit = min(limit, kStageInts - (uint32_t(ws.flushed) & (kGroup - 1)) - ws.staged);
         const bool valid = iscw && e <= limit;
         const uint32_t T = __reduce_max_sync(FULL, valid ? e : 0u);
         if (T == 0) break;  // malformed stream (a codeword straddles the end of the run)
-        const uint32_t adv = __reduce_max_sync(FULL, valid ? lane + step : 0u);  // symbols consumed
+        // symbols consumed: up to and including the last taken codeword and its payload
+        const uint32_t step = sym < 2u ? 1u + ((4u >> (sym == 0u ? 1 : 0)) >> szsh) : 1u;
+        const uint32_t adv = __reduce_max_sync(FULL, valid ? lane + step : 0u);
 
         // ---- scatter into the staging ring ------------------------------------------------------
         if (MODE != OUT_SKIP) {
-            const uint32_t base = uint32_t(ws.flushed) + ws.staged + s;
-            uint32_t* st = ws.stage;
-            const uint32_t L = (valid && sym >= dint::kReserved) ? len : 0u;
+            const uint32_t idx = (uint32_t(ws.flushed) + ws.staged + e - len) & (kStageInts - 1);
+            const uint32_t sa = ws.stage_s + (idx << 2);
+            const uint32_t L = (valid && sym >= dint::kReserved) ? len : 0u;  // words to copy from the dictionary
             const uint4* rp = reinterpret_cast<const uint4*>(rows + size_t(row) * dint::kEntry);
             uint4 r0 = make_uint4(0, 0, 0, 0);
             if (L) r0 = __ldg(rp);
-            if (valid && sym < 2u) {
-                const uint32_t pa = a + sz;
-                r0.x = ws.rb(pa) | (ws.rb(pa + 1) << 8);
-                if (sym == 1u) r0.x |= (ws.rb(pa + 2) << 16) | (ws.rb(pa + 3) << 24);
+            if (valid && sym < 2u) {  // exception: the value follows the codeword (u16 after 0, u32 after 1)
+                r0.x = ws.r32(a + (1u << szsh));
+                if (sym == 0u) r0.x &= 0xFFFFu;
             }
             if (MODE == OUT_DOCIDS && (H || F == c_cs)) {  // a segment starts in this tile: re-base
                 const uint32_t my_corr = __shfl_sync(FULL, sl.corr, kl);
-                if (fi == my_cs) r0.x += my_corr;
+                if (F + lane == my_cs) r0.x += my_corr;
             }
-            if (valid) st[base & (kStageInts - 1)] = r0.x;
-            if (L > 1) st[(base + 1) & (kStageInts - 1)] = r0.y;
-            if (L > 2) {
-                st[(base + 2) & (kStageInts - 1)] = r0.z;
-                st[(base + 3) & (kStageInts - 1)] = r0.w;
-            }
+            const bool wraps = idx + 16u > uint32_t(kStageInts);  // the entry may wrap around the ring
+            if (valid) sts_u32(sa, r0.x);
+            if (!wraps) sts_tail3(sa, L, r0.y, r0.z, r0.w);
             if (__any_sync(FULL, L > 4)) {
-                if (L > 4) {
-                    const uint4 r1 = __ldg(rp + 1);
-                    st[(base + 4) & (kStageInts - 1)] = r1.x;
-                    st[(base + 5) & (kStageInts - 1)] = r1.y;
-                    st[(base + 6) & (kStageInts - 1)] = r1.z;
-                    st[(base + 7) & (kStageInts - 1)] = r1.w;
-                }
+                if (L > 4 && !wraps) sts_4(sa + 16, __ldg(rp + 1));
                 if (__any_sync(FULL, L > 8)) {
-                    if (L > 8) {
-                        const uint4 r2 = __ldg(rp + 2);
-                        const uint4 r3 = __ldg(rp + 3);
-                        st[(base + 8) & (kStageInts - 1)] = r2.x;
-                        st[(base + 9) & (kStageInts - 1)] = r2.y;
-                        st[(base + 10) & (kStageInts - 1)] = r2.z;
-                        st[(base + 11) & (kStageInts - 1)] = r2.w;
-                        st[(base + 12) & (kStageInts - 1)] = r3.x;
-                        st[(base + 13) & (kStageInts - 1)] = r3.y;
-                        st[(base + 14) & (kStageInts - 1)] = r3.z;
-                        st[(base + 15) & (kStageInts - 1)] = r3.w;
+                    if (L > 8 && !wraps) {
+                        sts_4(sa + 32, __ldg(rp + 2));
+                        sts_4(sa + 48, __ldg(rp + 3));
                     }
                 }
+            }
+            if (wraps && L > 1) {
+                const uint32_t* rw = rows + size_t(row) * dint::kEntry;
+                for (uint32_t j = 1; j < L; ++j) sts_u32(ws.stage_s + (((idx + j) & (kStageInts - 1)) << 2), __ldg(rw + j));
             }
             ws.staged += T;
             __syncwarp();
@@ -405,8 +451,17 @@ __device__ __forceinline__ uint32_t decode_run(warp_state& ws, const uint32_t* _
                 __syncwarp();
             }
         }
-        produced += T;
+        remaining -= T;
         F += adv;
+        if (F >= next_start) {
+            // the next tile starts in another segment
+            ck = __popc(__ballot_sync(FULL, has && sl.cs <= F)) - 1u;
+            c_cs = uniform(__shfl_sync(FULL, sl.cs, ck));
+            c_ab = uniform(__shfl_sync(FULL, sl.ab, ck));
+            c_pk = uniform(__shfl_sync(FULL, sl.pk, ck));
+            c_rows = uniform(__shfl_sync(FULL, sl.rows, ck));
+            next_start = ck + 1 < cnt ? uniform(__shfl_sync(FULL, sl.cs, (ck + 1) & 31)) : kNoSegment;
+        }
     }
     return F;
 }
@@ -425,8 +480,8 @@ struct class_info {
 // byte (the reference's returned pointer).
 template <int MODE>
 __device__ __forceinline__ uint64_t decode_one(warp_state& ws, const uint32_t* __restrict__ rows,
-                                               const uint8_t* __restrict__ lut, const class_info* __restrict__ classes,
-                                               uint32_t n_classes, bool multi, uint64_t g, uint32_t n, unsigned lane) {
+                                               const class_info* __restrict__ classes, uint32_t n_classes, bool multi,
+                                               uint64_t g, uint32_t n, unsigned lane) {
     if (n == 0) return g;
     uint32_t a = ws.set_anchor(g, ~uint64_t(0));
     seg_lane sl;
@@ -436,7 +491,7 @@ __device__ __forceinline__ uint64_t decode_one(warp_state& ws, const uint32_t* _
         sl.ab = a;
         sl.pk = 0;
         sl.rows = classes[0].rows;
-        const uint32_t F = decode_run<false, MODE>(ws, rows, lut, sl, 1, kUnknownLen, n, lane);
+        const uint32_t F = decode_run<false, MODE>(ws, rows, sl, 1, kUnknownLen, n, lane);
         return ws.anchor + a + 2ull * F;
     }
     ws.ensure_input(a, 1, lane);
@@ -446,7 +501,7 @@ __device__ __forceinline__ uint64_t decode_one(warp_state& ws, const uint32_t* _
     sl.ab = a + 1;
     sl.pk = ci.row_base | (wide ? 0u : 0x80000000u);
     sl.rows = wide ? ci.rows : min(ci.rows, 256u);
-    const uint32_t F = decode_run<true, MODE>(ws, rows, lut, sl, 1, kUnknownLen, n, lane);
+    const uint32_t F = decode_run<true, MODE>(ws, rows, sl, 1, kUnknownLen, n, lane);
     return ws.anchor + a + 1ull + (wide ? 2ull : 1ull) * F;
 }
 

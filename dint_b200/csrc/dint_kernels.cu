@@ -61,9 +61,10 @@ __device__ __forceinline__ const class_info* cta_setup(const dint_dict_view& dv,
         classes[c] = ci;
     }
     uint8_t* mine = g_smem + lut_bytes + kClassBytes + (threadIdx.x >> 5) * kWarpSmem;
-    ws.stage = reinterpret_cast<uint32_t*>(mine);
-    ws.inb = mine + kStageInts * 4;
-    for (uint32_t i = lane_id(); i < kStageInts / 4; i += 32) reinterpret_cast<uint4*>(ws.stage)[i] = make_uint4(0, 0, 0, 0);
+    ws.stage_s = smem_u32(mine);
+    ws.inb_s = ws.stage_s + kStageInts * 4;
+    ws.lut_s = smem_u32(g_smem);
+    for (uint32_t i = lane_id(); i < kStageInts / 4; i += 32) reinterpret_cast<uint4*>(mine)[i] = make_uint4(0, 0, 0, 0);
     ws.out = out;
     ws.flushed = 0;
     ws.staged = 0;
@@ -71,6 +72,7 @@ __device__ __forceinline__ const class_info* cta_setup(const dint_dict_view& dv,
     ws.anchor = 0;
     ws.win_end = 0;
     ws.safe_end = 0;
+    ws.fast_end = 0;
     ws.lo_rel = 0;
     ws.hi_rel = 0;
     const uint64_t a = reinterpret_cast<uint64_t>(in);
@@ -113,7 +115,7 @@ decode_units_kernel(dint_dict_view dv, uint32_t lut_bytes, const uint8_t* __rest
                 // ---- the longest prefix of the batch that forms one flat run -----------------------
                 const bool has = lane < cnt;
                 const uint64_t out0 = shfl64(sg.out_off, 0), in0 = shfl64(sg.in_off, 0);
-                const uint32_t n_incl = warp_inclusive_scan(has ? sg.n : 0u, lane);
+                const uint32_t n_incl = warp_inclusive_scan(has ? sg.n : 0u);
                 const uint64_t my_end = sg.in_off + sg.in_len;
                 const uint64_t prev_end = shfl64(my_end, lane ? int(lane) - 1 : 0);
                 bool ok = sg.in_len != 0 && sg.n != 0 && my_end <= in_bytes && my_end - in0 < kMaxRunBytes &&
@@ -142,7 +144,7 @@ decode_units_kernel(dint_dict_view dv, uint32_t lut_bytes, const uint8_t* __rest
                         ws.flushed = out0;
                         ws.acc = doc_base0 - 1u;
                     }
-                    if (in0 < in_bytes) decode_one<MODE>(ws, dv.rows, g_smem, classes, dv.n_classes, MULTI, in_base + in0, n0, lane);
+                    if (in0 < in_bytes) decode_one<MODE>(ws, dv.rows, classes, dv.n_classes, MULTI, in_base + in0, n0, lane);
                     ws.flush_all<MODE>(lane);
                     __syncwarp();
                 } else {
@@ -161,7 +163,7 @@ decode_units_kernel(dint_dict_view dv, uint32_t lut_bytes, const uint8_t* __rest
                         sl.rows = wide ? ci.rows : min(ci.rows, 256u);
                     }
                     const uint32_t ns = hasr ? (sg.in_len - hdr) >> (narrow ? 0 : 1) : 0u;
-                    const uint32_t cs_incl = warp_inclusive_scan(ns, lane);
+                    const uint32_t cs_incl = warp_inclusive_scan(ns);
                     sl.cs = cs_incl - ns;
                     const uint32_t S = __shfl_sync(FULL, cs_incl, 31);
                     const uint32_t N = __shfl_sync(FULL, n_incl, r - 1);
@@ -171,7 +173,7 @@ decode_units_kernel(dint_dict_view dv, uint32_t lut_bytes, const uint8_t* __rest
                     const uint32_t my_tail = sg.doc_base - 1u + sg.doc_sum;
                     const uint32_t prev_tail = __shfl_up_sync(FULL, my_tail, 1);
                     sl.corr = lane ? sg.doc_base - 1u - prev_tail : corr0;
-                    decode_run<MULTI, MODE>(ws, dv.rows, g_smem, sl, r, S, N, lane);
+                    decode_run<MULTI, MODE>(ws, dv.rows, sl, r, S, N, lane);
                     tail = __shfl_sync(FULL, my_tail, r - 1);
                 }
                 // ---- drop the segments just decoded ---------------------------------------------------
@@ -212,7 +214,7 @@ index_docs_kernel(dint_dict_view dv, uint32_t lut_bytes, int multi, const uint8_
         ws.staged = 0;
         ws.flushed = b.out_off;
         ws.acc = b.cur_base - 1u;  // docid[0] = buf[0] + cur_base (dict_posting_list.hpp:304)
-        const uint64_t end = decode_one<MODE>(ws, dv.rows, g_smem, classes, dv.n_classes, multi != 0, base + b.in_off,
+        const uint64_t end = decode_one<MODE>(ws, dv.rows, classes, dv.n_classes, multi != 0, base + b.in_off,
                                               b.size, lane);
         if (MODE != OUT_SKIP) {
             ws.flush_all<MODE>(lane);
@@ -240,7 +242,7 @@ index_freqs_kernel(dint_dict_view dv, uint32_t lut_bytes, int multi, const uint8
         __syncwarp();
         ws.staged = 0;
         ws.flushed = b.out_off;
-        decode_one<OUT_FREQS>(ws, dv.rows, g_smem, classes, dv.n_classes, multi != 0, base + b.in_off + docs_len, b.size,
+        decode_one<OUT_FREQS>(ws, dv.rows, classes, dv.n_classes, multi != 0, base + b.in_off + docs_len, b.size,
                               lane);
         ws.flush_all<OUT_FREQS>(lane);
         __syncwarp();
@@ -408,10 +410,10 @@ decode_list_kernel(dint_dict_view dv, uint32_t lut_bytes, int multi, const uint8
     uint64_t addr = base;
     ws.flushed = 0;
     if (!multi) {
-        addr = decode_one<OUT_RAW>(ws, dv.rows, g_smem, classes, dv.n_classes, false, addr, n, lane);
+        addr = decode_one<OUT_RAW>(ws, dv.rows, classes, dv.n_classes, false, addr, n, lane);
     } else {
         for (uint32_t done = 0; done < n; done += block_size)  // vroom_env/dint_codecs.hpp:525-534
-            addr = decode_one<OUT_RAW>(ws, dv.rows, g_smem, classes, dv.n_classes, true, addr, min(block_size, n - done), lane);
+            addr = decode_one<OUT_RAW>(ws, dv.rows, classes, dv.n_classes, true, addr, min(block_size, n - done), lane);
     }
     ws.flush_all<OUT_RAW>(lane);
     if (lane == 0) *consumed = addr - base;
