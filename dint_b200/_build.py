@@ -42,9 +42,9 @@ def build(force=False, verbose=False):
             print("+", " ".join(cmd), flush=True)
         subprocess.run(cmd, check=True)
     main = os.path.join(CSRC, "vroom_decode_main.cpp")
-    if os.path.exists(main) and nvcc is not None and (force or _stale(DRIVER, [main, LIB] + HEADERS)):
-        cmd = [nvcc, "-O2", "-std=c++17", "-o", DRIVER, main, "-L", HERE, "-ldint_b200",
-               "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN"]
+    if os.path.exists(main) and (force or _stale(DRIVER, [main, LIB] + HEADERS)):
+        cxx = os.environ.get("CXX") or shutil.which("g++") or "g++"
+        cmd = [cxx, "-O2", "-std=c++17", "-Wall", "-o", DRIVER, main, "-L", HERE, "-ldint_b200", "-Wl,-rpath,$ORIGIN"]
         if verbose:
             print("+", " ".join(cmd), flush=True)
         subprocess.run(cmd, check=True)

@@ -36,6 +36,7 @@ SYMBOLS = [
     "dint_index_plan_list_offsets", "dint_index_plan_endpoints", "dint_index_plan_layout",
     "dint_decode_segments", "dint_decode_units", "dint_decode_index", "dint_checksum_lists", "dint_decode_list_host",
     "dint_vroom_ctx_create", "dint_vroom_ctx_destroy", "dint_vroom_ctx_device_output", "dint_vroom_decode_host",
+    "dint_vroom_decode_resident", "dint_vroom_ctx_sync",
 ]
 
 
@@ -97,6 +98,8 @@ def lib():
         L.dint_vroom_ctx_device_output.argtypes = [vp]
         L.dint_vroom_ctx_device_output.restype = vp
         L.dint_vroom_decode_host.argtypes = [vp, vp, sz, i32, vp, vp, vp]
+        L.dint_vroom_decode_resident.argtypes = [vp, i32, vp]
+        L.dint_vroom_ctx_sync.argtypes = [vp, vp]
         _lib = L
     return _lib
 
@@ -212,6 +215,12 @@ class VroomHostDecoder:
 
     def decode(self, h_bin_ptr, nbytes, mode=MODE_RAW, h_out_ptr=None, h_sums_ptr=None, stream=0):
         check(lib().dint_vroom_decode_host(self.handle, h_bin_ptr, nbytes, mode, h_out_ptr, h_sums_ptr, stream))
+
+    def decode_resident(self, mode=MODE_RAW, stream=0):
+        check(lib().dint_vroom_decode_resident(self.handle, mode, stream))
+
+    def sync(self, stream=0):
+        check(lib().dint_vroom_ctx_sync(self.handle, stream))
 
     @property
     def device_output(self):

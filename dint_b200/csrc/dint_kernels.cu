@@ -383,19 +383,66 @@ index_tails_kernel(const uint8_t* __restrict__ lists, uint64_t lists_bytes, cons
 }
 
 // ---- per-list checksums ---------------------------------------------------------------------
+// sums[i] = sum_{j in list i} (value_j + 1) * (j + 1). Work is cut by VALUES, not by lists: one warp
+// per tile of kSumTile consecutive values, so neither a 100 K-posting list nor a million
+// one-posting lists unbalance the grid. Lists that lie inside a tile are summed by one lane
+// each (short ones) or by the whole warp; pieces of lists that straddle tiles are added with
+// 64-bit atomics (sums[] is zeroed first).
+constexpr uint32_t kSumTile = 4096;
+constexpr uint32_t kSumShort = 48;
+
 __global__ void __launch_bounds__(256)
 checksum_kernel(const uint32_t* __restrict__ values, const uint64_t* __restrict__ offs, uint64_t n_lists,
-                uint64_t* __restrict__ sums) {
+                unsigned long long* __restrict__ sums) {
     const unsigned lane = lane_id();
     const uint64_t gwarp = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const uint64_t nwarps = (uint64_t(gridDim.x) * blockDim.x) >> 5;
-    for (uint64_t i = gwarp; i < n_lists; i += nwarps) {
-        const uint64_t b = offs[i], e = offs[i + 1];
-        uint64_t acc = 0;
-        for (uint64_t j = b + lane; j < e; j += 32) acc += (uint64_t(values[j]) + 1ull) * (j - b + 1ull);
+    const uint64_t total = offs[n_lists];
+    const uint64_t n_tiles = (total + kSumTile - 1) / kSumTile;
+    for (uint64_t t = gwarp; t < n_tiles; t += nwarps) {
+        const uint64_t t0 = t * kSumTile, t1 = min(total, t0 + kSumTile);
+        // last list that starts at or before t0 (lists may be empty: take the last such)
+        uint64_t lo = 0, hi = n_lists;  // invariant: offs[lo] <= t0 < offs[hi] (offs[n_lists] = total > t0)
+        while (hi - lo > 1) {
+            const uint64_t mid = (lo + hi) >> 1;
+            if (offs[mid] <= t0) lo = mid;
+            else hi = mid;
+        }
+        uint64_t i = lo;
+        while (i < n_lists) {
+            const uint64_t li = i + lane;
+            uint64_t b = total, e = total;
+            if (li < n_lists) {
+                b = offs[li];
+                e = offs[li + 1];
+            }
+            const bool act = li < n_lists && b < t1;
+            const uint64_t cb = max(b, t0), ce = min(e, t1);
+            const bool whole = cb == b && ce == e;
+            const bool shortp = act && ce - cb <= kSumShort;
+            if (shortp && ce > cb) {
+                unsigned long long acc = 0;
+                for (uint64_t j = cb; j < ce; ++j) acc += (uint64_t(values[j]) + 1ull) * (j - b + 1ull);
+                if (whole) sums[li] = acc;
+                else atomicAdd(&sums[li], acc);
+            }
+            uint32_t m = __ballot_sync(FULL, act && !shortp);
+            while (m) {
+                const int k = __ffs(m) - 1;
+                m &= m - 1;
+                const uint64_t kb = shfl64(b, k), kcb = shfl64(cb, k), kce = shfl64(ce, k);
+                unsigned long long acc = 0;
+                for (uint64_t j = kcb + lane; j < kce; j += 32) acc += (uint64_t(values[j]) + 1ull) * (j - kb + 1ull);
 #pragma unroll
-        for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
-        if (lane == 0) sums[i] = acc;
+                for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
+                if (lane == 0) atomicAdd(&sums[i + k], acc);
+            }
+            // lists that end inside the tile are done; stop at the first one that reaches its end
+            const uint32_t done = __ballot_sync(FULL, act && e <= t1);
+            const uint32_t nact = __popc(__ballot_sync(FULL, act));
+            if (__popc(done) < 32 || nact < 32) break;
+            i += 32;
+        }
     }
 }
 
@@ -650,9 +697,11 @@ int dint_checksum_lists(const uint32_t* d_values, const uint64_t* d_list_offsets
     device_info di;
     int rc = get_device_info(dev, &di);
     if (rc) return rc;
-    uint64_t want = (n_lists + 7) / 8;
-    int grid = int(std::max<uint64_t>(1, std::min<uint64_t>(want, uint64_t(di.sms) * 8)));
-    checksum_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_values, d_list_offsets, n_lists, d_sums);
+    // persistent grid over value tiles; partial sums of lists that straddle tiles arrive by atomics
+    CUDA_TRY(cudaMemsetAsync(d_sums, 0, n_lists * sizeof(uint64_t), static_cast<cudaStream_t>(stream)));
+    int grid = di.sms * 8;
+    checksum_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        d_values, d_list_offsets, n_lists, reinterpret_cast<unsigned long long*>(d_sums));
     ++g_launches;
     CUDA_TRY(cudaGetLastError());
     return DINT_OK;
@@ -744,6 +793,19 @@ int dint_vroom_decode_host(dint_vroom_ctx* c, const void* h_bin, size_t len, int
         CUDA_TRY(cudaMemcpyAsync(h_sums, c->d_sums, c->n_lists * 8, cudaMemcpyDeviceToHost, st));
     }
     if (h_out && c->n_ints) CUDA_TRY(cudaMemcpyAsync(h_out, c->d_out, c->n_ints * 4, cudaMemcpyDeviceToHost, st));
+    return DINT_OK;
+}
+
+int dint_vroom_decode_resident(dint_vroom_ctx* c, int mode, void* stream) {
+    if (!c) return DINT_E_ARG;
+    return dint_decode_units(c->dict, c->d_in, c->in_bytes, c->d_segs, c->n_segs, c->n_units ? c->d_unit_first : nullptr,
+                             c->n_units, c->d_out, mode, stream);
+}
+
+int dint_vroom_ctx_sync(dint_vroom_ctx* c, void* stream) {
+    if (!c) return DINT_E_ARG;
+    device_guard g(c->dict->device);
+    CUDA_TRY(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
     return DINT_OK;
 }
 

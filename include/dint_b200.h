@@ -205,6 +205,11 @@ uint32_t* dint_vroom_ctx_device_output(const dint_vroom_ctx* c);
  * of all num_ints decoded integers. Returns without synchronising the stream. */
 int dint_vroom_decode_host(dint_vroom_ctx* c, const void* h_bin, size_t len, int mode, uint32_t* h_out,
                            uint64_t* h_sums, void* stream);
+/* Decodes again from the bytes the last dint_vroom_decode_host call left in HBM (no copies):
+ * what the reference's decode loop does once the file is mapped. */
+int dint_vroom_decode_resident(dint_vroom_ctx* c, int mode, void* stream);
+/* Blocks until everything enqueued on `stream` of the ctx's device has finished. */
+int dint_vroom_ctx_sync(dint_vroom_ctx* c, void* stream);
 
 #ifdef __cplusplus
 }

@@ -232,3 +232,32 @@ def test_interpolative_tail_blocks_random(golden, sum_known):
                       d_freqs.data_ptr(), stream=torch.cuda.current_stream().cuda_stream)
     assert np.array_equal(_np(d_docs), np.concatenate(want_d))
     assert np.array_equal(_np(d_freqs), np.concatenate(want_f))
+
+
+@pytest.mark.parametrize("type_", g.TYPES)
+def test_cpp_host_driver(golden, tmp_path, type_):
+    """dint_b200_decode (C++ over the C ABI, mirror of vroom_env/decode.cpp): stats line + per-list
+    checksums of the fused docID decode must match the collection itself"""
+    import json
+    import os
+    import subprocess
+    from dint_b200 import _build
+    _build.build()
+    binp = golden.path(golden.vroom_name(type_, "docs"))
+    dictp = golden.path(golden.dict_name(type_, "docs"))
+    sums_file = str(tmp_path / "sums.bin")
+    out = subprocess.run([_build.DRIVER, type_, binp, "--dict", dictp, "--mode", "docids", "--repeat", "3",
+                          "--sums", sums_file], check=True, capture_output=True, text=True).stdout
+    st = json.loads(out.strip().splitlines()[-1])
+    assert int(st["num_sequences"]) == golden.n_lists and int(st["num_integers"]) == golden.n_postings
+    assert st["type"] == type_ and int(st["ints_x_sec"]) > 0 and st["kernel_launches"] >= 4
+    vf = driver.VroomFile(type_, golden.bytes(golden.vroom_name(type_, "docs")), golden.bytes(golden.dict_name(type_, "docs")))
+    docs = _np(vf.decode(mode=capi.MODE_DOCIDS))
+    assert g.sha(docs.tobytes()) == golden.sha["docids_sha256"]
+    want = g.checksum_lists(docs, np.diff(vf.plan.list_offsets.astype(np.int64)))
+    got = np.fromfile(sums_file, dtype=np.uint64)
+    assert np.array_equal(got, want)
+    assert int(st["checksum"]) == int(want.sum(dtype=np.uint64))
+    # unknown type: logged, exit code 0, like the reference (decode.cpp:259)
+    r = subprocess.run([_build.DRIVER, "nope", binp, "--dict", dictp], capture_output=True, text=True)
+    assert r.returncode == 0 and "unknown type" in r.stderr
