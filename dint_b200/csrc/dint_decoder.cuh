@@ -59,7 +59,8 @@ constexpr int kStageInts = 512;  // output staging ring per warp (power of two)
 constexpr int kInBytes = 1024;   // input ring per warp (two chunks)
 constexpr int kChunk = 512;      // bytes per cp.async round (32 lanes x 16 bytes)
 constexpr int kGroup = 128;      // integers per flush round (one uint4 per lane)
-constexpr int kWarpSmem = kStageInts * 4 + kInBytes;
+constexpr int kQueue = 64;        // codeword queue entries per warp (power of two, 8 bytes each)
+constexpr int kWarpSmem = kStageInts * 4 + kInBytes + kQueue * 8;
 constexpr uint32_t kMaxRunBytes = 1u << 30;  // input span of one run (32-bit relative offsets)
 constexpr uint32_t kUnknownLen = 0xFFFFFFFFu;
 constexpr uint32_t kNoSegment = 0xFFFFFFFFu;
@@ -152,6 +153,7 @@ struct warp_state {
     uint32_t stage_s;   // shared address of the output staging ring [kStageInts]
     uint32_t inb_s;     // shared address of the input ring [kInBytes]
     uint32_t lut_s;     // shared address of the 4-bit length table
+    uint32_t que_s;     // shared address of the codeword queue [kQueue] x {meta, value}
     uint32_t* out;      // packed output array (global)
     uint64_t flushed;   // output index: everything below it (of this run) is in global memory
     uint32_t staged;    // integers sitting in the ring: [flushed, flushed + staged)
@@ -464,6 +466,162 @@ __device__ __forceinline__ uint32_t decode_run(warp_state& ws, const uint32_t* _
         }
     }
     return F;
+}
+
+// ---- two-phase run decoder: parse tiles into a codeword queue, expand 32 codewords at a time -----
+// In sparse posting lists most symbols are exception payload (a 32-bit exception takes 3 u16 or 5 u8
+// symbols), so a 32-symbol tile holds only 6..10 codewords and the per-tile work of decode_run
+// (length lookup, scan, scatter, flush test) runs with most lanes idle. Here the run is parsed in
+// phase A (symbols -> codewords, tile by tile, no output state involved) into a small per-warp
+// queue of {dictionary row | kind, value}, and phase B expands FULL batches of 32 queued codewords
+// into the staging ring. Requires the run's symbol count S (segment byte lengths), so it serves
+// the vroom work units; segments of unknown length go through decode_run.
+constexpr uint32_t kMetaExc = 0x80000000u;  // queue meta: exception (value = the integer itself)
+constexpr uint32_t kMetaRun = 0x40000000u;  // queue meta: run of zeros (nothing to copy)
+
+template <int MODE>
+__device__ __forceinline__ bool expand_batch(warp_state& ws, const uint32_t* __restrict__ rows, uint32_t& qhead,
+                                             uint32_t qtail, uint32_t& remaining, unsigned lane) {
+    const uint32_t qn = qtail - qhead;
+    const bool has = lane < qn;
+    const uint32_t qa = ws.que_s + (((qhead + lane) & (kQueue - 1)) << 3);
+    uint32_t meta = 0, val = 0;
+    if (has) asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(meta), "=r"(val) : "r"(qa));
+    const uint32_t row = meta & 0x3FFFFFFFu;
+    const uint32_t nib = (lds_u8(ws.lut_s + (row >> 1)) >> ((row & 1u) * 4u)) & 15u;
+    const uint32_t len = has ? (1u << nib) : 0u;
+    const uint32_t e = warp_inclusive_scan(len);
+    const uint32_t limit = min(remaining, kStageInts - (uint32_t(ws.flushed) & (kGroup - 1)) - ws.staged);
+    const bool valid = has && e <= limit;
+    const uint32_t V = __ballot_sync(FULL, valid);
+    if (V == 0) return false;  // malformed stream: more integers than the run declares
+    const uint32_t T = __shfl_sync(FULL, e, 31 - __clz(V));
+    const uint32_t idx = (uint32_t(ws.flushed) + ws.staged + e - len) & (kStageInts - 1);
+    const uint32_t sa = ws.stage_s + (idx << 2);
+    const uint32_t L = (valid && !(meta & (kMetaExc | kMetaRun))) ? len : 0u;  // words to copy from the dictionary
+    const uint4* rp = reinterpret_cast<const uint4*>(rows + size_t(row) * dint::kEntry);
+    uint4 r0 = make_uint4(0, 0, 0, 0);
+    if (L) r0 = __ldg(rp);
+    r0.x += val;  // exception value, or the docID re-basing term of a segment's first codeword, or 0
+    const bool wraps = idx + 16u > uint32_t(kStageInts);  // the entry may wrap around the ring
+    if (valid) sts_u32(sa, r0.x);
+    if (!wraps) sts_tail3(sa, L, r0.y, r0.z, r0.w);
+    if (__any_sync(FULL, L > 4)) {
+        if (L > 4 && !wraps) sts_4(sa + 16, __ldg(rp + 1));
+        if (__any_sync(FULL, L > 8)) {
+            if (L > 8 && !wraps) {
+                sts_4(sa + 32, __ldg(rp + 2));
+                sts_4(sa + 48, __ldg(rp + 3));
+            }
+        }
+    }
+    if (wraps && L > 1) {
+        const uint32_t* rw = rows + size_t(row) * dint::kEntry;
+#pragma unroll 1
+        for (uint32_t j = 1; j < L; ++j) sts_u32(ws.stage_s + (((idx + j) & (kStageInts - 1)) << 2), __ldg(rw + j));
+    }
+    ws.staged += T;
+    remaining -= T;
+    qhead += __popc(V);
+    __syncwarp();
+    if ((uint32_t(ws.flushed) & (kGroup - 1)) + ws.staged >= uint32_t(kGroup)) {
+        ws.flush_full<MODE>(lane);
+        __syncwarp();
+    }
+    return true;
+}
+
+template <bool MULTI, int MODE>
+__device__ __forceinline__ void decode_run_queued(warp_state& ws, const uint32_t* __restrict__ rows, const seg_lane& sl,
+                                                  uint32_t cnt_, uint32_t S_, uint32_t N_, unsigned lane) {
+    const uint32_t cnt = uniform(cnt_), S = uniform(S_);
+    uint32_t F = 0, remaining = uniform(N_);
+    uint32_t qhead = 0, qtail = 0;
+    const bool has = lane < cnt;
+    const unsigned le = lanemask_le();
+    uint32_t ck = 0;
+    uint32_t c_cs = 0, c_ab = uniform(__shfl_sync(FULL, sl.ab, 0));
+    uint32_t c_pk = uniform(__shfl_sync(FULL, sl.pk, 0)), c_rows = uniform(__shfl_sync(FULL, sl.rows, 0));
+    uint32_t next_start = cnt > 1 ? uniform(__shfl_sync(FULL, sl.cs, 1)) : kNoSegment;
+    while (F < S && remaining) {
+        // ======== phase A: one tile of symbols -> codewords appended to the queue ========================
+        const uint32_t szsh = (MULTI && (c_pk >> 31)) ? 0u : 1u;
+        uint32_t nlive = min(S - F, 32u);
+        uint32_t H = 0, kl = ck;
+        uint32_t my_cs = c_cs, my_pk = c_pk, my_rows = c_rows;
+        uint32_t a, sym;
+        if (next_start - F >= 32u) {
+            const uint32_t a0 = c_ab + ((F - c_cs) << szsh);
+            ws.ensure_input(a0, kTileLook, lane);
+            a = a0 + (lane << szsh);
+            if (szsh == 0) sym = ws.rb(a);
+            else if ((a0 & 1u) == 0) sym = lds_u16(ws.inb_s + (a & (kInBytes - 1)));
+            else sym = ws.rb(a) | (ws.rb(a + 1) << 8);
+        } else {
+            const uint32_t rel = sl.cs - F;
+            H = __reduce_or_sync(FULL, (has && rel - 1u < 31u) ? (1u << rel) : 0u);
+            kl = ck + __popc(H & le);
+            my_cs = __shfl_sync(FULL, sl.cs, kl);
+            my_pk = __shfl_sync(FULL, sl.pk, kl);
+            my_rows = __shfl_sync(FULL, sl.rows, kl);
+            const uint32_t my_ab = __shfl_sync(FULL, sl.ab, kl);
+            if (MULTI) {
+                const uint32_t other = __ballot_sync(FULL, (my_pk >> 31) != (c_pk >> 31));
+                if (other) nlive = min(nlive, uint32_t(__ffs(other) - 1));
+            }
+            a = my_ab + ((F + lane - my_cs) << szsh);
+            const uint32_t a0 = __shfl_sync(FULL, a, 0), a31 = __shfl_sync(FULL, a, 31);
+            ws.ensure_input(a0, max(kTileLook + 1u, min(a31 - a0 + 8u, uint32_t(kChunk))), lane);
+            sym = ws.rb(a);
+            if (szsh) sym |= ws.rb(a + 1) << 8;
+        }
+        const bool inlive = lane < nlive;
+        const uint32_t Z = __ballot_sync(FULL, inlive && sym == 0u);
+        const uint32_t O = __ballot_sync(FULL, inlive && sym == 1u);
+        uint32_t CW = nlive >= 32u ? FULL : ((1u << nlive) - 1u);
+        if (Z | O) CW &= ~(szsh ? payload_mask<1, 2>(Z, O, H | 1u) : payload_mask<2, 4>(Z, O, H | 1u));
+        const bool iscw = (CW >> lane) & 1u;
+        // queue entry of this lane's codeword
+        uint32_t meta = (my_pk & 0x3FFFFFFFu) + min(sym, my_rows - 1u);
+        uint32_t val = 0, step = 1;
+        if (sym < dint::kReserved) meta |= kMetaRun;
+        if (iscw && sym < 2u) {  // exception: the value follows the codeword (u16 after 0, u32 after 1)
+            val = ws.r32(a + (1u << szsh));
+            if (sym == 0u) val &= 0xFFFFu;
+            meta |= kMetaExc;
+            step = 1u + ((4u >> (sym == 0u ? 1 : 0)) >> szsh);
+        }
+        if (MODE == OUT_DOCIDS && (H || F == c_cs)) {  // a segment starts in this tile: re-base its first integer
+            const uint32_t my_corr = __shfl_sync(FULL, sl.corr, kl);
+            if (F + lane == my_cs) val += my_corr;
+        }
+        if (iscw) {
+            const uint32_t slot = (qtail + __popc(CW & (le >> 1))) & (kQueue - 1);
+            asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(ws.que_s + (slot << 3)), "r"(meta), "r"(val) : "memory");
+        }
+        qtail += __popc(CW);
+        F += __reduce_max_sync(FULL, iscw ? lane + step : 0u);  // symbols consumed, payload included
+        if (F >= next_start) {
+            ck = __popc(__ballot_sync(FULL, has && sl.cs <= F)) - 1u;
+            c_cs = uniform(__shfl_sync(FULL, sl.cs, ck));
+            c_ab = uniform(__shfl_sync(FULL, sl.ab, ck));
+            c_pk = uniform(__shfl_sync(FULL, sl.pk, ck));
+            c_rows = uniform(__shfl_sync(FULL, sl.rows, ck));
+            next_start = ck + 1 < cnt ? uniform(__shfl_sync(FULL, sl.cs, (ck + 1) & 31)) : kNoSegment;
+        }
+        // ======== phase B: expand full batches ============================================================
+        __syncwarp();
+        while (qtail - qhead >= 32u && remaining) {
+            if (!expand_batch<MODE>(ws, rows, qhead, qtail, remaining, lane)) {
+                remaining = 0;
+                break;
+            }
+        }
+    }
+    __syncwarp();
+    while (qtail != qhead && remaining) {  // drain
+        if (!expand_batch<MODE>(ws, rows, qhead, qtail, remaining, lane)) break;
+    }
 }
 
 // Per-class parameters of a dictionary, staged in shared memory next to the length table.

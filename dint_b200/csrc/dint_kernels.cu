@@ -63,6 +63,7 @@ __device__ __forceinline__ const class_info* cta_setup(const dint_dict_view& dv,
     uint8_t* mine = g_smem + lut_bytes + kClassBytes + (threadIdx.x >> 5) * kWarpSmem;
     ws.stage_s = smem_u32(mine);
     ws.inb_s = ws.stage_s + kStageInts * 4;
+    ws.que_s = ws.inb_s + kInBytes;
     ws.lut_s = smem_u32(g_smem);
     for (uint32_t i = lane_id(); i < kStageInts / 4; i += 32) reinterpret_cast<uint4*>(mine)[i] = make_uint4(0, 0, 0, 0);
     ws.out = out;
@@ -86,7 +87,7 @@ __device__ __forceinline__ const class_info* cta_setup(const dint_dict_view& dv,
 // vroom path: one warp per work unit (<= 32 consecutive segments, normally contiguous in the
 // file and in the output, which makes the whole unit one flat run).
 template <bool MULTI, int MODE, int W>
-__global__ void __launch_bounds__(W * 32, W == 16 ? 2 : 1)
+__global__ void __launch_bounds__(W * 32, W <= 16 ? 2 : 1)
 decode_units_kernel(dint_dict_view dv, uint32_t lut_bytes, const uint8_t* __restrict__ in, uint64_t in_bytes,
                     const dint_segment* __restrict__ segs, uint64_t n_segs, const uint32_t* __restrict__ unit_first,
                     uint64_t n_units, uint32_t* __restrict__ out) {
@@ -173,7 +174,7 @@ decode_units_kernel(dint_dict_view dv, uint32_t lut_bytes, const uint8_t* __rest
                     const uint32_t my_tail = sg.doc_base - 1u + sg.doc_sum;
                     const uint32_t prev_tail = __shfl_up_sync(FULL, my_tail, 1);
                     sl.corr = lane ? sg.doc_base - 1u - prev_tail : corr0;
-                    decode_run<MULTI, MODE>(ws, dv.rows, sl, r, S, N, lane);
+                    decode_run_queued<MULTI, MODE>(ws, dv.rows, sl, r, S, N, lane);
                     tail = __shfl_sync(FULL, my_tail, r - 1);
                 }
                 // ---- drop the segments just decoded ---------------------------------------------------

@@ -14,7 +14,7 @@ import json
 import numpy as np
 import torch
 
-from . import capi
+from . import capi, shard
 
 TYPES = ("single_rect_dint", "single_packed_dint", "multi_packed_dint")
 
@@ -75,6 +75,25 @@ class VroomFile:
         st = (stream or torch.cuda.current_stream(self.dev)).cuda_stream
         capi.checksum_lists(values.data_ptr(), self.d_list_offsets.data_ptr(), self.n_lists, sums.data_ptr(), stream=st)
         return sums
+
+
+class ShardedVroomFile(VroomFile):
+    """This rank's term-range shard of a vroom .bin (one process per GPU, dictionary replicated,
+    no traffic on the hot path). `totals()` is the job's only collective."""
+
+    def __init__(self, type_, bin_bytes, dict_bytes, rank, world, device=0, block_size=256):
+        host_dict = capi.Dictionary(capi.KIND_OF_TYPE[type_], dict_bytes)  # host tables: enough to walk the file
+        whole = capi.VroomPlan(host_dict, bin_bytes, block_size=block_size)
+        lengths = np.diff(whole.list_offsets.astype(np.int64))
+        mine, self.first_list, self.last_list = shard.shard_vroom(bin_bytes, lengths, whole.list_byte_offsets, rank, world)
+        self.rank, self.world = rank, world
+        super().__init__(type_, mine, dict_bytes, device=device, block_size=block_size)
+
+    def totals(self, values):
+        """(integers decoded, sum of per-list checksums mod 2^63) over all ranks"""
+        sums = self.checksums(values)
+        local = int(sums.view(torch.int64).sum().item()) if self.n_lists else 0
+        return shard.reduce_totals(self.n_ints, local, device=self.dev)
 
 
 class IndexFile:

@@ -261,3 +261,23 @@ def test_cpp_host_driver(golden, tmp_path, type_):
     # unknown type: logged, exit code 0, like the reference (decode.cpp:259)
     r = subprocess.run([_build.DRIVER, "nope", binp, "--dict", dictp], capture_output=True, text=True)
     assert r.returncode == 0 and "unknown type" in r.stderr
+
+
+def test_sharded_vroom_file_single_process(golden):
+    """term-range shards decoded one after the other on one GPU add up to the whole file"""
+    type_ = "multi_packed_dint"
+    bin_ = golden.bytes(golden.vroom_name(type_, "docs"))
+    dict_bytes = golden.bytes(golden.dict_name(type_, "docs"))
+    whole = driver.VroomFile(type_, bin_, dict_bytes)
+    full = _np(whole.decode(mode=capi.MODE_DOCIDS))
+    parts, count, check = [], 0, 0
+    for r in range(3):
+        sh = driver.ShardedVroomFile(type_, bin_, dict_bytes, r, 3)
+        out = sh.decode(mode=capi.MODE_DOCIDS)
+        parts.append(_np(out))
+        c, k = sh.totals(out)
+        count += c
+        check = (check + k) & 0x7FFFFFFFFFFFFFFF
+    assert np.array_equal(np.concatenate(parts), full) and count == golden.n_postings
+    want = int(whole.checksums(whole.decode(mode=capi.MODE_DOCIDS)).cpu().numpy().view(np.uint64).sum(dtype=np.uint64))
+    assert check == want & 0x7FFFFFFFFFFFFFFF
