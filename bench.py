@@ -250,8 +250,9 @@ class ClockSampler:
 class ReplicatedStream:
     """R back-to-back copies of one vroom .bin in HBM + the matching segment table."""
 
-    def __init__(self, torch, capi, dev, type_, bin_bytes, dict_bytes, replicas, block_size):
+    def __init__(self, torch, capi, dev, type_, bin_bytes, dict_bytes, replicas, block_size, engine="strips"):
         self.capi = capi
+        self.engine = engine
         self.dict = capi.Dictionary(KINDS[type_], dict_bytes, device=dev.index)
         self.plan = capi.VroomPlan(self.dict, bin_bytes, block_size=block_size)
         self.R = replicas
@@ -272,6 +273,13 @@ class ReplicatedStream:
         self.d_unit_first = torch.cat([(uf[:-1][None, :] + (r * self.n_segs)[:, None]).reshape(-1),
                                        torch.tensor([replicas * self.n_segs], dtype=torch.int64, device=dev)]
                                       ).to(torch.int32)
+        # strip units (lane-sequential decoder): 160-byte records, in_off / out_off are the first two u64
+        self.n_strip_units = int(self.plan.n_strip_units)
+        su = torch.from_numpy(self.plan.strip_units.view(np.int64).reshape(-1, 20).copy()).to(dev)
+        sshift = torch.zeros(replicas, 1, 20, dtype=torch.int64, device=dev)
+        sshift[:, 0, 0] = r * self.in_bytes
+        sshift[:, 0, 1] = r * self.n_ints
+        self.d_strip_units = (su[None, :, :] + sshift).reshape(-1, 20).contiguous()
         lo = torch.from_numpy(self.plan.list_offsets.astype(np.int64)).to(dev)
         self.d_list_offsets = torch.cat([(lo[:-1][None, :] + (r * self.n_ints)[:, None]).reshape(-1),
                                          torch.tensor([replicas * self.n_ints], dtype=torch.int64, device=dev)])
@@ -279,6 +287,10 @@ class ReplicatedStream:
         self.algo_bytes = replicas * (self.in_bytes + 4 * self.n_ints)
 
     def launch(self, mode, stream):
+        if self.engine == "strips":
+            self.capi.decode_strips(self.dict, self.d_in.data_ptr(), self.R * self.in_bytes, self.d_strip_units.data_ptr(),
+                                    self.R * self.n_strip_units, self.out.data_ptr(), mode, stream=stream)
+            return
         self.capi.decode_units(self.dict, self.d_in.data_ptr(), self.R * self.in_bytes, self.d_segs.data_ptr(),
                                self.R * self.n_segs, self.d_unit_first.data_ptr(), self.R * self.n_units,
                                self.out.data_ptr(), mode, stream=stream)
@@ -307,7 +319,7 @@ def run_gpu(args):
     streams = {}
     for part in ("docs", "freqs"):
         bin_, dict_bytes, _ = w["parts"][part]
-        streams[part] = ReplicatedStream(torch, capi, dev, args.type, bin_, dict_bytes, R, w["block_size"])
+        streams[part] = ReplicatedStream(torch, capi, dev, args.type, bin_, dict_bytes, R, w["block_size"], args.engine)
     sd, sf = streams["docs"], streams["freqs"]
     ints_per_step = R * (sd.n_ints + sf.n_ints)
     st = torch.cuda.current_stream(dev)
@@ -408,7 +420,8 @@ def run_gpu(args):
                    "sharding": f"term-range, {world} rank(s), dictionary replicated, no hot-path collective",
                    "l2": "inputs+outputs per step >> 126 MB L2 (no flush needed)",
                    "parity": "sha256 of replica 0 == reference collection; all replicas' per-list checksums equal"},
-        "roofline": {"bound": "hbm", "kernel": "decode_segments_kernel<DOCIDS> (docs stream)", "achieved": achieved,
+        "roofline": {"bound": "hbm", "kernel": ("decode_strips_kernel<DOCIDS>" if args.engine == "strips" else
+                                                  "decode_units_kernel<DOCIDS>") + " (docs stream)", "achieved": achieved,
                      "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
                      "algorithmic_bytes_per_launch": sd.algo_bytes, "avg_launch_ms": docs_ms, "traffic": traffic,
                      "freqs_kernel": {"achieved": sf.algo_bytes / (freqs_ms * 1e-3) / 1e9, "avg_launch_ms": freqs_ms,
@@ -545,6 +558,8 @@ def main():
     ap.add_argument("--impl", default="dint_b200", choices=["dint_b200", "reference"])
     ap.add_argument("--workload", default="gov2_r256")
     ap.add_argument("--type", default=None, choices=sorted(KINDS))
+    ap.add_argument("--engine", default="strips", choices=("strips", "units"),
+                    help="strips = lane-sequential strip decoder (default); units = warp-per-unit tile decoder")
     ap.add_argument("--replicas", type=int, default=0, help="override the number of HBM replicas (debug)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--e2e-batch", type=int, default=8, help="sample .bin copies per host-buffer call")

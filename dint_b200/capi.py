@@ -21,11 +21,15 @@ SEGMENT_DTYPE = np.dtype([("in_off", "<u8"), ("out_off", "<u8"), ("n", "<u4"), (
                           ("in_len", "<u4"), ("doc_sum", "<u4")])
 BLOCK_DTYPE = np.dtype([("in_off", "<u8"), ("out_off", "<u8"), ("size", "<u4"), ("cur_base", "<u4"),
                         ("block_max", "<u4"), ("reserved", "<u4")])
-assert SEGMENT_DTYPE.itemsize == 32 and BLOCK_DTYPE.itemsize == 32
+STRIP_UNIT_DTYPE = np.dtype([("in_off", "<u8"), ("out_off", "<u8"), ("doc_base", "<u4"), ("list_starts", "<u4"),
+                             ("in_len", "<u2"), ("n_ints", "<u2"), ("n_strips", "u1"), ("reserved", "u1", (3,)),
+                             ("strip", "<u4", (32,))])
+assert SEGMENT_DTYPE.itemsize == 32 and BLOCK_DTYPE.itemsize == 32 and STRIP_UNIT_DTYPE.itemsize == 160
 
 # every symbol include/dint_b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
-    "dint_last_error", "dint_abi_version", "dint_kernel_launches",
+    "dint_last_error", "dint_abi_version", "dint_kernel_launches", "dint_strip_limits",
+    "dint_vroom_plan_num_strip_units", "dint_vroom_plan_strip_units", "dint_decode_strips",
     "dint_dict_create", "dint_dict_create_mapped", "dint_dict_destroy", "dint_dict_kind", "dint_dict_num_rows",
     "dint_dict_device_bytes", "dint_dict_copy",
     "dint_vroom_plan_create", "dint_vroom_plan_destroy", "dint_vroom_plan_num_lists", "dint_vroom_plan_num_ints",
@@ -71,10 +75,13 @@ def lib():
         L.dint_vroom_plan_create.argtypes = [vp, vp, sz, u32, u32, C.POINTER(vp)]
         L.dint_vroom_plan_destroy.argtypes = [vp]
         L.dint_vroom_plan_destroy.restype = None
-        for f in ("num_lists", "num_ints", "num_segments", "num_units"):
+        L.dint_strip_limits.argtypes = [C.POINTER(u32)] * 3
+        L.dint_strip_limits.restype = None
+        L.dint_decode_strips.argtypes = [vp, vp, sz, vp, sz, vp, i32, vp]
+        for f in ("num_lists", "num_ints", "num_segments", "num_units", "num_strip_units"):
             getattr(L, "dint_vroom_plan_" + f).argtypes = [vp]
             getattr(L, "dint_vroom_plan_" + f).restype = u64
-        for f in ("segments", "unit_first", "list_offsets", "list_byte_offsets"):
+        for f in ("segments", "unit_first", "list_offsets", "list_byte_offsets", "strip_units"):
             getattr(L, "dint_vroom_plan_" + f).argtypes = [vp]
             getattr(L, "dint_vroom_plan_" + f).restype = vp
         L.dint_index_plan_create.argtypes = [i32, vp, sz, u32, C.POINTER(vp)]
@@ -184,6 +191,8 @@ class VroomPlan:
         self.segments = _view(L.dint_vroom_plan_segments(h), self.n_segments, SEGMENT_DTYPE)
         self.n_units = L.dint_vroom_plan_num_units(h)
         self.unit_first = _view(L.dint_vroom_plan_unit_first(h), self.n_units + 1, np.uint32)
+        self.n_strip_units = L.dint_vroom_plan_num_strip_units(h)
+        self.strip_units = _view(L.dint_vroom_plan_strip_units(h), self.n_strip_units, STRIP_UNIT_DTYPE)
         self.list_offsets = _view(L.dint_vroom_plan_list_offsets(h), self.n_lists + 1, np.uint64)
         self.list_byte_offsets = _view(L.dint_vroom_plan_list_byte_offsets(h), self.n_lists + 1, np.uint64)
         self.block_size = block_size
@@ -269,6 +278,16 @@ def decode_segments(dictionary, d_in_ptr, in_bytes, d_segs_ptr, n_segs, d_out_pt
 def decode_units(dictionary, d_in_ptr, in_bytes, d_segs_ptr, n_segs, d_unit_first_ptr, n_units, d_out_ptr, mode, stream=0):
     check(lib().dint_decode_units(dictionary.handle, d_in_ptr, in_bytes, d_segs_ptr, n_segs, d_unit_first_ptr, n_units,
                                   d_out_ptr, mode, stream))
+
+
+def decode_strips(dictionary, d_in_ptr, in_bytes, d_units_ptr, n_units, d_out_ptr, mode, stream=0):
+    check(lib().dint_decode_strips(dictionary.handle, d_in_ptr, in_bytes, d_units_ptr, n_units, d_out_ptr, mode, stream))
+
+
+def strip_limits():
+    a, b, c = C.c_uint32(), C.c_uint32(), C.c_uint32()
+    lib().dint_strip_limits(C.byref(a), C.byref(b), C.byref(c))
+    return {"unit_ints": a.value, "unit_bytes": b.value, "strip_codewords": c.value}
 
 
 def decode_index(docs_dict, freqs_dict, d_lists_ptr, lists_bytes, d_blocks_ptr, n_blocks, block_size, d_docids_ptr,

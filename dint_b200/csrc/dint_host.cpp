@@ -13,6 +13,7 @@
 //                         include/dint/dict_posting_list.hpp:10-56 (per-list layout)
 #include <algorithm>
 #include <atomic>
+#include <cstdlib>
 #include <memory>
 #include <mutex>
 #include <new>
@@ -23,6 +24,25 @@ namespace dint {
 
 static thread_local std::string g_error;
 void set_error(const std::string& msg) { g_error = msg; }
+
+static uint32_t env_u32(const char* name, uint32_t dflt, uint32_t lo, uint32_t hi) {
+    const char* v = std::getenv(name);
+    if (!v || !*v) return dflt;
+    unsigned long x = std::strtoul(v, nullptr, 10);
+    return uint32_t(std::min<unsigned long>(std::max<unsigned long>(x, lo), hi));
+}
+
+const strip_limits& get_strip_limits() {
+    static const strip_limits lim = [] {
+        strip_limits l;
+        l.unit_ints = env_u32("DINT_B200_UNIT_INTS", 2048, 1024, DINT_UNIT_MAX_INTS) & ~3u;
+        l.unit_bytes = env_u32("DINT_B200_UNIT_BYTES", 3584, 512, DINT_UNIT_MAX_BYTES - 15);
+        l.strip_codewords = env_u32("DINT_B200_STRIP_CODEWORDS", 16, 1, 64);
+        l.strip_ints = std::min(512u, l.unit_ints - 256u);
+        return l;
+    }();
+    return lim;
+}
 
 static inline uint32_t msb64(uint64_t x) { return 63u - uint32_t(__builtin_clzll(x)); }
 
@@ -186,6 +206,12 @@ extern "C" {
 
 const char* dint_last_error(void) { return g_error.c_str(); }
 int dint_abi_version(void) { return DINT_B200_ABI_VERSION; }
+void dint_strip_limits(uint32_t* unit_max_ints, uint32_t* unit_max_bytes, uint32_t* strip_codewords) {
+    const dint::strip_limits& l = dint::get_strip_limits();
+    if (unit_max_ints) *unit_max_ints = l.unit_ints;
+    if (unit_max_bytes) *unit_max_bytes = l.unit_bytes;
+    if (strip_codewords) *strip_codewords = l.strip_codewords;
+}
 
 static int dict_finish(dint_dict* d, int rc, int device, dint_dict** out) {
     if (rc == DINT_OK) rc = validate(d);
@@ -275,7 +301,8 @@ struct walker {
         }
         return p;
     }
-    const uint8_t* walk8(const uint8_t* p, uint32_t cls, uint64_t count, uint32_t& acc) const {
+    template <typename Cut>
+    const uint8_t* walk8(const uint8_t* p, uint32_t cls, uint64_t count, uint32_t& acc, Cut&& cut) const {
         const uint32_t base = d->class_base[cls], csize = d->class_size[cls];
         uint64_t i = 0;
         while (i < count) {
@@ -300,8 +327,71 @@ struct walker {
             }
             i += len;
             if (i > count) return nullptr;
+            cut(p, i, acc);
         }
         return p;
+    }
+};
+
+// Cuts the codeword streams of a vroom file into strips and packs them into strip units
+// (include/dint_b200.h: dint_strip_unit). Fed codeword by codeword by the walker.
+struct strip_builder {
+    const dint::strip_limits lim;
+    const uint8_t* bin;
+    std::vector<dint_strip_unit>& units;
+    dint_strip_unit cur;
+    bool open = false;
+    // the strip being filled
+    const uint8_t* s_ptr = nullptr;
+    uint64_t s_out = 0;
+    uint32_t s_cw = 0, s_base = 0, s_sel = 0;
+    bool s_list_start = false;
+
+    strip_builder(const uint8_t* b, std::vector<dint_strip_unit>& u) : lim(dint::get_strip_limits()), bin(b), units(u) {
+        std::memset(&cur, 0, sizeof cur);
+    }
+    // a codeword stream begins at p (first codeword), producing output from index out_idx on
+    void begin_stream(const uint8_t* p, uint64_t out_idx, uint32_t sel, uint32_t acc, bool list_start) {
+        s_ptr = p;
+        s_out = out_idx;
+        s_cw = 0;
+        s_base = acc;
+        s_sel = sel;
+        s_list_start = list_start;
+    }
+    // one codeword was walked: the stream is now at q, out_idx integers are out, acc = sum(v + 1) of the list so far
+    void codeword(const uint8_t* q, uint64_t out_idx, uint32_t acc, bool stream_end) {
+        ++s_cw;
+        if (stream_end || s_cw >= lim.strip_codewords || out_idx - s_out >= lim.strip_ints) {
+            emit(q, out_idx);
+            begin_stream(q, out_idx, s_sel, acc, false);
+        }
+    }
+    void close_unit() {
+        if (!open) return;
+        for (uint32_t k = cur.n_strips; k < DINT_UNIT_STRIPS; ++k) cur.strip[k] = uint32_t(cur.n_ints) << 13;
+        units.push_back(cur);
+        open = false;
+    }
+    void emit(const uint8_t* end_ptr, uint64_t out_end) {
+        const uint32_t n = uint32_t(out_end - s_out);
+        const uint64_t in0 = uint64_t(s_ptr - bin), in1 = uint64_t(end_ptr - bin);
+        if (open && (cur.n_strips >= DINT_UNIT_STRIPS || in1 - cur.in_off > lim.unit_bytes ||
+                     cur.n_ints + n > lim.unit_ints || s_out != cur.out_off + cur.n_ints))
+            close_unit();
+        if (!open) {
+            std::memset(&cur, 0, sizeof cur);
+            cur.in_off = in0;
+            cur.out_off = s_out;
+            cur.doc_base = s_base;
+            open = true;
+        }
+        const uint32_t k = cur.n_strips;
+        cur.strip[k] = uint32_t(in0 - cur.in_off) | (uint32_t(cur.n_ints) << 13) | (s_sel << 25);
+        if (k && s_list_start) cur.list_starts |= 1u << k;
+        cur.n_ints = uint16_t(cur.n_ints + n);
+        cur.in_len = uint16_t(in1 - cur.in_off);
+        cur.n_strips = uint8_t(k + 1);
     }
 };
 
@@ -320,6 +410,7 @@ int dint_vroom_plan_create(const dint_dict* d, const void* bin_, size_t len, uin
     std::unique_ptr<dint_vroom_plan> plan(new (std::nothrow) dint_vroom_plan);
     if (!plan) return DINT_E_NOMEM;
     walker wk{d, bin, end};
+    strip_builder sb(bin, plan->strip_units);
     const uint8_t* p = bin;
     uint64_t out_off = 0;
     plan->list_offsets.push_back(0);
@@ -339,7 +430,9 @@ int dint_vroom_plan_create(const dint_dict* d, const void* bin_, size_t len, uin
             const uint8_t* seg_p = p;
             uint64_t seg_i = 0;
             uint32_t seg_base = 0;
+            sb.begin_stream(p, out_off, 0, 0, true);
             auto cut = [&](const uint8_t* q, uint64_t i, uint32_t a) {
+                sb.codeword(q, out_off + i, a, i == n);
                 if (i - seg_i >= chunk_ints && i < n) {
                     plan->segments.push_back({uint64_t(seg_p - bin), out_off + seg_i, uint32_t(i - seg_i), seg_base,
                                               uint32_t(q - seg_p), a - seg_base});
@@ -372,8 +465,10 @@ int dint_vroom_plan_create(const dint_dict* d, const void* bin_, size_t len, uin
                     return DINT_E_FORMAT;
                 }
                 const uint32_t acc0 = acc;
-                const uint8_t* q = sel < kSelectors ? wk.walk16(p + 1, sel, size, acc, [](const uint8_t*, uint64_t, uint32_t) {})
-                                                    : wk.walk8(p + 1, sel - kSelectors, size, acc);
+                sb.begin_stream(p + 1, out_off + done, sel, acc, done == 0);
+                auto cut = [&](const uint8_t* qq, uint64_t i, uint32_t a) { sb.codeword(qq, out_off + done + i, a, i == size); };
+                const uint8_t* q = sel < kSelectors ? wk.walk16(p + 1, sel, size, acc, cut)
+                                                    : wk.walk8(p + 1, sel - kSelectors, size, acc, cut);
                 if (!q) {
                     set_error("vroom .bin: codeword stream does not tile the block");
                     return DINT_E_FORMAT;
@@ -386,6 +481,7 @@ int dint_vroom_plan_create(const dint_dict* d, const void* bin_, size_t len, uin
         out_off += n;
         plan->list_offsets.push_back(out_off);
     }
+    sb.close_unit();
     plan->list_byte_offsets.push_back(len);
     plan->n_ints = out_off;
     if (plan->segments.size() > 0xFFFFFFF0ull) {
@@ -412,6 +508,10 @@ uint64_t dint_vroom_plan_num_lists(const dint_vroom_plan* p) { return p ? p->lis
 uint64_t dint_vroom_plan_num_ints(const dint_vroom_plan* p) { return p ? p->n_ints : 0; }
 uint64_t dint_vroom_plan_num_segments(const dint_vroom_plan* p) { return p ? p->segments.size() : 0; }
 const dint_segment* dint_vroom_plan_segments(const dint_vroom_plan* p) { return p ? p->segments.data() : nullptr; }
+uint64_t dint_vroom_plan_num_strip_units(const dint_vroom_plan* p) { return p ? p->strip_units.size() : 0; }
+const dint_strip_unit* dint_vroom_plan_strip_units(const dint_vroom_plan* p) {
+    return p ? p->strip_units.data() : nullptr;
+}
 uint64_t dint_vroom_plan_num_units(const dint_vroom_plan* p) { return p ? p->unit_first.size() - 1 : 0; }
 const uint32_t* dint_vroom_plan_unit_first(const dint_vroom_plan* p) { return p ? p->unit_first.data() : nullptr; }
 const uint64_t* dint_vroom_plan_list_offsets(const dint_vroom_plan* p) { return p ? p->list_offsets.data() : nullptr; }

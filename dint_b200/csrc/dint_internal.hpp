@@ -21,6 +21,16 @@ constexpr uint32_t kDefaultChunk = 1024;
 constexpr uint32_t kUnitInts = 2048;     // a work unit closes once it holds this many integers ...
 constexpr uint32_t kUnitSegments = 32;   // ... or this many segments (one per lane of the decoding warp)
 
+
+// strip tables (lane-sequential decoder): tunables, see dint_strip_limits()
+struct strip_limits {
+    uint32_t unit_ints;        // integers per strip unit (shared-memory output image per warp)
+    uint32_t unit_bytes;       // compressed bytes spanned by a strip unit (shared-memory input buffer per warp)
+    uint32_t strip_codewords;  // codewords per strip (steps of the per-thread loop)
+    uint32_t strip_ints;       // a strip also closes once it holds this many integers (runs of zeros)
+};
+const strip_limits& get_strip_limits();
+
 void set_error(const std::string& msg);
 
 inline uint16_t rd16(const uint8_t* p) { uint16_t v; std::memcpy(&v, p, 2); return v; }
@@ -36,6 +46,12 @@ struct dint_dict_view {
     uint32_t class_base[8]; // first row of each class (single kinds: one class at 0)
     uint32_t n_rows;
     uint32_t n_classes;
+    // lane-sequential decoder: the same 4-bit table, one 16-byte aligned slice per class indexed by the
+    // symbol itself; the first lut_rows rows of every class are staged in shared memory
+    const uint8_t* lens_cls;
+    uint32_t lens_cls_off[8];
+    uint32_t class_rows[8];
+    uint32_t lut_rows;
 };
 
 struct dint_dict {
@@ -50,10 +66,19 @@ struct dint_dict {
     std::vector<uint32_t> h_sums;  // sum(v_j + 1) over the entry, mod 2^32 (for doc_base of chunks)
     uint32_t* d_rows = nullptr;
     uint8_t* d_lens = nullptr;
+    uint8_t* d_lens_cls = nullptr;
+    uint32_t lens_cls_off[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    uint32_t lut_rows = 0;
     dint_dict_view view() const {
         dint_dict_view v;
         v.rows = d_rows;
         v.lens = d_lens;
+        v.lens_cls = d_lens_cls;
+        v.lut_rows = lut_rows;
+        for (int i = 0; i < 8; ++i) {
+            v.lens_cls_off[i] = lens_cls_off[i];
+            v.class_rows[i] = class_size[i];
+        }
         for (int i = 0; i < 8; ++i) v.class_base[i] = class_base[i];
         v.n_rows = n_rows;
         v.n_classes = n_classes;
@@ -65,6 +90,7 @@ struct dint_vroom_plan {
     uint64_t n_ints = 0;
     std::vector<dint_segment> segments;
     std::vector<uint32_t> unit_first;         // n_units + 1
+    std::vector<dint_strip_unit> strip_units; // lane-sequential decoder's work table
     std::vector<uint64_t> list_offsets;       // n_lists + 1
     std::vector<uint64_t> list_byte_offsets;  // n_lists + 1
 };

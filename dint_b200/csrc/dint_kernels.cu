@@ -18,6 +18,7 @@
 #include <string>
 
 #include "dint_decoder.cuh"
+#include "dint_strips.cuh"
 #include "dint_internal.hpp"
 
 namespace {
@@ -555,16 +556,41 @@ int dint_dict_upload(dint_dict* d) {
         lut[r >> 1] |= uint8_t(code << ((r & 1u) * 4u));
     }
     CUDA_TRY(cudaMemcpy(d->d_lens, lut.data(), lens_bytes, cudaMemcpyHostToDevice));
+    // the same table as one slice per class, indexed by the symbol (lane-sequential decoder). The first
+    // lut_rows rows of every class are staged in shared memory: everything for a single dictionary
+    // (32 KB), the 8192 most frequent rows of each class of a multi dictionary (<= 24 KB; covers every
+    // u8 block, whose symbols are < 256)
+    uint32_t max_rows = 0;
+    for (uint32_t c = 0; c < d->n_classes; ++c) max_rows = std::max(max_rows, std::min(d->class_size[c], dint::kNumEntries));
+    max_rows = std::max((max_rows + 31u) & ~31u, 32u);
+    d->lut_rows = (size_t(max_rows) / 2 * d->n_classes <= 40u * 1024u) ? max_rows : 8192u;
+    size_t cls_bytes = 0;
+    for (uint32_t c = 0; c < d->n_classes; ++c) {
+        d->lens_cls_off[c] = uint32_t(cls_bytes);
+        const uint32_t rows = std::max((d->class_size[c] + 31u) & ~31u, d->lut_rows);
+        cls_bytes += (size_t(rows) / 2 + 15) & ~size_t(15);
+    }
+    std::vector<uint8_t> lut_cls(cls_bytes + 16, 0);
+    for (uint32_t c = 0; c < d->n_classes; ++c)
+        for (uint32_t s = 0; s < d->class_size[c]; ++s) {
+            uint32_t len = uint32_t(d->h_lens[d->class_base[c] + s]) + 1, code = 0;
+            while ((1u << code) < len) ++code;
+            lut_cls[d->lens_cls_off[c] + (s >> 1)] |= uint8_t(code << ((s & 1u) * 4u));
+        }
+    CUDA_TRY(cudaMalloc(&d->d_lens_cls, lut_cls.size()));
+    CUDA_TRY(cudaMemcpy(d->d_lens_cls, lut_cls.data(), lut_cls.size(), cudaMemcpyHostToDevice));
     return DINT_OK;
 }
 
 void dint_dict_release_device(dint_dict* d) {
-    if (d->d_rows || d->d_lens) {
+    if (d->d_rows || d->d_lens || d->d_lens_cls) {
         device_guard g(d->device);
         cudaFree(d->d_rows);
         cudaFree(d->d_lens);
+        cudaFree(d->d_lens_cls);
         d->d_rows = nullptr;
         d->d_lens = nullptr;
+        d->d_lens_cls = nullptr;
     }
 }
 
@@ -622,6 +648,61 @@ int dint_decode_units(const dint_dict* d, const uint8_t* d_in, size_t in_bytes, 
         else { LAUNCH_SEG(false, OUT_FREQS, 16) }
     }
 #undef LAUNCH_SEG
+    ++g_launches;
+    CUDA_TRY(cudaGetLastError());
+    return DINT_OK;
+}
+
+int dint_decode_strips(const dint_dict* d, const uint8_t* d_in, size_t in_bytes, const dint_strip_unit* d_units,
+                       size_t n_units, uint32_t* d_out, int mode, void* stream) {
+    if (!d || mode < DINT_MODE_RAW || mode > DINT_MODE_FREQS) return DINT_E_ARG;
+    if (!d->d_rows) {
+        dint::set_error("dictionary is not device resident (no CPU fallback)");
+        return DINT_E_NODEVICE;
+    }
+    if (n_units == 0) return DINT_OK;
+    if (!d_in || !d_units || !d_out || (reinterpret_cast<uintptr_t>(d_units) & 15)) return DINT_E_ARG;
+    device_guard g(d->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    device_info di;
+    int rc = get_device_info(d->device, &di);
+    if (rc) return rc;
+    const dint::strip_limits& lim = dint::get_strip_limits();
+    strip_params P;
+    P.dv = d->view();
+    P.in = d_in;
+    P.in_bytes = in_bytes;
+    P.units = d_units;
+    P.n_units = n_units;
+    P.out = d_out;
+    P.unit_ints = lim.unit_ints;
+    P.unit_bytes = lim.unit_bytes;
+    P.image_words = strip_image_words(lim.unit_ints);
+    P.bits_words = strip_bits_words(lim.unit_ints);
+    P.inbuf_bytes = strip_inbuf_bytes(lim.unit_bytes);
+    // one persistent CTA per SM: as many warps as the shared-memory budget holds next to the length table
+    // (the rest of the 256 KB stays L1 for the dictionary rows)
+    const size_t fixed = size_t(P.dv.lut_rows) / 2 * P.dv.n_classes + 8 * sizeof(strip_class);
+    const size_t per_warp = strip_warp_smem(lim.unit_ints, lim.unit_bytes);
+    static const uint32_t budget_kb = [] {
+        const char* v = std::getenv("DINT_B200_STRIP_SMEM_KB");
+        return v && *v ? uint32_t(std::strtoul(v, nullptr, 10)) : 200u;
+    }();
+    const size_t budget = std::min(size_t(budget_kb) * 1024, size_t(di.max_smem_optin));
+    if (fixed + per_warp > budget) {
+        dint::set_error("strip decoder: shared-memory budget too small for one warp");
+        return DINT_E_ARG;
+    }
+    int warps = int(std::min<size_t>((budget - fixed) / per_warp, 24));
+    const size_t smem = fixed + size_t(warps) * per_warp;
+    const int grid = int(std::max<uint64_t>(1, std::min<uint64_t>((n_units + warps - 1) / warps, uint64_t(di.sms))));
+#define LAUNCH_STRIPS(M)                                                                                   \
+    CUDA_TRY(cudaFuncSetAttribute(decode_strips_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))); \
+    decode_strips_kernel<M><<<grid, warps * 32, smem, st>>>(P);
+    if (mode == DINT_MODE_RAW) { LAUNCH_STRIPS(OUT_RAW) }
+    else if (mode == DINT_MODE_DOCIDS) { LAUNCH_STRIPS(OUT_DOCIDS) }
+    else { LAUNCH_STRIPS(OUT_FREQS) }
+#undef LAUNCH_STRIPS
     ++g_launches;
     CUDA_TRY(cudaGetLastError());
     return DINT_OK;
@@ -711,10 +792,9 @@ int dint_checksum_lists(const uint32_t* d_values, const uint64_t* d_list_offsets
 struct dint_vroom_ctx {
     const dint_dict* dict = nullptr;
     uint32_t block_size = 0;
-    uint64_t n_lists = 0, n_ints = 0, n_segs = 0, n_units = 0, in_bytes = 0;
+    uint64_t n_lists = 0, n_ints = 0, n_units = 0, in_bytes = 0;
     uint8_t* d_in = nullptr;
-    dint_segment* d_segs = nullptr;
-    uint32_t* d_unit_first = nullptr;
+    dint_strip_unit* d_units = nullptr;
     uint64_t* d_list_offsets = nullptr;
     uint32_t* d_out = nullptr;
     uint64_t* d_sums = nullptr;
@@ -733,8 +813,7 @@ int dint_vroom_ctx_create(const dint_dict* d, const dint_vroom_plan* plan, uint3
     c->block_size = block_size ? block_size : dint::kDefaultBlock;
     c->n_lists = plan->list_offsets.size() - 1;
     c->n_ints = plan->n_ints;
-    c->n_segs = plan->segments.size();
-    c->n_units = plan->unit_first.empty() ? 0 : plan->unit_first.size() - 1;
+    c->n_units = plan->strip_units.size();
     c->in_bytes = plan->list_byte_offsets.back();
     auto fail = [&](cudaError_t e) {
         dint::set_error(std::string("dint_vroom_ctx_create: ") + cudaGetErrorString(e));
@@ -743,19 +822,15 @@ int dint_vroom_ctx_create(const dint_dict* d, const dint_vroom_plan* plan, uint3
     };
     cudaError_t e;
     if ((e = cudaMalloc(&c->d_in, c->in_bytes + 16)) != cudaSuccess) return fail(e);
-    if ((e = cudaMalloc(&c->d_segs, (c->n_segs + 1) * sizeof(dint_segment))) != cudaSuccess) return fail(e);
-    if ((e = cudaMalloc(&c->d_unit_first, (c->n_units + 1) * 4)) != cudaSuccess) return fail(e);
+    if ((e = cudaMalloc(&c->d_units, (c->n_units + 1) * sizeof(dint_strip_unit))) != cudaSuccess) return fail(e);
     if ((e = cudaMalloc(&c->d_list_offsets, (c->n_lists + 1) * 8)) != cudaSuccess) return fail(e);
     if ((e = cudaMalloc(&c->d_out, (c->n_ints + 1) * 4)) != cudaSuccess) return fail(e);
     if ((e = cudaMalloc(&c->d_sums, (c->n_lists + 1) * 8)) != cudaSuccess) return fail(e);
-    if ((e = cudaMemcpy(c->d_segs, plan->segments.data(), c->n_segs * sizeof(dint_segment), cudaMemcpyHostToDevice)) !=
-        cudaSuccess)
+    if (c->n_units && (e = cudaMemcpy(c->d_units, plan->strip_units.data(), c->n_units * sizeof(dint_strip_unit),
+                                      cudaMemcpyHostToDevice)) != cudaSuccess)
         return fail(e);
     if ((e = cudaMemcpy(c->d_list_offsets, plan->list_offsets.data(), (c->n_lists + 1) * 8, cudaMemcpyHostToDevice)) !=
         cudaSuccess)
-        return fail(e);
-    if (c->n_units && (e = cudaMemcpy(c->d_unit_first, plan->unit_first.data(), (c->n_units + 1) * 4,
-                                      cudaMemcpyHostToDevice)) != cudaSuccess)
         return fail(e);
     *out = c;
     return DINT_OK;
@@ -765,8 +840,7 @@ void dint_vroom_ctx_destroy(dint_vroom_ctx* c) {
     if (!c) return;
     device_guard g(c->dict->device);
     cudaFree(c->d_in);
-    cudaFree(c->d_segs);
-    cudaFree(c->d_unit_first);
+    cudaFree(c->d_units);
     cudaFree(c->d_list_offsets);
     cudaFree(c->d_out);
     cudaFree(c->d_sums);
@@ -785,8 +859,7 @@ int dint_vroom_decode_host(dint_vroom_ctx* c, const void* h_bin, size_t len, int
     device_guard g(c->dict->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (len) CUDA_TRY(cudaMemcpyAsync(c->d_in, h_bin, len, cudaMemcpyHostToDevice, st));
-    int rc = dint_decode_units(c->dict, c->d_in, len, c->d_segs, c->n_segs, c->n_units ? c->d_unit_first : nullptr,
-                               c->n_units, c->d_out, mode, stream);
+    int rc = dint_decode_strips(c->dict, c->d_in, len, c->d_units, c->n_units, c->d_out, mode, stream);
     if (rc) return rc;
     if (h_sums && c->n_lists) {
         rc = dint_checksum_lists(c->d_out, c->d_list_offsets, c->n_lists, c->d_sums, stream);
@@ -799,8 +872,7 @@ int dint_vroom_decode_host(dint_vroom_ctx* c, const void* h_bin, size_t len, int
 
 int dint_vroom_decode_resident(dint_vroom_ctx* c, int mode, void* stream) {
     if (!c) return DINT_E_ARG;
-    return dint_decode_units(c->dict, c->d_in, c->in_bytes, c->d_segs, c->n_segs, c->n_units ? c->d_unit_first : nullptr,
-                             c->n_units, c->d_out, mode, stream);
+    return dint_decode_strips(c->dict, c->d_in, c->in_bytes, c->d_units, c->n_units, c->d_out, mode, stream);
 }
 
 int dint_vroom_ctx_sync(dint_vroom_ctx* c, void* stream) {

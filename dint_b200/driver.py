@@ -45,7 +45,7 @@ def _structured_to_device(arr, dev):
 class VroomFile:
     """A vroom-encoded .bin + its dictionary, resident on one GPU, ready for batch decode."""
 
-    def __init__(self, type_, bin_bytes, dict_bytes, device=0, block_size=256, chunk_ints=0):
+    def __init__(self, type_, bin_bytes, dict_bytes, device=0, block_size=256, chunk_ints=0, engine="strips"):
         if type_ not in capi.KIND_OF_TYPE:
             raise ValueError(f"unknown type '{type_}'")  # decode.cpp:259 logs "ERROR: unknown type"
         self.type = type_
@@ -53,7 +53,13 @@ class VroomFile:
         self.block_size = block_size
         self.dict = capi.Dictionary(capi.KIND_OF_TYPE[type_], dict_bytes, device=device)
         self.plan = capi.VroomPlan(self.dict, bin_bytes, block_size=block_size, chunk_ints=chunk_ints)
+        # engine: "strips" = lane-sequential decoder over the plan's strip table (dint_decode_strips, the
+        # fast path); "units" = warp-per-work-unit tile decoder over the segment table (dint_decode_units)
+        if engine not in ("strips", "units"):
+            raise ValueError(f"unknown engine '{engine}'")
+        self.engine = engine
         self.d_in = _to_device_bytes(bin_bytes, self.dev)
+        self.d_strip_units = _structured_to_device(self.plan.strip_units, self.dev)
         self.d_segs = _structured_to_device(self.plan.segments, self.dev)
         self.d_unit_first = torch.from_numpy(self.plan.unit_first.astype(np.int64)).to(torch.int32).to(self.dev)
         self.d_list_offsets = torch.from_numpy(self.plan.list_offsets.astype(np.int64)).to(self.dev)
@@ -65,6 +71,10 @@ class VroomFile:
         if out is None:
             out = torch.empty(self.n_ints, dtype=torch.int32, device=self.dev)
         st = (stream or torch.cuda.current_stream(self.dev)).cuda_stream
+        if self.engine == "strips":
+            capi.decode_strips(self.dict, self.d_in.data_ptr(), self.plan.in_bytes, self.d_strip_units.data_ptr(),
+                               int(self.plan.n_strip_units), out.data_ptr(), mode, stream=st)
+            return out
         capi.decode_units(self.dict, self.d_in.data_ptr(), self.plan.in_bytes, self.d_segs.data_ptr(),
                           int(self.plan.n_segments), self.d_unit_first.data_ptr(), int(self.plan.n_units),
                           out.data_ptr(), mode, stream=st)

@@ -27,6 +27,9 @@
  *                            include/dint/dict_posting_list.hpp:284-318, 113-124, 164-169
  *                            include/dint/dint_codecs.hpp:13-49, 269-274, 460-510
  *                            include/ds2i/block_codecs.hpp:130-150
+ *   dint_decode_strips     the same two decoders, lane-sequential: one THREAD walks one strip of
+ *                          <= 16 codewords exactly like the reference's scalar loop
+ *                            vroom_env/dint_codecs.hpp:37-107 (u16), :574-609 (u8)
  *   dint_decode_list_host  one Decoder::decode(dict, in, out, universe, n) call, host buffers
  *   dint_vroom_ctx_* /     the whole decode_dint() loop of vroom_env/decode.cpp:139-150 on HOST
  *   dint_vroom_decode_host   buffers: H2D of the .bin, batch decode, D2H of the result
@@ -50,7 +53,7 @@
 extern "C" {
 #endif
 
-#define DINT_B200_ABI_VERSION 2
+#define DINT_B200_ABI_VERSION 3
 
 /* dictionary kinds == the reference's three dictionary types */
 enum {
@@ -102,6 +105,39 @@ typedef struct dint_block {
     uint32_t reserved;
 } dint_block;
 
+/* Strip tables: the work decomposition of the lane-sequential decoder (dint_decode_strips).
+ * A STRIP is a piece of one codeword stream that starts on a codeword boundary, holds at most
+ * a fixed number of codewords (default 16) of ONE dictionary class / symbol width and
+ * produces a known number of integers; one thread decodes one strip. A STRIP UNIT is up to 32
+ * consecutive strips (one per lane of a warp) whose compressed bytes lie within
+ * DINT_UNIT_MAX_BYTES of each other and whose outputs are contiguous in the packed output
+ * (at most DINT_UNIT_MAX_INTS integers). 160 bytes, 16-byte aligned. */
+#define DINT_UNIT_STRIPS 32
+#define DINT_UNIT_MAX_INTS 4095u  /* out_rel has 12 bits                                    */
+#define DINT_UNIT_MAX_BYTES 8191u /* in_rel has 13 bits                                     */
+/* The limits this build of the library actually uses (they size the decoder's shared-memory
+ * buffers; defaults 2048 integers / 3584 bytes / 16 codewords per strip; the environment
+ * variables DINT_B200_UNIT_INTS, DINT_B200_UNIT_BYTES, DINT_B200_STRIP_CODEWORDS override
+ * them at first use, for tuning). Units beyond them are rejected by dint_decode_strips'
+ * kernels (their output is left untouched). */
+void dint_strip_limits(uint32_t* unit_max_ints, uint32_t* unit_max_bytes, uint32_t* strip_codewords);
+typedef struct dint_strip_unit {
+    uint64_t in_off;      /* byte offset of the unit's first strip in the .bin                */
+    uint64_t out_off;     /* index of the unit's first output integer                         */
+    uint32_t doc_base;    /* DOCIDS mode: docid[first] = doc_base + v[first]                  */
+    uint32_t list_starts; /* bit k (k >= 1): strip k begins a new list, i.e. the docID prefix
+                             sum restarts there (docid = v). Strip 0 is covered by doc_base. */
+    uint16_t in_len;      /* bytes from in_off to the end of the last strip                   */
+    uint16_t n_ints;      /* integers the unit produces                                       */
+    uint8_t n_strips;     /* 1..32                                                            */
+    uint8_t reserved[3];
+    /* strip k: bits 0-12 in_rel (bytes from in_off to its first codeword), bits 13-24 out_rel
+     * (integers before it inside the unit), bits 25-28 selector: 0..5 = u16 codewords of class
+     * selector, 6..11 = u8 codewords of class selector - 6 (single dictionaries: 0). The strip
+     * produces out_rel[k+1] - out_rel[k] integers (the last one n_ints - out_rel). */
+    uint32_t strip[DINT_UNIT_STRIPS];
+} dint_strip_unit;
+
 typedef struct dint_dict dint_dict;
 typedef struct dint_vroom_plan dint_vroom_plan;
 typedef struct dint_index_plan dint_index_plan;
@@ -144,6 +180,10 @@ const dint_segment* dint_vroom_plan_segments(const dint_vroom_plan* p);
  * num_units + 1 entries. */
 uint64_t dint_vroom_plan_num_units(const dint_vroom_plan* p);
 const uint32_t* dint_vroom_plan_unit_first(const dint_vroom_plan* p);
+/* Strip units of the same file (see dint_strip_unit); what dint_decode_strips and the
+ * dint_vroom_ctx_* calls consume. */
+uint64_t dint_vroom_plan_num_strip_units(const dint_vroom_plan* p);
+const dint_strip_unit* dint_vroom_plan_strip_units(const dint_vroom_plan* p);
 /* n_lists + 1 offsets into the packed output; list i is [off[i], off[i+1]) */
 const uint64_t* dint_vroom_plan_list_offsets(const dint_vroom_plan* p);
 /* n_lists + 1 byte offsets of the list headers; the last one is the file size */
@@ -173,6 +213,15 @@ int dint_decode_segments(const dint_dict* d, const uint8_t* d_in, size_t in_byte
  * dint_vroom_plan_unit_first). dint_decode_segments groups every 8 consecutive segments. */
 int dint_decode_units(const dint_dict* d, const uint8_t* d_in, size_t in_bytes, const dint_segment* d_segs, size_t n_segs,
                       const uint32_t* d_unit_first, size_t n_units, uint32_t* d_out, int mode, void* stream);
+
+/* Lane-sequential decode of a strip table (the fast path for whole vroom files): one warp per
+ * strip unit, one thread per strip; the unit's bytes are staged in shared memory with 16-byte
+ * cp.async, every thread runs the reference's scalar codeword loop over its strip into a
+ * shared-memory image of the unit's output, and the warp writes the image with the fused
+ * transform of `mode` in 16-byte aligned, fully coalesced stores. d_units: n_units DEVICE
+ * dint_strip_unit records. */
+int dint_decode_strips(const dint_dict* d, const uint8_t* d_in, size_t in_bytes, const dint_strip_unit* d_units,
+                       size_t n_units, uint32_t* d_out, int mode, void* stream);
 
 /* d_lists: the m_lists bytes of the index. Writes docids and freqs (enumerator
  * semantics: docid(), freq()) of every block into the packed arrays. Either output

@@ -22,20 +22,24 @@ def _np(t):
 def vroom_files(golden):
     cache = {}
 
-    def get(type_, part, chunk_ints=0):
-        key = (type_, part, chunk_ints)
+    def get(type_, part, chunk_ints=0, engine="strips"):
+        key = (type_, part, chunk_ints, engine)
         if key not in cache:
             cache[key] = driver.VroomFile(type_, golden.bytes(golden.vroom_name(type_, part)),
-                                          golden.bytes(golden.dict_name(type_, part)), chunk_ints=chunk_ints)
+                                          golden.bytes(golden.dict_name(type_, part)), chunk_ints=chunk_ints, engine=engine)
         return cache[key]
     return get
 
 
+ENGINES = ("strips", "units")  # lane-sequential strip decoder (default) / warp-per-unit tile decoder
+
+
+@pytest.mark.parametrize("engine", ENGINES)
 @pytest.mark.parametrize("type_", g.TYPES)
 @pytest.mark.parametrize("part,key", (("docs", "vroom_docs_gaps_sha256"), ("freqs", "vroom_freqs_minus1_sha256")))
-def test_vroom_raw_equals_reference_output(golden, oracle, vroom_files, type_, part, key):
+def test_vroom_raw_equals_reference_output(golden, oracle, vroom_files, type_, part, key, engine):
     """config 1: vroom decode of the whole test collection, full-output comparison"""
-    vf = vroom_files(type_, part)
+    vf = vroom_files(type_, part, engine=engine)
     before = capi.kernel_launches()
     out = _np(vf.decode(mode=capi.MODE_RAW))
     assert capi.kernel_launches() == before + 1
@@ -46,15 +50,15 @@ def test_vroom_raw_equals_reference_output(golden, oracle, vroom_files, type_, p
     assert np.array_equal(out, want)
 
 
+@pytest.mark.parametrize("engine,chunk", (("strips", 0), ("units", 0), ("units", 1), ("units", 33), ("units", 100)))
 @pytest.mark.parametrize("type_", g.TYPES)
-@pytest.mark.parametrize("chunk", (0, 1, 33, 100))
-def test_vroom_fused_docids_and_freqs(golden, vroom_files, type_, chunk):
+def test_vroom_fused_docids_and_freqs(golden, vroom_files, type_, engine, chunk):
     """fused prefix sum / +1 shift must reproduce the .docs / .freqs collection itself"""
-    d = _np(vroom_files(type_, "docs", chunk).decode(mode=capi.MODE_DOCIDS))
+    d = _np(vroom_files(type_, "docs", chunk, engine).decode(mode=capi.MODE_DOCIDS))
     assert g.sha(d.tobytes()) == golden.sha["docids_sha256"]
-    f = _np(vroom_files(type_, "freqs", chunk).decode(mode=capi.MODE_FREQS))
+    f = _np(vroom_files(type_, "freqs", chunk, engine).decode(mode=capi.MODE_FREQS))
     assert g.sha(f.tobytes()) == golden.sha["freqs_sha256"]
-    r = _np(vroom_files(type_, "docs", chunk).decode(mode=capi.MODE_RAW))
+    r = _np(vroom_files(type_, "docs", chunk, engine).decode(mode=capi.MODE_RAW))
     assert g.sha(r.tobytes()) == golden.sha["vroom_docs_gaps_sha256"]
 
 
@@ -97,10 +101,10 @@ def test_query_log_ragged_batch(golden, oracle):
     assert np.array_equal(_np(out), want)
 
 
-def _decode_lists(type_, dict_bytes, lists_vals, block_size=256, chunk_ints=0, mode=capi.MODE_RAW, **kw):
+def _decode_lists(type_, dict_bytes, lists_vals, block_size=256, chunk_ints=0, mode=capi.MODE_RAW, engine="strips", **kw):
     di = sb.DictImage(capi.KIND_OF_TYPE[type_], dict_bytes)
     data = b"".join(sb.encode_vroom_list(di, v, block_size=block_size, **kw) for v in lists_vals)
-    vf = driver.VroomFile(type_, data, dict_bytes, chunk_ints=chunk_ints, block_size=block_size)
+    vf = driver.VroomFile(type_, data, dict_bytes, chunk_ints=chunk_ints, block_size=block_size, engine=engine)
     return _np(vf.decode(mode=mode)), data, vf
 
 
@@ -124,9 +128,9 @@ def test_edge_case_streams(golden, oracle, type_, kw):
     dict_bytes = golden.bytes(golden.dict_name(type_, "docs"))
     want = np.concatenate([np.asarray(v, dtype=np.uint32) for v in lists])
     for sels in ([0, 6, 3, 9, 1, 7], [8], [2]):
-        for chunk in (0, 1, 5):
-            out, data, vf = _decode_lists(type_, dict_bytes, lists, chunk_ints=chunk, selectors=sels, **kw)
-            assert np.array_equal(out, want), (sels, chunk)
+        for engine, chunk in (("strips", 0), ("units", 0), ("units", 1), ("units", 5)):
+            out, data, vf = _decode_lists(type_, dict_bytes, lists, chunk_ints=chunk, engine=engine, selectors=sels, **kw)
+            assert np.array_equal(out, want), (sels, engine, chunk)
             ho = oracle.dict_parse(KINDS[type_], dict_bytes)
             o, _ = oracle.vroom_decode_file(ho, data, len(want), len(lists))
             assert np.array_equal(o, want)
@@ -135,6 +139,26 @@ def test_edge_case_streams(golden, oracle, type_, kw):
             exp = np.concatenate([(np.cumsum(np.asarray(v, dtype=np.uint64) + 1) - 1).astype(np.uint32) for v in lists])
             assert np.array_equal(docs, exp)
             assert np.array_equal(_np(vf.decode(mode=capi.MODE_FREQS)), want + np.uint32(1))
+
+
+@pytest.mark.parametrize("type_", ("single_packed_dint", "multi_packed_dint"))
+@pytest.mark.parametrize("shift", (1, 2, 3))
+def test_strips_unaligned_output_and_input(golden, type_, shift):
+    """output array / .bin that do not start on a 16-byte boundary: the strip decoder falls back to
+    scalar stores and stages the input from the enclosing aligned blocks"""
+    bin_ = golden.bytes(golden.vroom_name(type_, "docs"))
+    vf = driver.VroomFile(type_, bin_, golden.bytes(golden.dict_name(type_, "docs")))
+    want = _np(vf.decode(mode=capi.MODE_DOCIDS))
+    assert g.sha(want.tobytes()) == golden.sha["docids_sha256"]
+    out = torch.full((vf.n_ints + 8,), -1, dtype=torch.int32, device="cuda")
+    d_in = torch.zeros(len(bin_) + 64, dtype=torch.uint8, device="cuda")
+    d_in[shift * 5:shift * 5 + len(bin_)] = vf.d_in
+    capi.decode_strips(vf.dict, d_in.data_ptr() + shift * 5, len(bin_), vf.d_strip_units.data_ptr(),
+                       int(vf.plan.n_strip_units), out.data_ptr() + 4 * shift, capi.MODE_DOCIDS,
+                       stream=torch.cuda.current_stream().cuda_stream)
+    got = _np(out)
+    assert np.array_equal(got[shift:shift + vf.n_ints], want)
+    assert np.all(got[:shift] == 0xFFFFFFFF) and np.all(got[shift + vf.n_ints:] == 0xFFFFFFFF)
 
 
 def test_empty_batch_and_empty_file(golden):

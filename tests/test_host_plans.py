@@ -137,3 +137,63 @@ def test_chunking_respects_exception_payload(golden):
             pos += 4 if v < 65536 else 6
         for s in plan.segments:
             assert expect[int(s["out_off"])] == int(s["in_off"])
+
+
+@pytest.mark.parametrize("type_", g.TYPES)
+@pytest.mark.parametrize("part", ("docs", "freqs"))
+def test_strip_units_tile_the_file(oracle, golden, type_, part):
+    """strip table of the lane-sequential decoder: units tile the output, every strip starts on a
+    codeword boundary of the right class and decodes (with the oracle) to its slice of the output"""
+    kind = KINDS[type_]
+    bin_ = golden.bytes(golden.vroom_name(type_, part))
+    d = capi.Dictionary(kind, golden.bytes(golden.dict_name(type_, part)))
+    plan = capi.VroomPlan(d, bin_)
+    lim = capi.strip_limits()
+    ho = oracle.dict_parse(kind, golden.bytes(golden.dict_name(type_, part)))
+    vals, _ = oracle.vroom_decode_file(ho, bin_, golden.n_postings, golden.n_lists)
+    U = plan.strip_units
+    assert len(U) == plan.n_strip_units > 0
+    n_ints = U["n_ints"].astype(np.int64)
+    assert int(U["out_off"][0]) == 0 and np.array_equal(U["out_off"][1:].astype(np.int64), (U["out_off"].astype(np.int64) + n_ints)[:-1])
+    assert int(U["out_off"][-1]) + int(n_ints[-1]) == golden.n_postings
+    assert n_ints.min() >= 1 and n_ints.max() <= lim["unit_ints"] and int(U["in_len"].max()) <= lim["unit_bytes"]
+    assert U["n_strips"].min() >= 1 and U["n_strips"].max() <= 32
+    assert np.all(U["in_off"].astype(np.int64) + U["in_len"] <= len(bin_))
+    in_rel, out_rel, sel = U["strip"] & 0x1FFF, (U["strip"] >> 13) & 0xFFF, (U["strip"] >> 25) & 15
+    k = np.arange(32)[None, :]
+    used = k < U["n_strips"][:, None]
+    assert np.all(out_rel[:, 0] == 0) and np.all(in_rel[:, 0] == 0)
+    assert np.all(out_rel[~used] == np.broadcast_to(U["n_ints"][:, None], out_rel.shape)[~used])
+    assert np.all(np.diff(np.where(used, out_rel.astype(np.int64), 1 << 20), axis=1)[used[:, 1:]] > 0)  # no empty strips
+    assert np.all(sel[used] < (12 if kind == 2 else 1))
+    # docID bookkeeping: doc_base = sum(v + 1) over the list's postings before the unit; list_starts marks list heads
+    csum = np.concatenate([np.zeros(1, dtype=np.uint64), np.cumsum(vals.astype(np.uint64) + np.uint64(1))])
+    lo = plan.list_offsets.astype(np.int64)
+    list_of = np.searchsorted(lo, U["out_off"].astype(np.int64), side="right") - 1
+    want = (csum[U["out_off"].astype(np.int64)] - csum[lo[list_of]]) & np.uint64(0xFFFFFFFF)
+    assert np.array_equal(U["doc_base"].astype(np.uint64), want)
+    pos = U["out_off"].astype(np.int64)[:, None] + out_rel
+    is_head = np.isin(pos, lo[:-1]) & used
+    is_head[:, 0] = False
+    bits = ((U["list_starts"][:, None] >> k) & 1).astype(bool)
+    assert np.array_equal(bits, is_head)
+    heads_covered = np.isin(lo[:-1], pos[used])
+    assert heads_covered.all()  # every list begins a strip
+    # decode sampled units strip by strip
+    raw = np.frombuffer(bin_ + b"\0" * 64, dtype=np.uint8)
+    rng = np.random.default_rng(11)
+    for ui in np.unique(np.concatenate([rng.integers(0, len(U), 60), [0, len(U) - 1]])):
+        u = U[ui]
+        ends = list(out_rel[ui][1:u["n_strips"]]) + [int(u["n_ints"])]
+        for j in range(int(u["n_strips"])):
+            n = int(ends[j]) - int(out_rel[ui][j])
+            start = int(u["in_off"]) + int(in_rel[ui][j])
+            if kind != 2:
+                a, used_bytes = oracle.vroom_decode_list(ho, raw[start:], n)
+            else:
+                fake = np.concatenate([np.array([sel[ui][j]], dtype=np.uint8), raw[start:start + 8 * n + 64]])
+                a, used_bytes = oracle.block_decode(ho, fake, 0, n, block_size=n)
+                used_bytes -= 1
+            o = int(u["out_off"]) + int(out_rel[ui][j])
+            assert np.array_equal(a, vals[o:o + n])
+            assert start + used_bytes <= int(u["in_off"]) + int(u["in_len"])
