@@ -117,6 +117,18 @@ __device__ __forceinline__ void sts_tail3(uint32_t a, uint32_t L, uint32_t y, ui
         "r"(L), "r"(y), "r"(z), "r"(w)
         : "memory");
 }
+// the same for an entry of 2^k words (k = 0: nothing, 1: word 1, >= 2: words 1..3)
+__device__ __forceinline__ void sts_tail3_log2(uint32_t a, uint32_t k, uint32_t y, uint32_t z, uint32_t w) {
+    asm volatile(
+        "{\n\t.reg .pred p1, p2;\n\t"
+        "setp.gt.u32 p1, %1, 0;\n\t"
+        "setp.gt.u32 p2, %1, 1;\n\t"
+        "@p1 st.shared.u32 [%0+4], %2;\n\t"
+        "@p2 st.shared.u32 [%0+8], %3;\n\t"
+        "@p2 st.shared.u32 [%0+12], %4;\n\t}" ::"r"(a),
+        "r"(k), "r"(y), "r"(z), "r"(w)
+        : "memory");
+}
 __device__ __forceinline__ void sts_4(uint32_t a, uint4 v) {
     asm volatile(
         "st.shared.u32 [%0], %1;\n\tst.shared.u32 [%0+4], %2;\n\tst.shared.u32 [%0+8], %3;\n\tst.shared.u32 [%0+12], %4;" ::"r"(a),

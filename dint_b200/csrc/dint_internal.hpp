@@ -52,6 +52,18 @@ struct dint_dict_view {
     uint32_t lens_cls_off[8];
     uint32_t class_rows[8];
     uint32_t lut_rows;
+    // lane-sequential decoder, tables every CTA stages in shared memory (one contiguous image):
+    //   hot0   [n_classes][hot_rows] uint4   words 0..3 of the first hot_rows rows of every class
+    //   hot1   [n_classes][hot_rows] uint4   words 4..7
+    //   hotlen [n_classes][hot_rows] u8      log2(entry length) of those rows
+    //   group  per class, one byte per 32 rows: log2(length) when the 32 rows agree, else 0xFF
+    //          (the rows of a DSF dictionary are almost sorted by length beyond the first few hundred)
+    const uint8_t* strip_tables;
+    uint32_t strip_tables_bytes;  // multiple of 16
+    uint32_t hot_rows;            // power of two >= 256 (every u8 symbol is hot)
+    uint32_t group_off[8];        // byte offset of the class's group slice inside the image
+    uint32_t detail_off[8];       // byte offset of the class's mixed-group detail: group byte 9 + k selects the 16
+                                  // bytes of per-row nibbles at detail_off + 16 k; 0xFF = look in lens_cls (global)
 };
 
 struct dint_dict {
@@ -69,12 +81,22 @@ struct dint_dict {
     uint8_t* d_lens_cls = nullptr;
     uint32_t lens_cls_off[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     uint32_t lut_rows = 0;
+    uint8_t* d_strip_tables = nullptr;
+    uint32_t strip_tables_bytes = 0;
+    uint32_t hot_rows = 0;
+    uint32_t group_off[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    uint32_t detail_off[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     dint_dict_view view() const {
         dint_dict_view v;
         v.rows = d_rows;
         v.lens = d_lens;
         v.lens_cls = d_lens_cls;
         v.lut_rows = lut_rows;
+        v.strip_tables = d_strip_tables;
+        v.strip_tables_bytes = strip_tables_bytes;
+        v.hot_rows = hot_rows;
+        for (int i = 0; i < 8; ++i) v.group_off[i] = group_off[i];
+        for (int i = 0; i < 8; ++i) v.detail_off[i] = detail_off[i];
         for (int i = 0; i < 8; ++i) {
             v.lens_cls_off[i] = lens_cls_off[i];
             v.class_rows[i] = class_size[i];

@@ -516,6 +516,11 @@ int plan_grid(K kernel, const dint_dict* d, uint64_t n_units, int* grid, size_t*
     return DINT_OK;
 }
 
+uint32_t env_u32_k(const char* name, uint32_t dflt) {
+    const char* v = std::getenv(name);
+    return v && *v ? uint32_t(std::strtoul(v, nullptr, 10)) : dflt;
+}
+
 struct device_guard {
     int prev = -1;
     bool ok = false;
@@ -579,15 +584,86 @@ int dint_dict_upload(dint_dict* d) {
         }
     CUDA_TRY(cudaMalloc(&d->d_lens_cls, lut_cls.size()));
     CUDA_TRY(cudaMemcpy(d->d_lens_cls, lut_cls.data(), lut_cls.size(), cudaMemcpyHostToDevice));
+    // shared-memory image of the lane-sequential decoder (dint_dict_view::strip_tables). A multi dictionary
+    // keeps the 256 rows of every class that u8 codewords can address (they are also the most frequent
+    // ones, the builder sorts by frequency); a single dictionary keeps its first 2048 rows.
+    {
+        uint32_t hot = 256;
+        if (d->n_classes == 1) {
+            const uint32_t cap = env_u32_k("DINT_B200_HOT_ROWS", 2048);
+            while (hot < cap && hot < d->class_size[0]) hot *= 2;
+        }
+        d->hot_rows = hot;
+        const size_t nc = d->n_classes;
+        const size_t hot0 = 0, hot1 = nc * hot * 16, hotlen = 2 * nc * hot * 16;
+        size_t off = hotlen + nc * hot;
+        for (uint32_t c = 0; c < d->n_classes; ++c) {
+            off = (off + 3) & ~size_t(3);
+            d->group_off[c] = uint32_t(off);
+            off += (size_t(d->class_size[c]) + 31) / 32;
+        }
+        // group byte: log2(length) when the 32 rows agree; else 9 + k = the k-th mixed group of the class beyond
+        // the hot rows (its per-row nibbles follow in the detail table), 0xFF once a class has more than 246 of them
+        std::vector<std::vector<uint8_t>> detail(d->n_classes);
+        std::vector<uint8_t> groups(off, 0);
+        auto code_of = [&](uint32_t row) {
+            uint32_t len = uint32_t(d->h_lens[row]) + 1, code = 0;
+            while ((1u << code) < len) ++code;
+            return code;
+        };
+        for (uint32_t c = 0; c < d->n_classes; ++c) {
+            const uint32_t rows = d->class_size[c], base = d->class_base[c];
+            for (uint32_t g = 0; g * 32 < rows; ++g) {
+                const uint32_t first = code_of(base + g * 32), hi = std::min(rows, g * 32 + 32);
+                bool same = true;
+                for (uint32_t s = g * 32; s < hi; ++s) same = same && code_of(base + s) == first;
+                uint8_t v = uint8_t(first);
+                if (!same) {
+                    const size_t k = detail[c].size() / 16;
+                    if (g * 32 + 32 <= hot || k > 245) v = 0xFF;  // hot rows never consult the group table
+                    else {
+                        v = uint8_t(9 + k);
+                        detail[c].resize(detail[c].size() + 16, 0);
+                        for (uint32_t s = g * 32; s < hi; ++s)
+                            detail[c][k * 16 + ((s & 31u) >> 1)] |= uint8_t(code_of(base + s) << ((s & 1u) * 4u));
+                    }
+                }
+                groups[d->group_off[c] + g] = v;
+            }
+        }
+        for (uint32_t c = 0; c < d->n_classes; ++c) {
+            off = (off + 3) & ~size_t(3);
+            d->detail_off[c] = uint32_t(off);
+            off += detail[c].size();
+        }
+        const size_t total = (off + 15) & ~size_t(15);
+        std::vector<uint8_t> img(total, 0);
+        std::memcpy(img.data() + hotlen, groups.data() + hotlen, groups.size() - hotlen);
+        for (uint32_t c = 0; c < d->n_classes; ++c) {
+            if (!detail[c].empty()) std::memcpy(img.data() + d->detail_off[c], detail[c].data(), detail[c].size());
+            const uint32_t rows = d->class_size[c];
+            for (uint32_t s = 0; s < std::min(rows, hot); ++s) {
+                const uint32_t* row = d->h_rows.data() + size_t(d->class_base[c] + s) * dint::kEntry;
+                std::memcpy(img.data() + hot0 + (size_t(c) * hot + s) * 16, row, 16);
+                std::memcpy(img.data() + hot1 + (size_t(c) * hot + s) * 16, row + 4, 16);
+                img[hotlen + size_t(c) * hot + s] = uint8_t(code_of(d->class_base[c] + s));
+            }
+        }
+        d->strip_tables_bytes = uint32_t(total);
+        CUDA_TRY(cudaMalloc(&d->d_strip_tables, total));
+        CUDA_TRY(cudaMemcpy(d->d_strip_tables, img.data(), total, cudaMemcpyHostToDevice));
+    }
     return DINT_OK;
 }
 
 void dint_dict_release_device(dint_dict* d) {
-    if (d->d_rows || d->d_lens || d->d_lens_cls) {
+    if (d->d_rows || d->d_lens || d->d_lens_cls || d->d_strip_tables) {
         device_guard g(d->device);
         cudaFree(d->d_rows);
         cudaFree(d->d_lens);
         cudaFree(d->d_lens_cls);
+        cudaFree(d->d_strip_tables);
+        d->d_strip_tables = nullptr;
         d->d_rows = nullptr;
         d->d_lens = nullptr;
         d->d_lens_cls = nullptr;
@@ -682,7 +758,7 @@ int dint_decode_strips(const dint_dict* d, const uint8_t* d_in, size_t in_bytes,
     P.inbuf_bytes = strip_inbuf_bytes(lim.unit_bytes);
     // one persistent CTA per SM: as many warps as the shared-memory budget holds next to the length table
     // (the rest of the 256 KB stays L1 for the dictionary rows)
-    const size_t fixed = size_t(P.dv.lut_rows) / 2 * P.dv.n_classes + 8 * sizeof(strip_class);
+    const size_t fixed = size_t(P.dv.strip_tables_bytes) + kStripClassBytes;
     const size_t per_warp = strip_warp_smem(lim.unit_ints, lim.unit_bytes);
     static const uint32_t budget_kb = [] {
         const char* v = std::getenv("DINT_B200_STRIP_SMEM_KB");

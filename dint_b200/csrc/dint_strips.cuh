@@ -36,11 +36,14 @@ constexpr uint32_t kImagePad = 20;  // image words past unit_ints: output misali
 
 // per-class constants, staged in shared memory (32 bytes)
 struct strip_class {
+    uint32_t hot0_s;     // shared address of the class's slice of hot0 (hot1 lies hot1_delta bytes further)
+    uint32_t hotlen_s;   // shared address of the class's slice of hotlen
+    uint32_t group_s;    // shared address of the class's group-length slice
+    uint32_t rows;       // rows of the class (>= 1)
     uint32_t row_base;   // first dictionary row of the class
-    uint32_t rows;       // rows of the class
-    uint32_t lut_s;      // shared address of the class's length-table slice
     uint32_t lut_g_off;  // byte offset of the class's slice in dint_dict_view::lens_cls
-    uint32_t pad[4];
+    uint32_t detail_s;   // shared address of the class's mixed-group detail (16 bytes of nibbles per group)
+    uint32_t pad;
 };
 
 struct strip_params {
@@ -60,8 +63,9 @@ struct strip_params {
 __host__ __device__ inline uint32_t strip_image_words(uint32_t unit_ints) { return (unit_ints + kImagePad + 127u) & ~127u; }
 __host__ __device__ inline uint32_t strip_bits_words(uint32_t unit_ints) { return (strip_image_words(unit_ints) / 32u + 3u) & ~3u; }
 __host__ __device__ inline uint32_t strip_inbuf_bytes(uint32_t unit_bytes) { return (unit_bytes + 15u + 12u + 15u + 16u) & ~15u; }
+constexpr uint32_t kColdQueue = 64;  // entries of 8 bytes; drained when more than half full
 __host__ __device__ inline uint32_t strip_warp_smem(uint32_t unit_ints, uint32_t unit_bytes) {
-    return strip_image_words(unit_ints) * 4u + strip_bits_words(unit_ints) * 4u + strip_inbuf_bytes(unit_bytes);
+    return strip_image_words(unit_ints) * 4u + strip_bits_words(unit_ints) * 4u + kColdQueue * 8u + strip_inbuf_bytes(unit_bytes);
 }
 
 __device__ __forceinline__ unsigned lanemask_lt() {
@@ -74,7 +78,7 @@ __device__ __forceinline__ unsigned lanemask_lt() {
 // re-zeroes it. a = out_off & 3, so that image quads are aligned quads of the output array.
 template <int MODE>
 __device__ __forceinline__ void flush_image(uint32_t image_s, uint32_t bits_s, uint32_t* __restrict__ out, uint64_t out_off,
-                                            uint32_t n_ints, uint32_t doc_base, bool vec_ok, unsigned lane) {
+                                            uint32_t n_ints, uint32_t doc_base, bool unit_heads, bool vec_ok, unsigned lane) {
     const uint32_t a = uint32_t(out_off) & 3u;
     const uint32_t total = a + n_ints;
     uint32_t* gq = out + (out_off - a) + 4u * lane;
@@ -89,7 +93,7 @@ __device__ __forceinline__ void flush_image(uint32_t image_s, uint32_t bits_s, u
         const uint32_t hi = min(128u, total - g0);
         uint32_t f = 0;  // bit i: element i of my quad starts a list
         bool heads = false;
-        if (MODE == OUT_DOCIDS) {
+        if (MODE == OUT_DOCIDS && unit_heads) {
             f = (lds_u32(bits_s + ((q >> 5) << 2)) >> (q & 31u)) & 15u;
             heads = __any_sync(FULL, f != 0u);
         }
@@ -155,6 +159,36 @@ __device__ __forceinline__ void flush_image(uint32_t image_s, uint32_t bits_s, u
     }
 }
 
+__device__ __forceinline__ uint4 lds_v4(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+
+// header words of a strip unit (two uint4 + this lane's strip word), see dint_strip_unit
+struct unit_header {
+    uint4 h0, h1;
+    uint32_t word;
+    __device__ __forceinline__ void load(const dint_strip_unit* units, uint64_t u, unsigned lane) {
+        const uint4* hp = reinterpret_cast<const uint4*>(units + u);
+        h0 = __ldg(hp);
+        h1 = __ldg(hp + 1);
+        word = __ldg(reinterpret_cast<const uint32_t*>(hp + 2) + lane);
+    }
+    __device__ __forceinline__ uint64_t in_off() const { return (uint64_t(h0.y) << 32) | h0.x; }
+    __device__ __forceinline__ uint64_t out_off() const { return (uint64_t(h0.w) << 32) | h0.z; }
+    __device__ __forceinline__ uint32_t in_len() const { return h1.z & 0xFFFFu; }
+    __device__ __forceinline__ uint32_t n_ints() const { return h1.z >> 16; }
+    __device__ __forceinline__ uint32_t n_strips() const { return h1.w & 0xFFu; }
+    // a unit this build can hold (warp-uniform); anything else is skipped, its output left untouched
+    __device__ __forceinline__ bool ok(const strip_params& P) const {
+        return !(n_ints() > P.unit_ints || in_len() > P.unit_bytes || n_strips() > 32u || in_off() + in_len() > P.in_bytes ||
+                 n_ints() == 0u);
+    }
+};
+
+constexpr uint32_t kStripClassBytes = 8u * uint32_t(sizeof(strip_class));
+
 template <int MODE>
 __global__ void __launch_bounds__(768, 1) decode_strips_kernel(const strip_params P) {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -162,131 +196,223 @@ __global__ void __launch_bounds__(768, 1) decode_strips_kernel(const strip_param
     const uint32_t warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
     const dint_dict_view& dv = P.dv;
 
-    // ---- CTA setup: length-table slices + class table -------------------------------------------
-    const uint32_t slice_bytes = dv.lut_rows / 2u;  // multiple of 16
-    {
-        const uint32_t per = slice_bytes / 16u;
-        for (uint32_t i = threadIdx.x; i < per * dv.n_classes; i += blockDim.x) {
-            const uint32_t c = i / per, k = i - c * per;
-            reinterpret_cast<uint4*>(smem)[i] = __ldg(reinterpret_cast<const uint4*>(dv.lens_cls + dv.lens_cls_off[c]) + k);
-        }
-    }
-    const uint32_t lut_total = slice_bytes * dv.n_classes;
-    strip_class* classes = reinterpret_cast<strip_class*>(smem + lut_total);
+    // ---- CTA setup: dictionary image (hot rows, lengths) + class table ---------------------------
+    for (uint32_t i = threadIdx.x; i < dv.strip_tables_bytes / 16u; i += blockDim.x)
+        reinterpret_cast<uint4*>(smem)[i] = __ldg(reinterpret_cast<const uint4*>(dv.strip_tables) + i);
+    const uint32_t hot_rows = dv.hot_rows;
+    const uint32_t hot1_delta = dv.n_classes * hot_rows * 16u;
+    strip_class* classes = reinterpret_cast<strip_class*>(smem + dv.strip_tables_bytes);
     if (threadIdx.x < 8) {
-        const uint32_t c = threadIdx.x;
-        strip_class ci = {0, 1, smem_u32(smem), 0, {0, 0, 0, 0}};
-        if (c < dv.n_classes) {
-            ci.row_base = dv.class_base[c];
-            ci.rows = max(dv.class_rows[c], 1u);
-            ci.lut_s = smem_u32(smem) + c * slice_bytes;
-            ci.lut_g_off = dv.lens_cls_off[c];
-        }
-        classes[c] = ci;
+        const uint32_t c = min(threadIdx.x, dv.n_classes - 1u);
+        strip_class ci;
+        ci.hot0_s = smem_u32(smem) + c * hot_rows * 16u;
+        ci.hotlen_s = smem_u32(smem) + 2u * hot1_delta + c * hot_rows;
+        ci.group_s = smem_u32(smem) + dv.group_off[c];
+        ci.rows = max(dv.class_rows[c], 1u);
+        ci.row_base = dv.class_base[c];
+        ci.lut_g_off = dv.lens_cls_off[c];
+        ci.detail_s = smem_u32(smem) + dv.detail_off[c];
+        ci.pad = 0;
+        classes[threadIdx.x] = ci;
     }
     const uint32_t classes_s = smem_u32(classes);
-    uint8_t* mine = smem + lut_total + 8 * sizeof(strip_class) + size_t(warp) * (P.image_words * 4u + P.bits_words * 4u + P.inbuf_bytes);
+    uint8_t* mine = smem + dv.strip_tables_bytes + kStripClassBytes +
+                    size_t(warp) * (P.image_words * 4u + P.bits_words * 4u + kColdQueue * 8u + P.inbuf_bytes);
     const uint32_t image_s = smem_u32(mine);
     const uint32_t bits_s = image_s + P.image_words * 4u;
-    const uint32_t inbuf_s = bits_s + P.bits_words * 4u;
+    const uint32_t queue_s = bits_s + P.bits_words * 4u;
+    const uint32_t inbuf_s = queue_s + kColdQueue * 8u;
     for (uint32_t i = lane; i < (P.image_words + P.bits_words) / 4u; i += 32) reinterpret_cast<uint4*>(mine)[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
 
     const uint64_t in_base = reinterpret_cast<uint64_t>(P.in);
     const uint64_t in_lo = in_base & ~uint64_t(15), in_hi = (in_base + P.in_bytes + 15) & ~uint64_t(15);
     const bool vec_ok = (reinterpret_cast<uint64_t>(P.out) & 15) == 0;
-    const uint32_t lut_rows = dv.lut_rows;
 
-    for (uint64_t u = uint64_t(blockIdx.x) * n_warps + warp; u < P.n_units; u += uint64_t(gridDim.x) * n_warps) {
-        // ---- unit header (uniform loads) + my strip --------------------------------------------------
-        const uint4* hp = reinterpret_cast<const uint4*>(P.units + u);
-        const uint4 h0 = __ldg(hp), h1 = __ldg(hp + 1);
-        const uint32_t word = __ldg(reinterpret_cast<const uint32_t*>(hp + 2) + lane);
-        const uint64_t in_off = (uint64_t(h0.y) << 32) | h0.x, out_off = (uint64_t(h0.w) << 32) | h0.z;
-        const uint32_t doc_base = h1.x, starts = h1.y, in_len = h1.z & 0xFFFFu, n_ints = h1.z >> 16, n_strips = h1.w & 0xFFu;
-        if (n_ints > P.unit_ints || in_len > P.unit_bytes || n_strips > 32u || in_off + in_len > P.in_bytes || n_ints == 0u)
-            continue;  // not a unit this build can hold (warp-uniform)
-
-        // ---- stage the unit's bytes ----------------------------------------------------------------------
+    // copies the bytes of a unit into this warp's input buffer (16-byte cp.async; the caller waits)
+    auto stage = [&](uint64_t in_off, uint32_t in_len) {
         const uint64_t g = in_base + in_off, g0 = g & ~uint64_t(15);
-        const uint32_t skew = uint32_t(g) & 15u;
-        const uint32_t n_chunks = (skew + in_len + 12u + 15u) >> 4;  // a thread reads up to 12 bytes past its symbol
+        const uint32_t n_chunks = ((uint32_t(g) & 15u) + in_len + 12u + 15u) >> 4;  // a thread reads up to 12 bytes past its symbol
         for (uint32_t i = lane; i < n_chunks; i += 32) {
             const uint64_t ga = g0 + 16ull * i;
             const uint32_t sa = inbuf_s + 16u * i;
             if (ga >= in_lo && ga < in_hi) cp_async16(sa, ga);
             else asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(sa), "r"(0u) : "memory");
         }
+    };
 
-        // ---- my strip ----------------------------------------------------------------------------------------
-        const bool has = lane < n_strips;
-        const uint32_t in_rel = min(word & 0x1FFFu, in_len), out_rel = min((word >> 13) & 0xFFFu, n_ints), sel = (word >> 25) & 15u;
-        uint32_t nxt = __shfl_down_sync(FULL, out_rel, 1);
-        if (lane + 1u >= n_strips) nxt = n_ints;
-        const uint32_t n = (has && nxt > out_rel) ? nxt - out_rel : 0u;
-        const uint32_t a = uint32_t(out_off) & 3u;
-        uint32_t o = image_s + ((a + out_rel) << 2);
-        const uint32_t o_end = o + (n << 2);
-        uint32_t p = inbuf_s + skew + in_rel;
-        const bool narrow = sel >= dint::kSelectors;
-        const uint32_t cls = min(narrow ? sel - dint::kSelectors : sel, dv.n_classes - 1u);
-        uint32_t c_row_base, c_rows, c_lut_s, c_lut_g;
-        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-                     : "=r"(c_row_base), "=r"(c_rows), "=r"(c_lut_s), "=r"(c_lut_g)
-                     : "r"(classes_s + cls * uint32_t(sizeof(strip_class))));
-        const uint32_t symbits = narrow ? 8u : 16u, symmask = narrow ? 0xFFu : 0xFFFFu, symbytes = narrow ? 1u : 2u;
-        const uint32_t last_row = (narrow ? min(c_rows, 256u) : c_rows) - 1u;
-        const uint32_t* rowp = dv.rows + size_t(c_row_base) * dint::kEntry;
-        const uint8_t* lutg = dv.lens_cls + c_lut_g;
+    const uint64_t stride = uint64_t(gridDim.x) * n_warps;
+    uint64_t u = uint64_t(blockIdx.x) * n_warps + warp;
+    unit_header H;
+    H.h0 = H.h1 = make_uint4(0, 0, 0, 0);
+    H.word = 0;
+    if (u < P.n_units) {
+        H.load(P.units, u, lane);
+        if (H.ok(P)) stage(H.in_off(), H.in_len());
+    }
+    while (u < P.n_units) {
+        // ---- the next unit's header is fetched while this one is decoded ---------------------------------
+        const uint64_t un = u + stride;
+        const bool more = un < P.n_units;
+        unit_header N = H;
+        if (more) N.load(P.units, un, lane);
+
+        const bool valid = H.ok(P);
+        const uint64_t out_off = H.out_off();
+        const uint32_t n_ints = H.n_ints();
+        const uint32_t doc_base = H.h1.x, starts = H.h1.y;
         uint32_t start_word_s = 0;
-        if (MODE == OUT_DOCIDS && has && lane && ((starts >> lane) & 1u)) {
-            const uint32_t pos = a + out_rel;
-            start_word_s = bits_s + ((pos >> 5) << 2);
-            asm volatile("atom.shared.or.b32 _, [%0], %1;" ::"r"(start_word_s), "r"(1u << (pos & 31u)) : "memory");
-        }
-        cp_async_wait_all();
-        __syncwarp();
+        if (valid) {
+            // ---- my strip ------------------------------------------------------------------------------------
+            const uint32_t in_len = H.in_len(), n_strips = H.n_strips();
+            const uint32_t skew = uint32_t(in_base + H.in_off()) & 15u;
+            const bool has = lane < n_strips;
+            const uint32_t word = H.word;
+            const uint32_t in_rel = min(word & 0x1FFFu, in_len), out_rel = min((word >> 13) & 0xFFFu, n_ints), sel = (word >> 25) & 15u;
+            uint32_t nxt = __shfl_down_sync(FULL, out_rel, 1);
+            if (lane + 1u >= n_strips) nxt = n_ints;
+            const uint32_t n = (has && nxt > out_rel) ? nxt - out_rel : 0u;
+            const uint32_t a = uint32_t(out_off) & 3u;
+            uint32_t o = image_s + ((a + out_rel) << 2);
+            const uint32_t o_end = o + (n << 2);
+            uint32_t p = inbuf_s + skew + in_rel;
+            const uint32_t p_lim = inbuf_s + skew + in_len;
+            const bool narrow = sel >= dint::kSelectors;
+            const uint32_t cls = min(narrow ? sel - dint::kSelectors : sel, 7u);
+            uint32_t hot0_s, hotlen_s, group_s, c_rows;
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(hot0_s), "=r"(hotlen_s), "=r"(group_s), "=r"(c_rows)
+                         : "r"(classes_s + cls * uint32_t(sizeof(strip_class))));
+            const uint32_t c_row_base = lds_u32(classes_s + cls * uint32_t(sizeof(strip_class)) + 16u);
+            const uint32_t c_lut_g = lds_u32(classes_s + cls * uint32_t(sizeof(strip_class)) + 20u);
+            const uint32_t detail_s = lds_u32(classes_s + cls * uint32_t(sizeof(strip_class)) + 24u);
+            const uint32_t symbits = narrow ? 8u : 16u, symmask = narrow ? 0xFFu : 0xFFFFu, symbytes = narrow ? 1u : 2u;
+            const uint32_t last_row = (narrow ? min(c_rows, 256u) : c_rows) - 1u;
+            const uint8_t* lutg = dv.lens_cls + c_lut_g;
+            if (MODE == OUT_DOCIDS && has && lane && ((starts >> lane) & 1u)) {
+                const uint32_t pos = a + out_rel;
+                start_word_s = bits_s + ((pos >> 5) << 2);
+                asm volatile("atom.shared.or.b32 _, [%0], %1;" ::"r"(start_word_s), "r"(1u << (pos & 31u)) : "memory");
+            }
+            cp_async_wait_all();
+            __syncwarp();
 
-        // ---- the reference's scalar loop, one strip per thread ------------------------------------------------
-        bool act = o < o_end;
-        while (__any_sync(FULL, act)) {
-            const uint32_t a4 = p & ~3u, sh = (p & 3u) << 3;
-            const uint32_t w0 = lds_u32(a4), w1 = lds_u32(a4 + 4);
-            const uint32_t lo = __funnelshift_r(w0, w1, sh);
-            const uint32_t sym = lo & symmask;
-            uint32_t pay = lo >> symbits;  // what follows the codeword
-            const bool exc = sym < 2u;     // 0: u16 value follows, 1: u32 value follows
-            if (sym == 1u) pay |= __funnelshift_r(w1, lds_u32(a4 + 8), sh) << (32u - symbits);
-            else pay &= 0xFFFFu;
-            const uint32_t symc = min(sym, last_row);
-            uint32_t lb;
-            if (symc < lut_rows) lb = lds_u8(c_lut_s + (symc >> 1));
-            else lb = __ldg(lutg + (symc >> 1));
-            const uint32_t nib = (lb >> ((symc & 1u) << 2)) & 15u;  // rows 0 and 1 hold length 1, rows 2..6 the run lengths
-            const uint4* rp = reinterpret_cast<const uint4*>(rowp + size_t(symc) * dint::kEntry);
-            const bool dic = act && sym >= dint::kReserved;
-            uint4 r = make_uint4(0, 0, 0, 0);
-            if (dic) r = __ldg(rp);
-            if (exc) r.x = pay;
-            const uint32_t L = dic ? (1u << nib) : 0u;  // dictionary words to copy (runs copy nothing: the image is zeroed)
-            if (act && (exc || dic)) sts_u32(o, r.x);
-            sts_tail3(o, L, r.y, r.z, r.w);
-            if (L > 4u) {
-                for (uint32_t k = 1; k < (L >> 2); ++k) sts_4(o + 16u * k, __ldg(rp + k));
+            // ---- the reference's scalar loop, one strip per thread ------------------------------------------------
+            // Lanes whose strip is finished keep stepping through whatever follows (no stores, addresses
+            // clamped), so the cursor updates need no guard.
+            // Entries beyond the hot rows (u16 codewords only) come from the L2-resident dictionary. Their
+            // length is known at once (group table), so the cursors move on; the copy itself is queued
+            // {image address | log2(length) << 24, dictionary row} and done for up to 64 codewords at a
+            // time, so that one round trip to L2 serves all of them.
+            uint32_t qn = 0;
+            auto drain = [&]() {
+                __syncwarp();
+                const uint32_t k0 = lane, k1 = lane + 32u;
+                uint32_t e0x = 0, e0y = 0, e1x = 0, e1y = 0;
+                if (k0 < qn) asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(e0x), "=r"(e0y) : "r"(queue_s + 8u * k0));
+                if (k1 < qn) asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(e1x), "=r"(e1y) : "r"(queue_s + 8u * k1));
+                const uint4* rp0 = reinterpret_cast<const uint4*>(dv.rows + size_t(e0y) * dint::kEntry);
+                const uint4* rp1 = reinterpret_cast<const uint4*>(dv.rows + size_t(e1y) * dint::kEntry);
+                uint4 r0 = make_uint4(0, 0, 0, 0), r1 = make_uint4(0, 0, 0, 0);
+                if (k0 < qn) r0 = __ldg(rp0);
+                if (k1 < qn) r1 = __ldg(rp1);
+                if (k0 < qn) {
+                    const uint32_t oo = e0x & 0xFFFFFFu, cc = e0x >> 24;
+                    sts_u32(oo, r0.x);
+                    sts_tail3_log2(oo, cc, r0.y, r0.z, r0.w);
+                    if (cc > 2u) {
+                        sts_4(oo + 16u, __ldg(rp0 + 1));
+                        if (cc > 3u) {
+                            sts_4(oo + 32u, __ldg(rp0 + 2));
+                            sts_4(oo + 48u, __ldg(rp0 + 3));
+                        }
+                    }
+                }
+                if (k1 < qn) {
+                    const uint32_t oo = e1x & 0xFFFFFFu, cc = e1x >> 24;
+                    sts_u32(oo, r1.x);
+                    sts_tail3_log2(oo, cc, r1.y, r1.z, r1.w);
+                    if (cc > 2u) {
+                        sts_4(oo + 16u, __ldg(rp1 + 1));
+                        if (cc > 3u) {
+                            sts_4(oo + 32u, __ldg(rp1 + 2));
+                            sts_4(oo + 48u, __ldg(rp1 + 3));
+                        }
+                    }
+                }
+                qn = 0;
+                __syncwarp();
+            };
+
+            bool act = o < o_end;
+            while (__any_sync(FULL, act)) {
+                const uint32_t a4 = p & ~3u, sh = p << 3;  // the funnel shift takes its count mod 32
+                const uint32_t w0 = lds_u32(a4), w1 = lds_u32(a4 + 4);
+                const uint32_t lo = __funnelshift_r(w0, w1, sh);
+                const uint32_t sym = lo & symmask;
+                uint32_t w2 = w1;
+                if (sym == 1u) w2 = lds_u32(a4 + 8);
+                // what follows the codeword: 32 bits after a 1, 16 bits after a 0
+                uint32_t pay = __funnelshift_r(lo, __funnelshift_r(w1, w2, sh), symbits);
+                if (sym != 1u) pay &= 0xFFFFu;
+                uint32_t code = 0;  // log2(entry length); rows 0 and 1 hold length 1, rows 2..6 the run lengths
+                uint4 r = make_uint4(0, 0, 0, 0);
+                const bool hot = sym < hot_rows;
+                const bool dic = act && sym >= dint::kReserved;
+                const bool cold = dic && !hot;
+                if (hot) {
+                    code = lds_u8(hotlen_s + sym);
+                    if (dic) r = lds_v4(hot0_s + (sym << 4));
+                }
+                const uint32_t cold_mask = __ballot_sync(FULL, cold);
+                if (cold_mask) {
+                    if (cold) {
+                        const uint32_t symc = min(sym, last_row);
+                        code = lds_u8(group_s + (symc >> 5));
+                        if (code > 8u) {  // the 32 rows of the group differ in length
+                            if (code != 0xFFu) code = lds_u8(detail_s + ((code - 9u) << 4) + ((symc & 31u) >> 1));
+                            else code = __ldg(lutg + (symc >> 1));
+                            code = (code >> ((symc & 1u) << 2)) & 15u;
+                        }
+                        const uint32_t slot = queue_s + 8u * (qn + __popc(cold_mask & lanemask_lt()));
+                        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(slot), "r"(o | (code << 24)), "r"(c_row_base + symc) : "memory");
+                    }
+                    qn += __popc(cold_mask);
+                }
+                const uint32_t words = (dic && hot) ? code : 0u;  // log2(words to copy now); runs copy nothing: the image is zeroed
+                if (sym < 2u) r.x = pay;
+                if (act && (sym < 2u || (dic && hot))) sts_u32(o, r.x);
+                sts_tail3_log2(o, words, r.y, r.z, r.w);
+                if (words > 2u) {
+                    sts_4(o + 16u, lds_v4(hot0_s + hot1_delta + (sym << 4)));
+                    if (words > 3u) {
+                        const uint4* rp = reinterpret_cast<const uint4*>(dv.rows + size_t(c_row_base + sym) * dint::kEntry);
+                        sts_4(o + 32u, __ldg(rp + 2));
+                        sts_4(o + 48u, __ldg(rp + 3));
+                    }
+                }
+                o += 4u << code;
+                p = min(p + symbytes + (sym < 2u ? 2u + 2u * sym : 0u), p_lim);
+                act = o < o_end;
+                if (qn > kColdQueue - 32u) drain();
             }
-            if (act) {
-                o += 4u << nib;
-                p += symbytes + (exc ? (sym ? 4u : 2u) : 0u);
-            }
-            act = o < o_end;
+            if (qn) drain();
+            __syncwarp();
         }
-        __syncwarp();
+
+        // ---- the next unit's bytes travel while this one is written ---------------------------------------
+        if (more && N.ok(P)) stage(N.in_off(), N.in_len());
 
         // ---- write the unit ------------------------------------------------------------------------------------
-        flush_image<MODE>(image_s, bits_s, P.out, out_off, n_ints, doc_base, vec_ok, lane);
-        if (MODE == OUT_DOCIDS && start_word_s) sts_u32(start_word_s, 0u);
-        __syncwarp();
+        if (valid) {
+            flush_image<MODE>(image_s, bits_s, P.out, out_off, n_ints, doc_base, (starts & ~1u) != 0u, vec_ok, lane);
+            if (MODE == OUT_DOCIDS && start_word_s) sts_u32(start_word_s, 0u);
+            __syncwarp();
+        }
+        u = un;
+        H = N;
     }
+    cp_async_wait_all();
 }
 
 }  // namespace dintk
