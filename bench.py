@@ -254,7 +254,9 @@ class ReplicatedStream:
         self.capi = capi
         self.engine = engine
         self.dict = capi.Dictionary(KINDS[type_], dict_bytes, device=dev.index)
+        t0 = time.perf_counter()
         self.plan = capi.VroomPlan(self.dict, bin_bytes, block_size=block_size)
+        self.plan_s = time.perf_counter() - t0
         self.R = replicas
         self.in_bytes = len(bin_bytes)
         self.n_ints = int(self.plan.n_ints)
@@ -429,6 +431,13 @@ def run_gpu(args):
                      "bytes_per_int": {"docs": sd.algo_bytes / (R * sd.n_ints), "freqs": sf.algo_bytes / (R * sf.n_ints)}},
         "clocks": clocks, "gpu_launches": int(launches),
         "checksum": int(red[1].item()),
+        # one-time host pre-pass per .bin (dint_vroom_plan_create: header walk + strip table), NOT in any timed region;
+        # a vroom file has no list index, so one sequential walk is inherent (vroom_env/decode.cpp:139-150 is that walk)
+        "prepass": {"what": "dint_vroom_plan_create, docs + freqs sample files, 1 host thread",
+                    "ms": (sd.plan_s + sf.plan_s) * 1e3,
+                    "G_ints_per_s": (sd.n_ints + sf.n_ints) / (sd.plan_s + sf.plan_s) / 1e9,
+                    "strip_table_bytes_per_int": 160.0 * (sd.n_strip_units + sf.n_strip_units) / (sd.n_ints + sf.n_ints),
+                    "codewords": {"docs": sd.plan.codeword_stats, "freqs": sf.plan.codeword_stats}},
     }
     if e2e is not None:
         line["e2e"] = e2e

@@ -29,7 +29,7 @@ assert SEGMENT_DTYPE.itemsize == 32 and BLOCK_DTYPE.itemsize == 32 and STRIP_UNI
 # every symbol include/dint_b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
     "dint_last_error", "dint_abi_version", "dint_kernel_launches", "dint_strip_limits",
-    "dint_vroom_plan_num_strip_units", "dint_vroom_plan_strip_units", "dint_decode_strips",
+    "dint_vroom_plan_num_strip_units", "dint_vroom_plan_codeword_stats", "dint_vroom_plan_strip_units", "dint_decode_strips",
     "dint_dict_create", "dint_dict_create_mapped", "dint_dict_destroy", "dint_dict_kind", "dint_dict_num_rows",
     "dint_dict_device_bytes", "dint_dict_copy",
     "dint_vroom_plan_create", "dint_vroom_plan_destroy", "dint_vroom_plan_num_lists", "dint_vroom_plan_num_ints",
@@ -75,6 +75,8 @@ def lib():
         L.dint_vroom_plan_create.argtypes = [vp, vp, sz, u32, u32, C.POINTER(vp)]
         L.dint_vroom_plan_destroy.argtypes = [vp]
         L.dint_vroom_plan_destroy.restype = None
+        L.dint_vroom_plan_codeword_stats.argtypes = [vp, C.POINTER(u64 * 16)]
+        L.dint_vroom_plan_codeword_stats.restype = None
         L.dint_strip_limits.argtypes = [C.POINTER(u32)] * 3
         L.dint_strip_limits.restype = None
         L.dint_decode_strips.argtypes = [vp, vp, sz, vp, sz, vp, i32, vp]
@@ -195,6 +197,10 @@ class VroomPlan:
         self.strip_units = _view(L.dint_vroom_plan_strip_units(h), self.n_strip_units, STRIP_UNIT_DTYPE)
         self.list_offsets = _view(L.dint_vroom_plan_list_offsets(h), self.n_lists + 1, np.uint64)
         self.list_byte_offsets = _view(L.dint_vroom_plan_list_byte_offsets(h), self.n_lists + 1, np.uint64)
+        st = (C.c_uint64 * 16)()
+        L.dint_vroom_plan_codeword_stats(h, C.byref(st))
+        self.codeword_stats = dict(zip(("exc16", "exc32", "runs", "len1", "len2", "len4", "len8", "len16", "u8_codewords",
+                                        "u16_codewords", "run_ints", "unit_trips", "strips"), (int(x) for x in st)))
         self.block_size = block_size
         self.in_bytes = len(a)
         self.handle = h

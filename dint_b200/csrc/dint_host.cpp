@@ -35,9 +35,9 @@ static uint32_t env_u32(const char* name, uint32_t dflt, uint32_t lo, uint32_t h
 const strip_limits& get_strip_limits() {
     static const strip_limits lim = [] {
         strip_limits l;
-        l.unit_ints = env_u32("DINT_B200_UNIT_INTS", 2048, 1024, DINT_UNIT_MAX_INTS) & ~3u;
-        l.unit_bytes = env_u32("DINT_B200_UNIT_BYTES", 3584, 512, DINT_UNIT_MAX_BYTES - 15);
-        l.strip_codewords = env_u32("DINT_B200_STRIP_CODEWORDS", 16, 1, 64);
+        l.unit_ints = env_u32("DINT_B200_UNIT_INTS", 1024, 512, DINT_UNIT_MAX_INTS) & ~3u;
+        l.unit_bytes = env_u32("DINT_B200_UNIT_BYTES", 1792, 512, DINT_UNIT_MAX_BYTES - 15);
+        l.strip_codewords = env_u32("DINT_B200_STRIP_CODEWORDS", 8, 1, 64);
         l.strip_ints = std::min(512u, l.unit_ints - 256u);
         return l;
     }();
@@ -346,6 +346,11 @@ struct strip_builder {
     uint64_t s_out = 0;
     uint32_t s_cw = 0, s_base = 0, s_sel = 0;
     bool s_list_start = false;
+    // codeword statistics (dint_vroom_plan_codeword_stats)
+    uint64_t* hist = nullptr;
+    const uint8_t* c_ptr = nullptr;
+    uint64_t c_out = 0;
+    uint32_t u_max_cw = 0;
 
     strip_builder(const uint8_t* b, std::vector<dint_strip_unit>& u) : lim(dint::get_strip_limits()), bin(b), units(u) {
         std::memset(&cur, 0, sizeof cur);
@@ -358,9 +363,23 @@ struct strip_builder {
         s_base = acc;
         s_sel = sel;
         s_list_start = list_start;
+        c_ptr = p;
+        c_out = out_idx;
     }
     // one codeword was walked: the stream is now at q, out_idx integers are out, acc = sum(v + 1) of the list so far
     void codeword(const uint8_t* q, uint64_t out_idx, uint32_t acc, bool stream_end) {
+        if (hist) {
+            const bool narrow = s_sel >= kSelectors;
+            const uint32_t sym = narrow ? uint32_t(*c_ptr) : uint32_t(c_ptr[0]) | (uint32_t(c_ptr[1]) << 8);
+            const uint64_t len = out_idx - c_out;
+            uint32_t k = sym == 0 ? 0u : sym == 1 ? 1u : sym < kReserved ? 2u : 3u;
+            if (k == 3u) for (uint64_t l = len; l > 1; l >>= 1) ++k;  // 3..7: entries of 1, 2, 4, 8, 16 integers
+            ++hist[k];
+            ++hist[narrow ? 8 : 9];
+            if (k == 2u) hist[10] += len;  // integers produced by run codewords
+        }
+        c_ptr = q;
+        c_out = out_idx;
         ++s_cw;
         if (stream_end || s_cw >= lim.strip_codewords || out_idx - s_out >= lim.strip_ints) {
             emit(q, out_idx);
@@ -369,6 +388,11 @@ struct strip_builder {
     }
     void close_unit() {
         if (!open) return;
+        if (hist) {
+            hist[11] += u_max_cw;  // trips of the lane-sequential loop = longest strip of the unit
+            hist[12] += cur.n_strips;
+        }
+        u_max_cw = 0;
         for (uint32_t k = cur.n_strips; k < DINT_UNIT_STRIPS; ++k) cur.strip[k] = uint32_t(cur.n_ints) << 13;
         units.push_back(cur);
         open = false;
@@ -386,6 +410,7 @@ struct strip_builder {
             cur.doc_base = s_base;
             open = true;
         }
+        u_max_cw = std::max(u_max_cw, s_cw);
         const uint32_t k = cur.n_strips;
         cur.strip[k] = uint32_t(in0 - cur.in_off) | (uint32_t(cur.n_ints) << 13) | (s_sel << 25);
         if (k && s_list_start) cur.list_starts |= 1u << k;
@@ -411,6 +436,7 @@ int dint_vroom_plan_create(const dint_dict* d, const void* bin_, size_t len, uin
     if (!plan) return DINT_E_NOMEM;
     walker wk{d, bin, end};
     strip_builder sb(bin, plan->strip_units);
+    sb.hist = plan->cw_stats;
     const uint8_t* p = bin;
     uint64_t out_off = 0;
     plan->list_offsets.push_back(0);
@@ -508,6 +534,9 @@ uint64_t dint_vroom_plan_num_lists(const dint_vroom_plan* p) { return p ? p->lis
 uint64_t dint_vroom_plan_num_ints(const dint_vroom_plan* p) { return p ? p->n_ints : 0; }
 uint64_t dint_vroom_plan_num_segments(const dint_vroom_plan* p) { return p ? p->segments.size() : 0; }
 const dint_segment* dint_vroom_plan_segments(const dint_vroom_plan* p) { return p ? p->segments.data() : nullptr; }
+void dint_vroom_plan_codeword_stats(const dint_vroom_plan* p, uint64_t out[16]) {
+    for (int i = 0; i < 16; ++i) out[i] = p ? p->cw_stats[i] : 0;
+}
 uint64_t dint_vroom_plan_num_strip_units(const dint_vroom_plan* p) { return p ? p->strip_units.size() : 0; }
 const dint_strip_unit* dint_vroom_plan_strip_units(const dint_vroom_plan* p) {
     return p ? p->strip_units.data() : nullptr;

@@ -113,6 +113,7 @@ struct dint_vroom_plan {
     std::vector<dint_segment> segments;
     std::vector<uint32_t> unit_first;         // n_units + 1
     std::vector<dint_strip_unit> strip_units; // lane-sequential decoder's work table
+    uint64_t cw_stats[16] = {0};              // see dint_vroom_plan_codeword_stats
     std::vector<uint64_t> list_offsets;       // n_lists + 1
     std::vector<uint64_t> list_byte_offsets;  // n_lists + 1
 };

@@ -762,14 +762,18 @@ int dint_decode_strips(const dint_dict* d, const uint8_t* d_in, size_t in_bytes,
     const size_t per_warp = strip_warp_smem(lim.unit_ints, lim.unit_bytes);
     static const uint32_t budget_kb = [] {
         const char* v = std::getenv("DINT_B200_STRIP_SMEM_KB");
-        return v && *v ? uint32_t(std::strtoul(v, nullptr, 10)) : 200u;
+        return v && *v ? uint32_t(std::strtoul(v, nullptr, 10)) : 224u;
     }();
     const size_t budget = std::min(size_t(budget_kb) * 1024, size_t(di.max_smem_optin));
     if (fixed + per_warp > budget) {
         dint::set_error("strip decoder: shared-memory budget too small for one warp");
         return DINT_E_ARG;
     }
-    int warps = int(std::min<size_t>((budget - fixed) / per_warp, 24));
+    static const uint32_t max_warps = [] {
+        const char* v = std::getenv("DINT_B200_STRIP_WARPS");
+        return v && *v ? std::min(32u, std::max(1u, uint32_t(std::strtoul(v, nullptr, 10)))) : 24u;
+    }();
+    int warps = int(std::min<size_t>((budget - fixed) / per_warp, max_warps));
     const size_t smem = fixed + size_t(warps) * per_warp;
     const int grid = int(std::max<uint64_t>(1, std::min<uint64_t>((n_units + warps - 1) / warps, uint64_t(di.sms))));
 #define LAUNCH_STRIPS(M)                                                                                   \

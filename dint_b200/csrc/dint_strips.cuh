@@ -63,7 +63,7 @@ struct strip_params {
 __host__ __device__ inline uint32_t strip_image_words(uint32_t unit_ints) { return (unit_ints + kImagePad + 127u) & ~127u; }
 __host__ __device__ inline uint32_t strip_bits_words(uint32_t unit_ints) { return (strip_image_words(unit_ints) / 32u + 3u) & ~3u; }
 __host__ __device__ inline uint32_t strip_inbuf_bytes(uint32_t unit_bytes) { return (unit_bytes + 15u + 12u + 15u + 16u) & ~15u; }
-constexpr uint32_t kColdQueue = 64;  // entries of 8 bytes; drained when more than half full
+constexpr uint32_t kColdQueue = 64;  // entries of 8 bytes; a trip of the decode loop adds at most 32
 __host__ __device__ inline uint32_t strip_warp_smem(uint32_t unit_ints, uint32_t unit_bytes) {
     return strip_image_words(unit_ints) * 4u + strip_bits_words(unit_ints) * 4u + kColdQueue * 8u + strip_inbuf_bytes(unit_bytes);
 }
@@ -82,7 +82,10 @@ __device__ __forceinline__ void flush_image(uint32_t image_s, uint32_t bits_s, u
     const uint32_t a = uint32_t(out_off) & 3u;
     const uint32_t total = a + n_ints;
     uint32_t* gq = out + (out_off - a) + 4u * lane;
-    uint32_t acc = doc_base - 1u;  // docid[i] = acc + sum_{j <= i} (v_j + 1)
+    // docid[i] = acc + sum_{j <= i} (v_j + 1). The a image words in front of the unit hold zeros and are
+    // scanned like values (each adds 1), so they are discounted here; words past the unit's end cannot
+    // change anything in front of them. Only groups that hold a list start need the segmented scan.
+    uint32_t acc = doc_base - 1u - a;
     for (uint32_t g0 = 0; g0 < total; g0 += 128u, gq += 128) {
         const uint32_t q = g0 + 4u * lane;
         const uint32_t sp = image_s + (q << 2);
@@ -91,14 +94,14 @@ __device__ __forceinline__ void flush_image(uint32_t image_s, uint32_t bits_s, u
         asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(sp), "r"(0u) : "memory");
         const uint32_t lo = g0 ? 0u : a;
         const uint32_t hi = min(128u, total - g0);
-        uint32_t f = 0;  // bit i: element i of my quad starts a list
-        bool heads = false;
-        if (MODE == OUT_DOCIDS && unit_heads) {
-            f = (lds_u32(bits_s + ((q >> 5) << 2)) >> (q & 31u)) & 15u;
-            heads = __any_sync(FULL, f != 0u);
-        }
-        if (lo == 0u && hi == 128u && !heads && vec_ok) {
-            if (MODE == OUT_DOCIDS) {
+        if (MODE == OUT_DOCIDS) {
+            uint32_t f = 0;  // bit i: element i of my quad starts a list
+            bool heads = false;
+            if (unit_heads) {
+                f = (lds_u32(bits_s + ((q >> 5) << 2)) >> (q & 31u)) & 15u;
+                heads = __any_sync(FULL, f != 0u);
+            }
+            if (!heads) {
                 v.x += 1u;
                 v.y += v.x + 1u;
                 v.z += v.y + 1u;
@@ -110,18 +113,10 @@ __device__ __forceinline__ void flush_image(uint32_t image_s, uint32_t bits_s, u
                 v.y += base;
                 v.z += base;
                 v.w += base;
-            } else if (MODE == OUT_FREQS) {
-                v.x += 1u;
-                v.y += 1u;
-                v.z += 1u;
-                v.w += 1u;
-            }
-            st_stream4(gq, v);
-        } else {
-            const uint32_t e = 4u * lane;
-            const bool l0 = e >= lo && e < hi, l1 = e + 1 >= lo && e + 1 < hi, l2 = e + 2 >= lo && e + 2 < hi,
-                       l3 = e + 3 >= lo && e + 3 < hi;
-            if (MODE == OUT_DOCIDS) {
+            } else {
+                const uint32_t e = 4u * lane;
+                const bool l0 = e >= lo && e < hi, l1 = e + 1 >= lo && e + 1 < hi, l2 = e + 2 >= lo && e + 2 < hi,
+                           l3 = e + 3 >= lo && e + 3 < hi;
                 const uint32_t t0 = l0 ? v.x + 1u : 0u, t1 = l1 ? v.y + 1u : 0u, t2 = l2 ? v.z + 1u : 0u,
                                t3 = l3 ? v.w + 1u : 0u;
                 // lane-local sums restarting at list starts; r = plain lane total
@@ -135,24 +130,30 @@ __device__ __forceinline__ void flush_image(uint32_t image_s, uint32_t bits_s, u
                 const uint32_t prevH = __ballot_sync(FULL, f != 0u) & lanemask_lt();
                 const uint32_t hl = prevH ? 31u - uint32_t(__clz(prevH)) : 0u;
                 const uint32_t from_head = __shfl_sync(FULL, p3 - S, hl);
-                const uint32_t c = (prevH ? from_head - 1u : acc) + (S - r);
+                const uint32_t c = (prevH ? from_head - 1u : acc + lo) + (S - r);
                 v.x = (f & 1u) ? p0 - 1u : c + p0;
                 v.y = (f & 3u) ? p1 - 1u : c + p1;
                 v.z = (f & 7u) ? p2 - 1u : c + p2;
                 v.w = (f & 15u) ? p3 - 1u : c + p3;
                 acc = __shfl_sync(FULL, v.w, 31);
-            } else if (MODE == OUT_FREQS) {
-                v.x += 1u;
-                v.y += 1u;
-                v.z += 1u;
-                v.w += 1u;
             }
+        } else if (MODE == OUT_FREQS) {
+            v.x += 1u;
+            v.y += 1u;
+            v.z += 1u;
+            v.w += 1u;
+        }
+        if (lo == 0u && hi == 128u && vec_ok) {
+            st_stream4(gq, v);
+        } else {
+            const uint32_t e = 4u * lane;
+            const bool l0 = e >= lo && e < hi, l3 = e + 3 >= lo && e + 3 < hi;
             if (l0 && l3 && vec_ok) {
                 st_stream4(gq, v);
             } else {
                 if (l0) st_stream(gq, v.x);
-                if (l1) st_stream(gq + 1, v.y);
-                if (l2) st_stream(gq + 2, v.z);
+                if (e + 1 >= lo && e + 1 < hi) st_stream(gq + 1, v.y);
+                if (e + 2 >= lo && e + 2 < hi) st_stream(gq + 2, v.z);
                 if (l3) st_stream(gq + 3, v.w);
             }
         }
@@ -190,7 +191,7 @@ struct unit_header {
 constexpr uint32_t kStripClassBytes = 8u * uint32_t(sizeof(strip_class));
 
 template <int MODE>
-__global__ void __launch_bounds__(768, 1) decode_strips_kernel(const strip_params P) {
+__global__ void __launch_bounds__(1024, 1) decode_strips_kernel(const strip_params P) {
     extern __shared__ __align__(16) uint8_t smem[];
     const unsigned lane = lane_id();
     const uint32_t warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
@@ -226,17 +227,19 @@ __global__ void __launch_bounds__(768, 1) decode_strips_kernel(const strip_param
     __syncthreads();
 
     const uint64_t in_base = reinterpret_cast<uint64_t>(P.in);
-    const uint64_t in_lo = in_base & ~uint64_t(15), in_hi = (in_base + P.in_bytes + 15) & ~uint64_t(15);
+    const uint64_t in_hi = (in_base + P.in_bytes + 15) & ~uint64_t(15);
     const bool vec_ok = (reinterpret_cast<uint64_t>(P.out) & 15) == 0;
 
-    // copies the bytes of a unit into this warp's input buffer (16-byte cp.async; the caller waits)
+    // copies the bytes of a unit into this warp's input buffer (16-byte cp.async; the caller waits). Aligned
+    // 16-byte pieces that hold at least one byte of the file are read whole; the ones past its end are zeroed.
     auto stage = [&](uint64_t in_off, uint32_t in_len) {
         const uint64_t g = in_base + in_off, g0 = g & ~uint64_t(15);
         const uint32_t n_chunks = ((uint32_t(g) & 15u) + in_len + 12u + 15u) >> 4;  // a thread reads up to 12 bytes past its symbol
-        for (uint32_t i = lane; i < n_chunks; i += 32) {
-            const uint64_t ga = g0 + 16ull * i;
-            const uint32_t sa = inbuf_s + 16u * i;
-            if (ga >= in_lo && ga < in_hi) cp_async16(sa, ga);
+        const uint32_t n_file = uint32_t(min(uint64_t(n_chunks), (in_hi - g0) >> 4));
+        uint64_t ga = g0 + 16u * lane;
+        uint32_t sa = inbuf_s + 16u * lane;
+        for (uint32_t i = lane; i < n_chunks; i += 32, ga += 512, sa += 512) {
+            if (i < n_file) cp_async16(sa, ga);
             else asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(sa), "r"(0u) : "memory");
         }
     };
@@ -307,92 +310,93 @@ __global__ void __launch_bounds__(768, 1) decode_strips_kernel(const strip_param
             uint32_t qn = 0;
             auto drain = [&]() {
                 __syncwarp();
-                const uint32_t k0 = lane, k1 = lane + 32u;
-                uint32_t e0x = 0, e0y = 0, e1x = 0, e1y = 0;
-                if (k0 < qn) asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(e0x), "=r"(e0y) : "r"(queue_s + 8u * k0));
-                if (k1 < qn) asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(e1x), "=r"(e1y) : "r"(queue_s + 8u * k1));
-                const uint4* rp0 = reinterpret_cast<const uint4*>(dv.rows + size_t(e0y) * dint::kEntry);
-                const uint4* rp1 = reinterpret_cast<const uint4*>(dv.rows + size_t(e1y) * dint::kEntry);
-                uint4 r0 = make_uint4(0, 0, 0, 0), r1 = make_uint4(0, 0, 0, 0);
-                if (k0 < qn) r0 = __ldg(rp0);
-                if (k1 < qn) r1 = __ldg(rp1);
-                if (k0 < qn) {
-                    const uint32_t oo = e0x & 0xFFFFFFu, cc = e0x >> 24;
-                    sts_u32(oo, r0.x);
-                    sts_tail3_log2(oo, cc, r0.y, r0.z, r0.w);
+                for (uint32_t k = lane; k < qn; k += 32u) {
+                    uint32_t ex, ey;
+                    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(ex), "=r"(ey) : "r"(queue_s + 8u * k));
+                    const uint4* rp = reinterpret_cast<const uint4*>(dv.rows + size_t(ey) * dint::kEntry);
+                    const uint4 r = __ldg(rp);
+                    const uint32_t oo = ex & 0xFFFFFFu, cc = ex >> 24;
+                    sts_u32(oo, r.x);
+                    sts_tail3_log2(oo, cc, r.y, r.z, r.w);
                     if (cc > 2u) {
-                        sts_4(oo + 16u, __ldg(rp0 + 1));
+                        sts_4(oo + 16u, __ldg(rp + 1));
                         if (cc > 3u) {
-                            sts_4(oo + 32u, __ldg(rp0 + 2));
-                            sts_4(oo + 48u, __ldg(rp0 + 3));
-                        }
-                    }
-                }
-                if (k1 < qn) {
-                    const uint32_t oo = e1x & 0xFFFFFFu, cc = e1x >> 24;
-                    sts_u32(oo, r1.x);
-                    sts_tail3_log2(oo, cc, r1.y, r1.z, r1.w);
-                    if (cc > 2u) {
-                        sts_4(oo + 16u, __ldg(rp1 + 1));
-                        if (cc > 3u) {
-                            sts_4(oo + 32u, __ldg(rp1 + 2));
-                            sts_4(oo + 48u, __ldg(rp1 + 3));
+                            sts_4(oo + 32u, __ldg(rp + 2));
+                            sts_4(oo + 48u, __ldg(rp + 3));
                         }
                     }
                 }
                 qn = 0;
                 __syncwarp();
             };
+            // length of a row beyond the hot rows + its place in the copy queue
+            auto cold_row = [&](uint32_t sym, uint32_t oo, uint32_t cold_mask) -> uint32_t {
+                const uint32_t symc = min(sym, last_row);
+                uint32_t code = lds_u8(group_s + (symc >> 5));
+                if (code > 8u) {  // the 32 rows of the group differ in length
+                    if (code != 0xFFu) code = lds_u8(detail_s + ((code - 9u) << 4) + ((symc & 31u) >> 1));
+                    else code = __ldg(lutg + (symc >> 1));
+                    code = (code >> ((symc & 1u) << 2)) & 15u;
+                }
+                const uint32_t slot = queue_s + 8u * (qn + __popc(cold_mask & lanemask_lt()));
+                asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(slot), "r"(oo | (code << 24)), "r"(c_row_base + symc) : "memory");
+                return code;
+            };
+            // stores of one codeword: exception payload, or the entry's words (runs store nothing: the image is zeroed)
+            auto put = [&](uint32_t oo, uint32_t sym, bool on, bool dichot, uint32_t code, uint4 r, uint32_t pay) {
+                const uint32_t words = dichot ? code : 0u;
+                if (sym < 2u) r.x = pay;
+                if (on && (sym < 2u || dichot)) sts_u32(oo, r.x);
+                sts_tail3_log2(oo, words, r.y, r.z, r.w);
+                if (words > 2u) {
+                    sts_4(oo + 16u, lds_v4(hot0_s + hot1_delta + (sym << 4)));
+                    if (words > 3u) {
+                        const uint4* rp = reinterpret_cast<const uint4*>(dv.rows + size_t(c_row_base + sym) * dint::kEntry);
+                        sts_4(oo + 32u, __ldg(rp + 2));
+                        sts_4(oo + 48u, __ldg(rp + 3));
+                    }
+                }
+            };
 
+            // One codeword per trip. The only loop-carried values are the two cursors; the input cursor depends
+            // on nothing but the symbol, so the words under the NEXT symbol are requested before the table
+            // lookups and the stores of this one (shared-memory stores would otherwise fence them).
             bool act = o < o_end;
+            uint32_t w0 = lds_u32(p & ~3u), w1 = lds_u32((p & ~3u) + 4);
             while (__any_sync(FULL, act)) {
                 const uint32_t a4 = p & ~3u, sh = p << 3;  // the funnel shift takes its count mod 32
-                const uint32_t w0 = lds_u32(a4), w1 = lds_u32(a4 + 4);
                 const uint32_t lo = __funnelshift_r(w0, w1, sh);
                 const uint32_t sym = lo & symmask;
                 uint32_t w2 = w1;
                 if (sym == 1u) w2 = lds_u32(a4 + 8);
+                const uint32_t pn = min(p + symbytes + (sym < 2u ? 2u + 2u * sym : 0u), p_lim);
+                const uint32_t n0 = lds_u32(pn & ~3u), n1 = lds_u32((pn & ~3u) + 4);
+                const bool hot = sym < hot_rows;
+                uint32_t code = 0;  // log2(entry length); rows 0 and 1 hold length 1, rows 2..6 the run lengths
+                uint4 r = make_uint4(0, 0, 0, 0);
+                const bool dic = act && sym >= dint::kReserved;
+                if (hot) {
+                    code = lds_u8(hotlen_s + sym);
+                    // one-integer entries (a third of the docs codewords) need one word, not the row's 16 bytes
+                    if (dic) {
+                        if (code) r = lds_v4(hot0_s + (sym << 4));
+                        else r.x = lds_u32(hot0_s + (sym << 4));
+                    }
+                }
                 // what follows the codeword: 32 bits after a 1, 16 bits after a 0
                 uint32_t pay = __funnelshift_r(lo, __funnelshift_r(w1, w2, sh), symbits);
                 if (sym != 1u) pay &= 0xFFFFu;
-                uint32_t code = 0;  // log2(entry length); rows 0 and 1 hold length 1, rows 2..6 the run lengths
-                uint4 r = make_uint4(0, 0, 0, 0);
-                const bool hot = sym < hot_rows;
-                const bool dic = act && sym >= dint::kReserved;
                 const bool cold = dic && !hot;
-                if (hot) {
-                    code = lds_u8(hotlen_s + sym);
-                    if (dic) r = lds_v4(hot0_s + (sym << 4));
+                const uint32_t cm = __ballot_sync(FULL, cold);
+                if (cm) {
+                    if (cold) code = cold_row(sym, o, cm);
+                    qn += __popc(cm);
                 }
-                const uint32_t cold_mask = __ballot_sync(FULL, cold);
-                if (cold_mask) {
-                    if (cold) {
-                        const uint32_t symc = min(sym, last_row);
-                        code = lds_u8(group_s + (symc >> 5));
-                        if (code > 8u) {  // the 32 rows of the group differ in length
-                            if (code != 0xFFu) code = lds_u8(detail_s + ((code - 9u) << 4) + ((symc & 31u) >> 1));
-                            else code = __ldg(lutg + (symc >> 1));
-                            code = (code >> ((symc & 1u) << 2)) & 15u;
-                        }
-                        const uint32_t slot = queue_s + 8u * (qn + __popc(cold_mask & lanemask_lt()));
-                        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(slot), "r"(o | (code << 24)), "r"(c_row_base + symc) : "memory");
-                    }
-                    qn += __popc(cold_mask);
-                }
-                const uint32_t words = (dic && hot) ? code : 0u;  // log2(words to copy now); runs copy nothing: the image is zeroed
-                if (sym < 2u) r.x = pay;
-                if (act && (sym < 2u || (dic && hot))) sts_u32(o, r.x);
-                sts_tail3_log2(o, words, r.y, r.z, r.w);
-                if (words > 2u) {
-                    sts_4(o + 16u, lds_v4(hot0_s + hot1_delta + (sym << 4)));
-                    if (words > 3u) {
-                        const uint4* rp = reinterpret_cast<const uint4*>(dv.rows + size_t(c_row_base + sym) * dint::kEntry);
-                        sts_4(o + 32u, __ldg(rp + 2));
-                        sts_4(o + 48u, __ldg(rp + 3));
-                    }
-                }
+                put(o, sym, act, dic && hot, code, r, pay);
                 o += 4u << code;
-                p = min(p + symbytes + (sym < 2u ? 2u + 2u * sym : 0u), p_lim);
+                p = pn;
+                w0 = n0;
+                w1 = n1;
                 act = o < o_end;
                 if (qn > kColdQueue - 32u) drain();
             }

@@ -107,7 +107,7 @@ typedef struct dint_block {
 
 /* Strip tables: the work decomposition of the lane-sequential decoder (dint_decode_strips).
  * A STRIP is a piece of one codeword stream that starts on a codeword boundary, holds at most
- * a fixed number of codewords (default 16) of ONE dictionary class / symbol width and
+ * a fixed number of codewords (default 8) of ONE dictionary class / symbol width and
  * produces a known number of integers; one thread decodes one strip. A STRIP UNIT is up to 32
  * consecutive strips (one per lane of a warp) whose compressed bytes lie within
  * DINT_UNIT_MAX_BYTES of each other and whose outputs are contiguous in the packed output
@@ -116,7 +116,7 @@ typedef struct dint_block {
 #define DINT_UNIT_MAX_INTS 4095u  /* out_rel has 12 bits                                    */
 #define DINT_UNIT_MAX_BYTES 8191u /* in_rel has 13 bits                                     */
 /* The limits this build of the library actually uses (they size the decoder's shared-memory
- * buffers; defaults 2048 integers / 3584 bytes / 16 codewords per strip; the environment
+ * buffers; defaults 1024 integers / 1792 bytes / 8 codewords per strip; the environment
  * variables DINT_B200_UNIT_INTS, DINT_B200_UNIT_BYTES, DINT_B200_STRIP_CODEWORDS override
  * them at first use, for tuning). Units beyond them are rejected by dint_decode_strips'
  * kernels (their output is left untouched). */
@@ -184,6 +184,11 @@ const uint32_t* dint_vroom_plan_unit_first(const dint_vroom_plan* p);
  * dint_vroom_ctx_* calls consume. */
 uint64_t dint_vroom_plan_num_strip_units(const dint_vroom_plan* p);
 const dint_strip_unit* dint_vroom_plan_strip_units(const dint_vroom_plan* p);
+/* Shape of the file's codeword streams, counted by the pre-pass (diagnostics; no reference counterpart):
+ * out[0] 16-bit exceptions, [1] 32-bit exceptions, [2] run codewords, [3..7] dictionary entries of
+ * 1, 2, 4, 8, 16 integers, [8] u8 codewords, [9] u16 codewords, [10] integers produced by runs,
+ * [11] sum over strip units of the longest strip (codewords), [12] strips. */
+void dint_vroom_plan_codeword_stats(const dint_vroom_plan* p, uint64_t out[16]);
 /* n_lists + 1 offsets into the packed output; list i is [off[i], off[i+1]) */
 const uint64_t* dint_vroom_plan_list_offsets(const dint_vroom_plan* p);
 /* n_lists + 1 byte offsets of the list headers; the last one is the file size */

@@ -38,3 +38,8 @@ for type_ in sys.argv[1:] or ["multi_packed_dint", "single_packed_dint"]:
               f"ints/strip {sint.sum()/n_strips.sum():.1f}, max ints/strip per unit (mean) {sint.max(1).mean():.0f}, "
               f"bytes/strip {sbytes.sum()/n_strips.sum():.1f} max-bytes/strip per unit mean {sbytes.max(1).mean():.0f}")
         print("   units with n_strips<32: %.1f%%; narrow strips %.1f%%" % (100*(n_strips<32).mean(), 100*((sel>=6)&(k<n_strips[:,None])).sum()/n_strips.sum()))
+        cs = plan.codeword_stats
+        ncw = cs["u8_codewords"] + cs["u16_codewords"]
+        print("   codewords %d (%.2f ints/codeword): " % (ncw, int(plan.n_ints) / ncw) +
+              ", ".join(f"{k} {100 * v / ncw:.1f}%" for k, v in cs.items() if k in ("exc16", "exc32", "runs", "len1", "len2", "len4", "len8", "len16", "u8_codewords")) +
+              f"; run ints {100 * cs['run_ints'] / int(plan.n_ints):.1f}% of ints; loop trips {cs['unit_trips']} for {ncw} codewords -> lane utilisation {100 * ncw / (32 * cs['unit_trips']):.1f}%")
