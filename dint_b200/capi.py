@@ -22,7 +22,7 @@ SEGMENT_DTYPE = np.dtype([("in_off", "<u8"), ("out_off", "<u8"), ("n", "<u4"), (
 BLOCK_DTYPE = np.dtype([("in_off", "<u8"), ("out_off", "<u8"), ("size", "<u4"), ("cur_base", "<u4"),
                         ("block_max", "<u4"), ("reserved", "<u4")])
 STRIP_UNIT_DTYPE = np.dtype([("in_off", "<u8"), ("out_off", "<u8"), ("doc_base", "<u4"), ("list_starts", "<u4"),
-                             ("in_len", "<u2"), ("n_ints", "<u2"), ("n_strips", "u1"), ("reserved", "u1", (3,)),
+                             ("in_len", "<u2"), ("n_ints", "<u2"), ("n_strips", "u1"), ("flags", "u1"), ("reserved", "u1", (2,)),
                              ("strip", "<u4", (32,))])
 assert SEGMENT_DTYPE.itemsize == 32 and BLOCK_DTYPE.itemsize == 32 and STRIP_UNIT_DTYPE.itemsize == 160
 

@@ -345,7 +345,7 @@ struct strip_builder {
     const uint8_t* s_ptr = nullptr;
     uint64_t s_out = 0;
     uint32_t s_cw = 0, s_base = 0, s_sel = 0;
-    bool s_list_start = false;
+    bool s_list_start = false, s_has_run = false;
     // codeword statistics (dint_vroom_plan_codeword_stats)
     uint64_t* hist = nullptr;
     const uint8_t* c_ptr = nullptr;
@@ -363,20 +363,24 @@ struct strip_builder {
         s_base = acc;
         s_sel = sel;
         s_list_start = list_start;
+        s_has_run = false;
         c_ptr = p;
         c_out = out_idx;
     }
     // one codeword was walked: the stream is now at q, out_idx integers are out, acc = sum(v + 1) of the list so far
     void codeword(const uint8_t* q, uint64_t out_idx, uint32_t acc, bool stream_end) {
-        if (hist) {
+        {
             const bool narrow = s_sel >= kSelectors;
             const uint32_t sym = narrow ? uint32_t(*c_ptr) : uint32_t(c_ptr[0]) | (uint32_t(c_ptr[1]) << 8);
             const uint64_t len = out_idx - c_out;
             uint32_t k = sym == 0 ? 0u : sym == 1 ? 1u : sym < kReserved ? 2u : 3u;
-            if (k == 3u) for (uint64_t l = len; l > 1; l >>= 1) ++k;  // 3..7: entries of 1, 2, 4, 8, 16 integers
-            ++hist[k];
-            ++hist[narrow ? 8 : 9];
-            if (k == 2u) hist[10] += len;  // integers produced by run codewords
+            if (k == 2u) s_has_run = true;
+            if (hist) {
+                if (k == 3u) for (uint64_t l = len; l > 1; l >>= 1) ++k;  // 3..7: entries of 1, 2, 4, 8, 16 integers
+                ++hist[k];
+                ++hist[narrow ? 8 : 9];
+                if (k == 2u) hist[10] += len;  // integers produced by run codewords
+            }
         }
         c_ptr = q;
         c_out = out_idx;
@@ -414,6 +418,7 @@ struct strip_builder {
         const uint32_t k = cur.n_strips;
         cur.strip[k] = uint32_t(in0 - cur.in_off) | (uint32_t(cur.n_ints) << 13) | (s_sel << 25);
         if (k && s_list_start) cur.list_starts |= 1u << k;
+        if (s_has_run) cur.flags |= DINT_UNIT_HAS_RUNS;
         cur.n_ints = uint16_t(cur.n_ints + n);
         cur.in_len = uint16_t(in1 - cur.in_off);
         cur.n_strips = uint8_t(k + 1);

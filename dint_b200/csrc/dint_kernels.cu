@@ -776,12 +776,22 @@ int dint_decode_strips(const dint_dict* d, const uint8_t* d_in, size_t in_bytes,
     int warps = int(std::min<size_t>((budget - fixed) / per_warp, max_warps));
     const size_t smem = fixed + size_t(warps) * per_warp;
     const int grid = int(std::max<uint64_t>(1, std::min<uint64_t>((n_units + warps - 1) / warps, uint64_t(di.sms))));
-#define LAUNCH_STRIPS(M)                                                                                   \
-    CUDA_TRY(cudaFuncSetAttribute(decode_strips_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))); \
-    decode_strips_kernel<M><<<grid, warps * 32, smem, st>>>(P);
+    // kernel variant (see decode_strips_kernel): d-gap streams 0, frequency streams 3; DINT_B200_STRIP_VARIANT overrides
+    static const int forced = [] {
+        const char* v = std::getenv("DINT_B200_STRIP_VARIANT");
+        return v && *v ? int(std::strtoul(v, nullptr, 10)) & 3 : -1;
+    }();
+    const int variant = forced >= 0 ? forced : (mode == DINT_MODE_FREQS ? 3 : 0);
+#define LAUNCH_STRIPS_V(M, V)                                                                                   \
+    CUDA_TRY(cudaFuncSetAttribute(decode_strips_kernel<M, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))); \
+    decode_strips_kernel<M, V><<<grid, warps * 32, smem, st>>>(P);
+#define LAUNCH_STRIPS(M)                                                                   \
+    if (variant == 0) { LAUNCH_STRIPS_V(M, 0) } else if (variant == 1) { LAUNCH_STRIPS_V(M, 1) } \
+    else if (variant == 2) { LAUNCH_STRIPS_V(M, 2) } else { LAUNCH_STRIPS_V(M, 3) }
     if (mode == DINT_MODE_RAW) { LAUNCH_STRIPS(OUT_RAW) }
     else if (mode == DINT_MODE_DOCIDS) { LAUNCH_STRIPS(OUT_DOCIDS) }
     else { LAUNCH_STRIPS(OUT_FREQS) }
+#undef LAUNCH_STRIPS_V
 #undef LAUNCH_STRIPS
     ++g_launches;
     CUDA_TRY(cudaGetLastError());

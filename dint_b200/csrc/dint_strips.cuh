@@ -4,28 +4,31 @@
 // to the output cursor, advance both cursors (vroom_env/dint_codecs.hpp:37-107 for u16
 // codewords, :574-609 for u8 codewords). The only loop-carried values are the two cursors, so
 // the loop parallelises over *pieces of the stream whose start cursors are known*. The host
-// pre-pass (dint_vroom_plan_create) cuts every stream into STRIPS of at most 16 codewords and
+// pre-pass (dint_vroom_plan_create) cuts every stream into STRIPS of at most 8 codewords and
 // records where each strip starts in the input and in the output (include/dint_b200.h,
 // dint_strip_unit). Here one THREAD runs the reference's loop over one strip, 32 strips (one
 // STRIP UNIT) per warp, with no warp-level coordination inside the loop:
 //
-//   input      the unit's compressed bytes (<= 3.5 KB, contiguous in the file) are staged in
+//   input      the unit's compressed bytes (<= 1.75 KB, contiguous in the file) are staged in
 //              shared memory with 16-byte cp.async; every thread then reads its own strip with
-//              aligned 4-byte shared loads + a funnel shift (any byte alignment).
-//   length     4-bit log2(length) table, one slice per dictionary class indexed by the symbol;
-//              the first lut_rows rows of every class live in shared memory, the rest (rare
-//              symbols of multi_packed's u16 blocks) are read through L1 from global memory.
-//   entry      16-byte vector loads from the expanded dictionary rows (L1/L2 resident).
+//              aligned 4-byte shared loads + a funnel shift (any byte alignment), keeping the two
+//              words under its cursor in registers from one codeword to the next.
+//   length     one byte of log2(length) per row for the hot rows of every dictionary class
+//              (the 256 rows u8 codewords can address; 2048 for a single dictionary) in shared
+//              memory; colder rows (u16 codewords only) use a per-32-row group table.
+//   entry      hot rows: the first 32 bytes of the row from shared memory; colder rows are
+//              queued and copied from the L2-resident dictionary 32 codewords at a time.
 //   output     an IMAGE of the unit's slice of the packed output array in shared memory
-//              (<= 2048 integers), pre-zeroed, so runs of zeros only advance the cursor. Each
-//              thread stores its entries at its own cursor.
+//              (<= 1024 integers by default). Each thread stores its entries at its own cursor. Run
+//              codewords store nothing, they only advance the cursor: a unit that holds one
+//              (DINT_UNIT_HAS_RUNS, set by the pre-pass) clears its image first.
 //   flush      when all strips are done the warp reads the image back one uint4 per lane,
 //              applies the fused transform (docID prefix sum with restarts at list starts, or
-//              the freq +1 shift), writes 512 contiguous, 16-byte aligned bytes per
-//              instruction with streaming stores, and re-zeroes the image.
+//              the freq +1 shift) and writes 512 contiguous, 16-byte aligned bytes per
+//              instruction with streaming stores.
 //
-// Work per codeword is ~50 warp instructions for 32 codewords; the warp-wide work (staging,
-// flush) is amortised over a whole unit (~512 codewords).
+// The kernel is bound by the shared-memory data pipe (LSU wavefronts: every lane reads its own
+// strip and writes at its own cursor, so most accesses pay 2-4 wavefronts), see profiles/.
 #pragma once
 
 #include "dint_decoder.cuh"
@@ -74,15 +77,15 @@ __device__ __forceinline__ unsigned lanemask_lt() {
     return m;
 }
 
-// Writes the image [0, a + n_ints) of a unit to out[out_off - a ...] with the transform of MODE and
-// re-zeroes it. a = out_off & 3, so that image quads are aligned quads of the output array.
-template <int MODE>
+// Writes the image [0, a + n_ints) of a unit to out[out_off - a ...] with the transform of MODE.
+// a = out_off & 3, so that image quads are aligned quads of the output array.
+template <int MODE, bool ZERO>
 __device__ __forceinline__ void flush_image(uint32_t image_s, uint32_t bits_s, uint32_t* __restrict__ out, uint64_t out_off,
                                             uint32_t n_ints, uint32_t doc_base, bool unit_heads, bool vec_ok, unsigned lane) {
     const uint32_t a = uint32_t(out_off) & 3u;
     const uint32_t total = a + n_ints;
     uint32_t* gq = out + (out_off - a) + 4u * lane;
-    // docid[i] = acc + sum_{j <= i} (v_j + 1). The a image words in front of the unit hold zeros and are
+    // docid[i] = acc + sum_{j <= i} (v_j + 1). The a image words in front of the unit are read as zeros and
     // scanned like values (each adds 1), so they are discounted here; words past the unit's end cannot
     // change anything in front of them. Only groups that hold a list start need the segmented scan.
     uint32_t acc = doc_base - 1u - a;
@@ -91,8 +94,13 @@ __device__ __forceinline__ void flush_image(uint32_t image_s, uint32_t bits_s, u
         const uint32_t sp = image_s + (q << 2);
         uint4 v;
         asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(sp));
-        asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(sp), "r"(0u) : "memory");
+        if (ZERO) asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(sp), "r"(0u) : "memory");
         const uint32_t lo = g0 ? 0u : a;
+        if (!ZERO && MODE == OUT_DOCIDS && g0 == 0u && lane == 0u) {  // the words in front of the unit count as zeros
+            if (a > 0u) v.x = 0u;
+            if (a > 1u) v.y = 0u;
+            if (a > 2u) v.z = 0u;
+        }
         const uint32_t hi = min(128u, total - g0);
         if (MODE == OUT_DOCIDS) {
             uint32_t f = 0;  // bit i: element i of my quad starts a list
@@ -181,6 +189,7 @@ struct unit_header {
     __device__ __forceinline__ uint32_t in_len() const { return h1.z & 0xFFFFu; }
     __device__ __forceinline__ uint32_t n_ints() const { return h1.z >> 16; }
     __device__ __forceinline__ uint32_t n_strips() const { return h1.w & 0xFFu; }
+    __device__ __forceinline__ bool has_runs() const { return (h1.w >> 8) & DINT_UNIT_HAS_RUNS; }
     // a unit this build can hold (warp-uniform); anything else is skipped, its output left untouched
     __device__ __forceinline__ bool ok(const strip_params& P) const {
         return !(n_ints() > P.unit_ints || in_len() > P.unit_bytes || n_strips() > 32u || in_off() + in_len() > P.in_bytes ||
@@ -190,8 +199,13 @@ struct unit_header {
 
 constexpr uint32_t kStripClassBytes = 8u * uint32_t(sizeof(strip_class));
 
-template <int MODE>
+// VARIANT bit 0: keep the input words under the cursor in registers instead of reloading them every trip;
+// bit 1: clear the image only for units with run codewords (else the flush always re-zeroes it). Both pay off
+// on streams of short codewords without runs or exceptions (freqs: -9 %) and cost 3 % each on d-gap streams
+// (half of the codewords are exceptions, half of the integers come from runs), see profiles/README.md.
+template <int MODE, int VARIANT>
 __global__ void __launch_bounds__(1024, 1) decode_strips_kernel(const strip_params P) {
+    constexpr bool REUSE = (VARIANT & 1) != 0, RUNFLAG = (VARIANT & 2) != 0;
     extern __shared__ __align__(16) uint8_t smem[];
     const unsigned lane = lane_id();
     const uint32_t warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
@@ -297,6 +311,9 @@ __global__ void __launch_bounds__(1024, 1) decode_strips_kernel(const strip_para
                 start_word_s = bits_s + ((pos >> 5) << 2);
                 asm volatile("atom.shared.or.b32 _, [%0], %1;" ::"r"(start_word_s), "r"(1u << (pos & 31u)) : "memory");
             }
+            if (RUNFLAG && H.has_runs())  // run codewords store nothing: they rely on a cleared image
+                for (uint32_t q = 4u * lane; q < a + n_ints; q += 128u)
+                    asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(image_s + (q << 2)), "r"(0u) : "memory");
             cp_async_wait_all();
             __syncwarp();
 
@@ -370,18 +387,23 @@ __global__ void __launch_bounds__(1024, 1) decode_strips_kernel(const strip_para
                 uint32_t w2 = w1;
                 if (sym == 1u) w2 = lds_u32(a4 + 8);
                 const uint32_t pn = min(p + symbytes + (sym < 2u ? 2u + 2u * sym : 0u), p_lim);
-                const uint32_t n0 = lds_u32(pn & ~3u), n1 = lds_u32((pn & ~3u) + 4);
+                const uint32_t a4n = pn & ~3u;  // a4, a4 + 4 or a4 + 8: most trips reuse a word already in a register
+                uint32_t n0 = w0, n1 = w1;
+                if (!REUSE) {
+                    n0 = lds_u32(a4n);
+                    n1 = lds_u32(a4n + 4);
+                } else if (a4n != a4) {
+                    n0 = w1;
+                    if (a4n != a4 + 4u) n0 = lds_u32(a4n);
+                    n1 = lds_u32(a4n + 4);
+                }
                 const bool hot = sym < hot_rows;
                 uint32_t code = 0;  // log2(entry length); rows 0 and 1 hold length 1, rows 2..6 the run lengths
                 uint4 r = make_uint4(0, 0, 0, 0);
                 const bool dic = act && sym >= dint::kReserved;
                 if (hot) {
                     code = lds_u8(hotlen_s + sym);
-                    // one-integer entries (a third of the docs codewords) need one word, not the row's 16 bytes
-                    if (dic) {
-                        if (code) r = lds_v4(hot0_s + (sym << 4));
-                        else r.x = lds_u32(hot0_s + (sym << 4));
-                    }
+                    if (dic) r = lds_v4(hot0_s + (sym << 4));
                 }
                 // what follows the codeword: 32 bits after a 1, 16 bits after a 0
                 uint32_t pay = __funnelshift_r(lo, __funnelshift_r(w1, w2, sh), symbits);
@@ -409,7 +431,7 @@ __global__ void __launch_bounds__(1024, 1) decode_strips_kernel(const strip_para
 
         // ---- write the unit ------------------------------------------------------------------------------------
         if (valid) {
-            flush_image<MODE>(image_s, bits_s, P.out, out_off, n_ints, doc_base, (starts & ~1u) != 0u, vec_ok, lane);
+            flush_image<MODE, !RUNFLAG>(image_s, bits_s, P.out, out_off, n_ints, doc_base, (starts & ~1u) != 0u, vec_ok, lane);
             if (MODE == OUT_DOCIDS && start_word_s) sts_u32(start_word_s, 0u);
             __syncwarp();
         }

@@ -113,6 +113,7 @@ typedef struct dint_block {
  * DINT_UNIT_MAX_BYTES of each other and whose outputs are contiguous in the packed output
  * (at most DINT_UNIT_MAX_INTS integers). 160 bytes, 16-byte aligned. */
 #define DINT_UNIT_STRIPS 32
+#define DINT_UNIT_HAS_RUNS 1u
 #define DINT_UNIT_MAX_INTS 4095u  /* out_rel has 12 bits                                    */
 #define DINT_UNIT_MAX_BYTES 8191u /* in_rel has 13 bits                                     */
 /* The limits this build of the library actually uses (they size the decoder's shared-memory
@@ -130,7 +131,9 @@ typedef struct dint_strip_unit {
     uint16_t in_len;      /* bytes from in_off to the end of the last strip                   */
     uint16_t n_ints;      /* integers the unit produces                                       */
     uint8_t n_strips;     /* 1..32                                                            */
-    uint8_t reserved[3];
+    uint8_t flags;        /* DINT_UNIT_HAS_RUNS: some codeword of the unit is a run of zeros, which the
+                             decoder does not store: it clears the unit's output image first       */
+    uint8_t reserved[2];
     /* strip k: bits 0-12 in_rel (bytes from in_off to its first codeword), bits 13-24 out_rel
      * (integers before it inside the unit), bits 25-28 selector: 0..5 = u16 codewords of class
      * selector, 6..11 = u8 codewords of class selector - 6 (single dictionaries: 0). The strip

@@ -2,6 +2,8 @@
   (1) the sha256 of the reference decoders' own output (tests/golden/manifest.json), and
   (2) the oracle (oracle/dint_oracle.c) on the same inputs, element by element.
 Bit-exact: this is integer work, there is no tolerance."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -79,12 +81,18 @@ def test_index_scan_equals_reference_enumerator(golden, oracle, type_):
 
 
 def test_query_log_ragged_batch(golden, oracle):
-    """config 3: ragged batch = only the lists touched by a query log (here: a seeded sample of
-    1088 distinct terms, the size of test_data/queries' vocabulary), decoded in one launch"""
+    """config 3: ragged batch = only the posting lists touched by the reference's query log
+    (tests/golden/queries.json <- test/test_data/queries: 500 AND queries, 1088 distinct terms,
+    731 581 postings), decoded in one launch"""
+    import json
     type_ = "single_packed_dint"
     vf = driver.VroomFile(type_, golden.bytes(golden.vroom_name(type_, "docs")), golden.bytes(golden.dict_name(type_, "docs")))
-    rng = np.random.default_rng(42)
-    terms = np.sort(rng.choice(vf.n_lists, 1088, replace=False))
+    with open(os.path.join(g.GOLD, "queries.json")) as fq:
+        queries = json.load(fq)["queries"]
+    terms = np.array(sorted({t for q in queries for t in q}), dtype=np.int64)
+    assert len(queries) == 500 and len(terms) == 1088 and terms.max() < vf.n_lists
+    lo = vf.plan.list_offsets.astype(np.int64)
+    assert int((lo[terms + 1] - lo[terms]).sum()) == 731581  # SURVEY §8d config 3
     segs = vf.plan.segments
     list_of = np.searchsorted(vf.plan.list_offsets, segs["out_off"], side="right") - 1
     pick = segs[np.isin(list_of, terms)].copy()
