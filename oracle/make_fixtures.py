@@ -60,6 +60,9 @@ def main():
     ap.add_argument("--bs", type=int, default=256)
     ap.add_argument("--seed-dir", default="/tmp/probe/run")
     ap.add_argument("--no-commit-fixtures", action="store_true")
+    ap.add_argument("--types", default=",".join(TYPES), help="comma-separated subset of the codec types")
+    ap.add_argument("--index-only", action="store_true",
+                    help="frozen dict_freq_index files only (the vroom streams of the single dictionaries do not depend on block_size)")
     args = ap.parse_args()
 
     sh(["make", "-C", HERE, "ref", f"BS={args.bs}", "-j8"])
@@ -69,7 +72,8 @@ def main():
 
     # dictionaries do not depend on block_size for the single kinds; multi statistics do
     # (statistics_collectors.hpp:93-104), so seeds are only reused at the shipped block size.
-    for t, (dname, _) in TYPES.items():
+    types = {t: TYPES[t] for t in args.types.split(",")}
+    for t, (dname, _) in types.items():
         for part in ("docs", "freqs"):
             f = f"dict.test_collection.{part}.{dname}.DSF-65536-16"
             src = os.path.join(args.seed_dir, f)
@@ -105,7 +109,7 @@ def main():
                                           ctypes.c_size_t, ctypes.POINTER(ctypes.c_uint64)]
     assert lib.ref_block_size() == args.bs
 
-    for t, (dname, kind) in TYPES.items():
+    for t, (dname, kind) in types.items():
         idx = f"index.{t}.bin"
         sh([os.path.join(out, "ref_index"), "build", t, COLL, idx], cwd=data)  # also builds missing dicts
         sh([os.path.join(out, "ref_index"), "dump", t, idx, "dump.docs.u32", "dump.freqs.u32"], cwd=data)
@@ -115,7 +119,7 @@ def main():
         assert sha(df.tobytes()) == manifest["golden"]["freqs_sha256"]
         os.remove(os.path.join(data, "dump.docs.u32"))
         os.remove(os.path.join(data, "dump.freqs.u32"))
-        for part, want in (("docs", gaps_flat), ("freqs", (freqs_flat - 1).astype("<u4"))):
+        for part, want in (() if args.index_only else (("docs", gaps_flat), ("freqs", (freqs_flat - 1).astype("<u4")))):
             dict_file = f"dict.test_collection.{part}.{dname}.DSF-65536-16"
             vb = f"vroom.{t}.{part}.bin"
             sh([os.path.join(out, "vroom_encode"), t, f"{COLL}.{part}", "--dict", dict_file, "--out", vb], cwd=data)
@@ -138,7 +142,7 @@ def main():
         manifest["files"][idx] = {"bytes": len(b), "sha256": sha(b)}
 
     # rect and packed vroom streams are byte-identical (SURVEY §8c cross-format pin)
-    for part in ("docs", "freqs"):
+    for part in (() if args.index_only or not {"single_rect_dint", "single_packed_dint"} <= set(types) else ("docs", "freqs")):
         a = manifest["files"][f"vroom.single_rect_dint.{part}.bin"]["sha256"]
         b = manifest["files"][f"vroom.single_packed_dint.{part}.bin"]["sha256"]
         assert a == b, "rect/packed vroom streams differ"

@@ -21,3 +21,11 @@ def oracle():
 def golden():
     import golden_data
     return golden_data.Golden()
+
+
+@pytest.fixture(scope="session")
+def golden128():
+    """frozen dict_freq_index files built by the reference with constants::block_size = 128
+    (BASELINE.json configs[1]; oracle/make_fixtures.py --bs 128)"""
+    import golden_data
+    return golden_data.Golden("bs128")

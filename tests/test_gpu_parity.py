@@ -80,6 +80,20 @@ def test_index_scan_equals_reference_enumerator(golden, oracle, type_):
     assert np.array_equal(_np(d2), wd) and np.array_equal(_np(f2), wf)
 
 
+@pytest.mark.parametrize("type_", ("single_rect_dint", "single_packed_dint"))
+def test_index_scan_block128(golden128, oracle, type_):
+    """config 2 with 128-integer blocks (BASELINE.json configs[1]); the index was built by the reference
+    compiled with constants::block_size = 128"""
+    data = golden128.bytes(golden128.index_name(type_))
+    idx = driver.IndexFile(type_, data, block_size=128)
+    d, f = idx.scan()
+    d, f = _np(d), _np(f)
+    assert g.sha(d.tobytes()) == golden128.sha["docids_sha256"]
+    assert g.sha(f.tobytes()) == golden128.sha["freqs_sha256"]
+    wd, wf, _ = oracle.index_decode(KINDS[type_], data, golden128.n_postings, 128)
+    assert np.array_equal(d, wd) and np.array_equal(f, wf)
+
+
 def test_query_log_ragged_batch(golden, oracle):
     """config 3: ragged batch = only the posting lists touched by the reference's query log
     (tests/golden/queries.json <- test/test_data/queries: 500 AND queries, 1088 distinct terms,

@@ -45,6 +45,16 @@ def test_oracle_index_matches_reference_digest(oracle, golden, type_):
     assert g.sha(f.astype("<u4").tobytes()) == golden.sha["freqs_sha256"]
 
 
+@pytest.mark.parametrize("type_", ("single_rect_dint", "single_packed_dint"))
+def test_oracle_index_block128_matches_reference_digest(oracle, golden128, type_):
+    """config 2 as BASELINE.json words it: 128-integer blocks (the reference ships 256)"""
+    assert golden128.block_size == 128
+    d, f, ln = oracle.index_decode(KINDS[type_], golden128.bytes(golden128.index_name(type_)), golden128.n_postings, 128)
+    assert len(ln) == golden128.n_lists and int(ln.sum()) == golden128.n_postings
+    assert g.sha(d.astype("<u4").tobytes()) == golden128.sha["docids_sha256"]
+    assert g.sha(f.astype("<u4").tobytes()) == golden128.sha["freqs_sha256"]
+
+
 def test_reserved_codewords(oracle, golden):
     """codeword space of SURVEY §9: 0,1 exceptions (len 1); 2..6 runs of 256..16 zeros"""
     for type_ in g.TYPES:
