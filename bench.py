@@ -202,44 +202,63 @@ def cpu_baseline(w, budget_s=12.0):
 # clocks
 # ------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi sampled every 20 ms from before the warm-up on; only the samples whose timestamp falls inside
+    the timed region [mark_begin, mark_end] are reported."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.proc = None
         self.index = index
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                          "-lms", "20", "-i", str(self.index)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
 
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             out, _ = self.proc.communicate(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
             out, _ = self.proc.communicate()
-        sm, mx, reasons = [], [], set()
+        import datetime
+        sm, mx, reasons, sm_all, mx_all = [], [], set(), [], []
         for line in out.splitlines():
             f = [x.strip() for x in line.split(",")]
             if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                clk, cmax = float(f[1]), float(f[2])
             except ValueError:
                 continue
+            sm_all.append(clk)
+            mx_all.append(cmax)
+            if self.t0 is not None and self.t1 is not None and not (self.t0 <= ts <= self.t1 + 0.02):
+                continue
+            sm.append(clk)
+            mx.append(cmax)
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
+        if not sm:  # clock skew between nvidia-smi's local time and ours: fall back to the last samples
+            sm, mx = sm_all[-3:], mx_all[-3:]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
 
@@ -336,6 +355,8 @@ def run_gpu(args):
         if events is not None:
             events[2].record(st)
 
+    sampler = ClockSampler(local)
+    sampler.start()
     # ---- warm-up + parity (untimed) ---------------------------------------------------------
     for _ in range(max(args.warmup, 1)):
         step()
@@ -359,12 +380,11 @@ def run_gpu(args):
     # ---- timed region -----------------------------------------------------------------------
     K = args.steps
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
-    sampler = ClockSampler(local)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(dev)
     launches0 = capi.kernel_launches()
-    sampler.start()
+    sampler.mark_begin()
     t_start = torch.cuda.Event(enable_timing=True)
     t_end = torch.cuda.Event(enable_timing=True)
     t_start.record(st)
@@ -372,6 +392,7 @@ def run_gpu(args):
         step(ev[i])
     t_end.record(st)
     torch.cuda.synchronize(dev)
+    sampler.mark_end()
     if world > 1:
         dist.barrier()
     clocks = sampler.stop()

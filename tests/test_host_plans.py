@@ -182,12 +182,30 @@ def test_strip_units_tile_the_file(oracle, golden, type_, part):
     # decode sampled units strip by strip
     raw = np.frombuffer(bin_ + b"\0" * 64, dtype=np.uint8)
     rng = np.random.default_rng(11)
+    flagged = 0
     for ui in np.unique(np.concatenate([rng.integers(0, len(U), 60), [0, len(U) - 1]])):
         u = U[ui]
         ends = list(out_rel[ui][1:u["n_strips"]]) + [int(u["n_ints"])]
+        has_run = False
         for j in range(int(u["n_strips"])):
             n = int(ends[j]) - int(out_rel[ui][j])
             start = int(u["in_off"]) + int(in_rel[ui][j])
+            # walk the strip's codewords (reference loop, lengths from the oracle's dictionary): <= strip_codewords of
+            # them, and DINT_UNIT_HAS_RUNS must be set exactly when one of them is a run
+            narrow = int(sel[ui][j]) >= 6
+            cls = int(sel[ui][j]) - 6 if narrow else int(sel[ui][j])
+            q, produced, cws = start, 0, 0
+            while produced < n:
+                sym = int(raw[q]) if narrow else int(raw[q]) | (int(raw[q + 1]) << 8)
+                q += 1 if narrow else 2
+                if sym < 2:
+                    q += 2 + 2 * sym
+                    produced += 1
+                else:
+                    produced += oracle.dict_copy(ho, cls, sym)[0]
+                    has_run = has_run or sym < 7
+                cws += 1
+            assert produced == n and 1 <= cws <= lim["strip_codewords"]
             if kind != 2:
                 a, used_bytes = oracle.vroom_decode_list(ho, raw[start:], n)
             else:
@@ -196,4 +214,12 @@ def test_strip_units_tile_the_file(oracle, golden, type_, part):
                 used_bytes -= 1
             o = int(u["out_off"]) + int(out_rel[ui][j])
             assert np.array_equal(a, vals[o:o + n])
-            assert start + used_bytes <= int(u["in_off"]) + int(u["in_len"])
+            assert start + used_bytes <= int(u["in_off"]) + int(u["in_len"]) and q == start + used_bytes
+        assert bool(u["flags"] & 1) == has_run
+        flagged += has_run
+    cs = plan.codeword_stats
+    assert cs["u8_codewords"] + cs["u16_codewords"] == sum(cs[k] for k in ("exc16", "exc32", "runs", "len1", "len2", "len4", "len8", "len16"))
+    assert cs["exc16"] + cs["exc32"] + cs["len1"] + 2 * cs["len2"] + 4 * cs["len4"] + 8 * cs["len8"] + 16 * cs["len16"] + \
+        cs["run_ints"] == golden.n_postings
+    assert cs["strips"] == int(U["n_strips"].sum()) and (cs["u8_codewords"] == 0 or kind == 2)
+    assert (cs["runs"] > 0) == bool((U["flags"] & 1).any()) and (flagged == 0 or cs["runs"] > 0)
