@@ -163,6 +163,66 @@ def test_edge_case_streams(golden, oracle, type_, kw):
             assert np.array_equal(_np(vf.decode(mode=capi.MODE_FREQS)), want + np.uint32(1))
 
 
+def _random_lists(di, rng, n_lists, long_list):
+    """lists assembled from real dictionary entries of every length (hot rows, cold rows, all classes), bursts
+    of zeros (run codewords), small values and >= 65 536 values (32-bit exceptions)"""
+    pools = []
+    for ents in di.classes:
+        by_len = {}
+        for i, t in enumerate(ents[:65536]):
+            if t is not None:
+                by_len.setdefault(len(t), []).append(t)
+        if by_len:  # the last class of a multi dictionary may hold nothing but the reserved rows
+            pools.append(by_len)
+    lists = []
+    for li in range(n_lists):
+        n = long_list if li == 0 else int(rng.choice([1, 2, 3, 7, 15, 16, 17, 31, 100, 255, 256, 257, 700, 3000]))
+        vals = []
+        bursts = (li // 15) % 2 == 0  # stretches of lists without zero bursts: units without run codewords
+        while len(vals) < n:
+            kind = rng.integers(0, 10)
+            if kind in (5, 6) and not bursts:
+                kind = 7
+            if kind < 5:
+                by_len = pools[int(rng.integers(0, len(pools)))]
+                ln = int(rng.choice(list(by_len)))
+                ents = by_len[ln]
+                vals.extend(ents[int(rng.integers(0, len(ents)))])
+            elif kind < 6:
+                vals.extend([0] * int(rng.choice([1, 5, 16, 17, 40, 128, 300])))
+            elif kind < 9:
+                vals.extend(rng.integers(0, 70000, int(rng.integers(1, 6))).tolist())
+            else:
+                vals.extend(rng.integers(65536, 1 << 32, int(rng.integers(1, 4))).tolist())
+        lists.append(vals[:n])
+    return lists
+
+
+@pytest.mark.parametrize("type_", g.TYPES)
+@pytest.mark.parametrize("seed", (1, 2))
+def test_random_streams_property(golden, oracle, type_, seed):
+    """randomised lists (one of 60 000 integers) through both decoders and all modes == oracle == numpy"""
+    rng = np.random.default_rng(seed)
+    dict_bytes = golden.bytes(golden.dict_name(type_, "docs" if seed == 1 else "freqs"))
+    di = sb.DictImage(capi.KIND_OF_TYPE[type_], dict_bytes)
+    lists = _random_lists(di, rng, 120, 60000)
+    want = np.concatenate([np.asarray(v, dtype=np.uint32) for v in lists])
+    sels = rng.integers(0, 12, 64).tolist()
+    ho = oracle.dict_parse(KINDS[type_], dict_bytes)
+    for engine in ENGINES:
+        out, data, vf = _decode_lists(type_, dict_bytes, lists, engine=engine, selectors=sels)
+        o, _ = oracle.vroom_decode_file(ho, data, len(want), len(lists))
+        assert np.array_equal(o, want)  # the stream is valid and says what we meant
+        assert np.array_equal(out, want), engine
+        exp = np.concatenate([(np.cumsum(np.asarray(v, dtype=np.uint64) + 1) - 1).astype(np.uint32) for v in lists])
+        assert np.array_equal(_np(vf.decode(mode=capi.MODE_DOCIDS)), exp), engine
+        assert np.array_equal(_np(vf.decode(mode=capi.MODE_FREQS)), want + np.uint32(1)), engine
+        if engine == "strips":  # the run flag is per unit: some units of this stream have runs, some do not
+            fl = vf.plan.strip_units["flags"] & 1
+            assert fl.any() and not fl.all()
+    oracle.dict_free(ho)
+
+
 @pytest.mark.parametrize("type_", ("single_packed_dint", "multi_packed_dint"))
 @pytest.mark.parametrize("shift", (1, 2, 3))
 def test_strips_unaligned_output_and_input(golden, type_, shift):
