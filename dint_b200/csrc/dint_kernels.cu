@@ -311,15 +311,15 @@ struct bit_reader {
 };
 
 // pre-order walk of read_interpolative (:124-146) with an explicit stack; emit(idx, val)
+// `stack`: this thread's 10 x uint4 of shared memory (depth <= 8 for n <= 255)
 template <typename Emit>
-__device__ void read_interpolative(bit_reader& br, uint32_t n, uint32_t low0, uint32_t high0, Emit&& emit) {
-    uint32_t st_off[10], st_n[10], st_lo[10], st_hi[10];
-    int sp = 0;
-    st_off[0] = 0; st_n[0] = n; st_lo[0] = low0; st_hi[0] = high0;
-    sp = 1;
+__device__ void read_interpolative(bit_reader& br, uint32_t n, uint32_t low0, uint32_t high0, uint4* stack, Emit&& emit) {
+    int sp = 1;
+    stack[0] = make_uint4(0u, n, low0, high0);
     while (sp) {
         --sp;
-        uint32_t off = st_off[sp], cnt = st_n[sp], lo = st_lo[sp], hi = st_hi[sp];
+        const uint4 e = stack[sp];
+        uint32_t off = e.x, cnt = e.y, lo = e.z, hi = e.w;
         for (;;) {
             uint32_t h = cnt / 2;
             uint32_t val = lo + br.read_int(hi - lo + 1u);
@@ -327,7 +327,7 @@ __device__ void read_interpolative(bit_reader& br, uint32_t n, uint32_t low0, ui
             if (cnt == 1) break;
             uint32_t rn = cnt - h - 1;
             if (rn) {  // right half later
-                st_off[sp] = off + h + 1; st_n[sp] = rn; st_lo[sp] = val; st_hi[sp] = hi;
+                stack[sp] = make_uint4(off + h + 1, rn, val, hi);
                 ++sp;
             }
             if (!h) break;
@@ -347,40 +347,72 @@ __device__ __forceinline__ uint32_t vbyte_at(const uint8_t* base, uint64_t nbyte
     return v;
 }
 
-__global__ void __launch_bounds__(128)
+constexpr int kTailThreads = 128;
+__global__ void __launch_bounds__(kTailThreads)
 index_tails_kernel(const uint8_t* __restrict__ lists, uint64_t lists_bytes, const dint_block* __restrict__ blocks,
                    uint64_t n_blocks, uint32_t block_size, uint32_t* __restrict__ docids, uint32_t* __restrict__ freqs) {
-    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n_blocks; i += uint64_t(gridDim.x) * blockDim.x) {
-        const dint_block b = blocks[i];
-        if (b.size >= block_size) continue;
-        const uint32_t n = b.size;
-        uint64_t p = b.in_off;
-        // docs: prefix sums P_i of the first n-1 values in [0, S], P_{n-1} = S
-        // (block_codecs.hpp:139-146); docid_i = cur_base + P_i + i (dict_posting_list.hpp:304-307,122)
-        const uint32_t S = b.block_max - b.cur_base - (n - 1u);
-        uint32_t* dd = docids ? docids + b.out_off : nullptr;
-        if (dd) dd[n - 1] = b.block_max;
-        if (n > 1) {
-            bit_reader br;
-            br.init(lists, lists_bytes, p);
-            const uint32_t cb = b.cur_base;
-            read_interpolative(br, n - 1, 0, S, [&](uint32_t idx, uint32_t val) {
-                if (dd) dd[idx] = cb + val + idx;
-            });
-            p += (br.pos + 7) / 8;
+    __shared__ uint4 stacks[kTailThreads * 10];
+    uint4* stack = stacks + threadIdx.x * 10;
+    const unsigned lane = threadIdx.x & 31u;
+    const uint64_t step = uint64_t(gridDim.x) * blockDim.x;
+    // warp-uniform trip count: the adjacent-difference pass at the end of a trip is done by the whole warp
+    for (uint64_t i0 = uint64_t(blockIdx.x) * blockDim.x + (threadIdx.x & ~31u); i0 < n_blocks; i0 += step) {
+        const uint64_t i = i0 + lane;
+        dint_block b;
+        b.size = block_size;  // lanes past the end / full blocks: nothing to do
+        if (i < n_blocks) b = blocks[i];
+        const bool tail = i < n_blocks && b.size < block_size;
+        const uint32_t n = tail ? b.size : 0u;
+        if (tail) {
+            uint64_t p = b.in_off;
+            // docs: prefix sums P_i of the first n-1 values in [0, S], P_{n-1} = S
+            // (block_codecs.hpp:139-146); docid_i = cur_base + P_i + i (dict_posting_list.hpp:304-307,122)
+            const uint32_t S = b.block_max - b.cur_base - (n - 1u);
+            uint32_t* dd = docids ? docids + b.out_off : nullptr;
+            if (dd) dd[n - 1] = b.block_max;
+            if (n > 1) {
+                bit_reader br;
+                br.init(lists, lists_bytes, p);
+                const uint32_t cb = b.cur_base;
+                read_interpolative(br, n - 1, 0, S, stack, [&](uint32_t idx, uint32_t val) {
+                    if (dd) dd[idx] = cb + val + idx;
+                });
+                p += (br.pos + 7) / 8;
+            }
+            if (freqs) {
+                // freqs: sum_of_values == -1 -> leading vbyte (block_codecs.hpp:134-136); prefix sums first
+                uint32_t* ff = freqs + b.out_off;
+                const uint32_t Sf = vbyte_at(lists, lists_bytes, p);
+                ff[n - 1] = Sf;
+                if (n > 1) {
+                    bit_reader br;
+                    br.init(lists, lists_bytes, p);
+                    read_interpolative(br, n - 1, 0, Sf, stack, [&](uint32_t idx, uint32_t val) { ff[idx] = val; });
+                }
+            }
         }
         if (!freqs) continue;
-        // freqs: sum_of_values == -1 -> leading vbyte (block_codecs.hpp:134-136)
-        uint32_t* ff = freqs + b.out_off;
-        const uint32_t Sf = vbyte_at(lists, lists_bytes, p);
-        ff[n - 1] = Sf;
-        if (n > 1) {
-            bit_reader br;
-            br.init(lists, lists_bytes, p);
-            read_interpolative(br, n - 1, 0, Sf, [&](uint32_t idx, uint32_t val) { ff[idx] = val; });
-            for (uint32_t k = n - 1; k > 0; --k) ff[k] = ff[k] - ff[k - 1] + 1u;  // adjacent differences, freq = v + 1
+        // adjacent differences, freq = v + 1 (block_codecs.hpp:147-149, dict_posting_list.hpp:168): the warp
+        // walks the 32 tails of this trip together, 32 values at a time from the back, instead of every
+        // thread running a serial read-modify-write loop over global memory
+        __syncwarp();
+        const uint32_t have = __ballot_sync(FULL, n > 0u);
+        for (uint32_t m = have; m; m &= m - 1u) {
+            const int k = __ffs(m) - 1;
+            const uint32_t kn = __shfl_sync(FULL, n, k);
+            uint32_t* ff = freqs + __shfl_sync(FULL, b.out_off, k);
+            for (int32_t c = int32_t((kn - 1u) / 32u); c >= 0; --c) {
+                const uint32_t j = uint32_t(c) * 32u + lane;
+                uint32_t v = 0, w = 0;
+                if (j < kn) {
+                    v = ff[j];
+                    w = j ? ff[j - 1] : 0u;
+                }
+                __syncwarp();
+                if (j < kn) ff[j] = v - w + 1u;
+                __syncwarp();
+            }
         }
-        ff[0] += 1u;
     }
 }
 
