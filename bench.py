@@ -202,7 +202,7 @@ def cpu_baseline(w, budget_s=12.0):
 # clocks
 # ------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi sampled every 20 ms from before the warm-up on; only the samples whose timestamp falls inside
+    """nvidia-smi sampled every 50 ms from before the warm-up on; only the samples whose timestamp falls inside
     the timed region [mark_begin, mark_end] are reported."""
     Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -216,7 +216,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "20", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                          "-lms", "50", "-i", str(self.index)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
