@@ -56,7 +56,7 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
-        path = _build.build()
+        path = os.environ.get("DINT_B200_LIB") or _build.build()  # override: A/B builds of the same ABI (profiles/tools)
         L = C.CDLL(path)
         vp, sz, u32, u64, i32 = C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint64, C.c_int
         L.dint_last_error.restype = C.c_char_p

@@ -204,7 +204,7 @@ constexpr uint32_t kStripClassBytes = 8u * uint32_t(sizeof(strip_class));
 // on streams of short codewords without runs or exceptions (freqs: -9 %) and cost 3 % each on d-gap streams
 // (half of the codewords are exceptions, half of the integers come from runs), see profiles/README.md.
 template <int MODE, int VARIANT>
-__global__ void __launch_bounds__(1024, 1) decode_strips_kernel(const strip_params P) {
+__global__ void __launch_bounds__(768, 1) decode_strips_kernel(const strip_params P) {
     constexpr bool REUSE = (VARIANT & 1) != 0, RUNFLAG = (VARIANT & 2) != 0;
     extern __shared__ __align__(16) uint8_t smem[];
     const unsigned lane = lane_id();
