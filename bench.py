@@ -317,6 +317,26 @@ class ReplicatedStream:
                                self.out.data_ptr(), mode, stream=stream)
 
 
+def bind_to_gpu_numa_node(torch, local):
+    """Multi-rank runs: keep this rank's host threads (and therefore its pinned staging buffers, first touch)
+    on the CPUs next to its GPU, so that the end-to-end copies do not cross sockets. Best effort."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pr = torch.cuda.get_device_properties(local)
+        bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = [i * 64 + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1]
+        allowed = set(os.sched_getaffinity(0))
+        cpus = [c for c in cpus if c in allowed]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return 0
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -331,6 +351,7 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        bind_to_gpu_numa_node(torch, local)
         dist.init_process_group("nccl", device_id=dev)
 
     w = load_workload(args.workload, args.type, FULL_POSTINGS.get(args.workload.split("_")[0], 6_000_000_000))
