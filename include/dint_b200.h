@@ -28,7 +28,7 @@
  *                            include/dint/dint_codecs.hpp:13-49, 269-274, 460-510
  *                            include/ds2i/block_codecs.hpp:130-150
  *   dint_decode_strips     the same two decoders, lane-sequential: one THREAD walks one strip of
- *                          <= 16 codewords exactly like the reference's scalar loop
+ *                          <= 8 codewords exactly like the reference's scalar loop
  *                            vroom_env/dint_codecs.hpp:37-107 (u16), :574-609 (u8)
  *   dint_decode_list_host  one Decoder::decode(dict, in, out, universe, n) call, host buffers
  *   dint_vroom_ctx_* /     the whole decode_dint() loop of vroom_env/decode.cpp:139-150 on HOST
