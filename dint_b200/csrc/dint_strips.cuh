@@ -168,6 +168,21 @@ __device__ __forceinline__ void flush_image(uint32_t image_s, uint32_t bits_s, u
     }
 }
 
+// predicated shared loads: the destination keeps its value when the predicate is false (no branch)
+__device__ __forceinline__ void lds_u8_if(uint32_t& v, uint32_t a, bool p) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q ld.shared.u8 %0, [%1];\n\t}" : "+r"(v) : "r"(a), "r"(uint32_t(p)));
+}
+__device__ __forceinline__ void lds_v4_if(uint4& v, uint32_t a, bool p) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %5, 0;\n\t@q ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];\n\t}"
+                 : "+r"(v.x), "+r"(v.y), "+r"(v.z), "+r"(v.w)
+                 : "r"(a), "r"(uint32_t(p)));
+}
+// a register quad whose contents do not matter yet (no instruction; avoids zeroing it every trip)
+__device__ __forceinline__ uint4 undefined_v4() {
+    uint4 v;
+    asm volatile("" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w));
+    return v;
+}
 __device__ __forceinline__ uint4 lds_v4(uint32_t a) {
     uint4 v;
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
@@ -249,12 +264,22 @@ __global__ void __launch_bounds__(768, 1) decode_strips_kernel(const strip_param
     auto stage = [&](uint64_t in_off, uint32_t in_len) {
         const uint64_t g = in_base + in_off, g0 = g & ~uint64_t(15);
         const uint32_t n_chunks = ((uint32_t(g) & 15u) + in_len + 12u + 15u) >> 4;  // a thread reads up to 12 bytes past its symbol
-        const uint32_t n_file = uint32_t(min(uint64_t(n_chunks), (in_hi - g0) >> 4));
-        uint64_t ga = g0 + 16u * lane;
-        uint32_t sa = inbuf_s + 16u * lane;
-        for (uint32_t i = lane; i < n_chunks; i += 32, ga += 512, sa += 512) {
-            if (i < n_file) cp_async16(sa, ga);
-            else asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(sa), "r"(0u) : "memory");
+        const bool at_end = g0 + 16ull * n_chunks > in_hi;                         // only the last units of a file
+        const uint32_t n_file = at_end ? uint32_t((in_hi - g0) >> 4) : n_chunks;
+        const uint64_t ga = g0 + 16u * lane;
+        const uint32_t sa = inbuf_s + 16u * lane;
+        if (P.inbuf_bytes <= 4u * 512u) {  // default limits: four straight-line rounds
+#pragma unroll
+            for (uint32_t j = 0; j < 4u; ++j) {
+                const uint32_t i = lane + 32u * j;
+                if (i < n_file) cp_async16(sa + 512u * j, ga + 512u * j);
+                else if (i < n_chunks) asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(sa + 512u * j), "r"(0u) : "memory");
+            }
+            return;
+        }
+        for (uint32_t i = lane, k = 0; i < n_chunks; i += 32, k += 512) {
+            if (i < n_file) cp_async16(sa + k, ga + k);
+            else asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(sa + k), "r"(0u) : "memory");
         }
     };
 
@@ -263,9 +288,11 @@ __global__ void __launch_bounds__(768, 1) decode_strips_kernel(const strip_param
     unit_header H;
     H.h0 = H.h1 = make_uint4(0, 0, 0, 0);
     H.word = 0;
+    bool valid = false;  // H passed ok() (checked once, when its bytes were requested)
     if (u < P.n_units) {
         H.load(P.units, u, lane);
-        if (H.ok(P)) stage(H.in_off(), H.in_len());
+        valid = H.ok(P);
+        if (valid) stage(H.in_off(), H.in_len());
     }
     while (u < P.n_units) {
         // ---- the next unit's header is fetched while this one is decoded ---------------------------------
@@ -274,7 +301,6 @@ __global__ void __launch_bounds__(768, 1) decode_strips_kernel(const strip_param
         unit_header N = H;
         if (more) N.load(P.units, un, lane);
 
-        const bool valid = H.ok(P);
         const uint64_t out_off = H.out_off();
         const uint32_t n_ints = H.n_ints();
         const uint32_t doc_base = H.h1.x, starts = H.h1.y;
@@ -399,20 +425,19 @@ __global__ void __launch_bounds__(768, 1) decode_strips_kernel(const strip_param
                 }
                 const bool hot = sym < hot_rows;
                 uint32_t code = 0;  // log2(entry length); rows 0 and 1 hold length 1, rows 2..6 the run lengths
-                uint4 r = make_uint4(0, 0, 0, 0);
+                uint4 r = undefined_v4();  // only the words a predicate below selects are ever stored
                 const bool dic = act && sym >= dint::kReserved;
-                if (hot) {
-                    code = lds_u8(hotlen_s + sym);
-                    if (dic) r = lds_v4(hot0_s + (sym << 4));
-                }
+                lds_u8_if(code, hotlen_s + sym, hot);
+                lds_v4_if(r, hot0_s + (sym << 4), dic && hot);
                 // what follows the codeword: 32 bits after a 1, 16 bits after a 0
                 uint32_t pay = __funnelshift_r(lo, __funnelshift_r(w1, w2, sh), symbits);
                 if (sym != 1u) pay &= 0xFFFFu;
                 const bool cold = dic && !hot;
                 const uint32_t cm = __ballot_sync(FULL, cold);
-                if (cm) {
+                if (cm) {  // warp-uniform
                     if (cold) code = cold_row(sym, o, cm);
                     qn += __popc(cm);
+                    if (qn > kColdQueue - 32u) drain();  // the queue only grows here
                 }
                 put(o, sym, act, dic && hot, code, r, pay);
                 o += 4u << code;
@@ -420,14 +445,14 @@ __global__ void __launch_bounds__(768, 1) decode_strips_kernel(const strip_param
                 w0 = n0;
                 w1 = n1;
                 act = o < o_end;
-                if (qn > kColdQueue - 32u) drain();
             }
             if (qn) drain();
             __syncwarp();
         }
 
         // ---- the next unit's bytes travel while this one is written ---------------------------------------
-        if (more && N.ok(P)) stage(N.in_off(), N.in_len());
+        const bool n_valid = more && N.ok(P);
+        if (n_valid) stage(N.in_off(), N.in_len());
 
         // ---- write the unit ------------------------------------------------------------------------------------
         if (valid) {
@@ -437,6 +462,7 @@ __global__ void __launch_bounds__(768, 1) decode_strips_kernel(const strip_param
         }
         u = un;
         H = N;
+        valid = n_valid;
     }
     cp_async_wait_all();
 }
