@@ -122,11 +122,9 @@ __device__ __forceinline__ void flush_image(uint32_t image_s, uint32_t bits_s, u
                 v.z += base;
                 v.w += base;
             } else {
-                const uint32_t e = 4u * lane;
-                const bool l0 = e >= lo && e < hi, l1 = e + 1 >= lo && e + 1 < hi, l2 = e + 2 >= lo && e + 2 < hi,
-                           l3 = e + 3 >= lo && e + 3 < hi;
-                const uint32_t t0 = l0 ? v.x + 1u : 0u, t1 = l1 ? v.y + 1u : 0u, t2 = l2 ? v.z + 1u : 0u,
-                               t3 = l3 ? v.w + 1u : 0u;
+                // as in the plain scan, the zeros in front of the unit count 1 each (acc is discounted for them)
+                // and whatever lies past its end cannot reach a stored value
+                const uint32_t t0 = v.x + 1u, t1 = v.y + 1u, t2 = v.z + 1u, t3 = v.w + 1u;
                 // lane-local sums restarting at list starts; r = plain lane total
                 const uint32_t p0 = t0;
                 const uint32_t p1 = (f & 2u) ? t1 : p0 + t1;
@@ -138,7 +136,7 @@ __device__ __forceinline__ void flush_image(uint32_t image_s, uint32_t bits_s, u
                 const uint32_t prevH = __ballot_sync(FULL, f != 0u) & lanemask_lt();
                 const uint32_t hl = prevH ? 31u - uint32_t(__clz(prevH)) : 0u;
                 const uint32_t from_head = __shfl_sync(FULL, p3 - S, hl);
-                const uint32_t c = (prevH ? from_head - 1u : acc + lo) + (S - r);
+                const uint32_t c = (prevH ? from_head - 1u : acc) + (S - r);
                 v.x = (f & 1u) ? p0 - 1u : c + p0;
                 v.y = (f & 3u) ? p1 - 1u : c + p1;
                 v.z = (f & 7u) ? p2 - 1u : c + p2;
