@@ -789,12 +789,12 @@ int dint_decode_strips(const dint_dict* d, const uint8_t* d_in, size_t in_bytes,
     P.bits_words = strip_bits_words(lim.unit_ints);
     P.inbuf_bytes = strip_inbuf_bytes(lim.unit_bytes);
     // one persistent CTA per SM: as many warps as the shared-memory budget holds next to the length table
-    // (the rest of the 256 KB stays L1 for the dictionary rows)
+    // (all of the 227 KB a CTA may have: the 24th warp is worth more than the L1 left for the colder dictionary rows)
     const size_t fixed = size_t(P.dv.strip_tables_bytes) + kStripClassBytes;
     const size_t per_warp = strip_warp_smem(lim.unit_ints, lim.unit_bytes);
     static const uint32_t budget_kb = [] {
         const char* v = std::getenv("DINT_B200_STRIP_SMEM_KB");
-        return v && *v ? uint32_t(std::strtoul(v, nullptr, 10)) : 224u;
+        return v && *v ? uint32_t(std::strtoul(v, nullptr, 10)) : 227u;
     }();
     const size_t budget = std::min(size_t(budget_kb) * 1024, size_t(di.max_smem_optin));
     if (fixed + per_warp > budget) {
@@ -803,7 +803,7 @@ int dint_decode_strips(const dint_dict* d, const uint8_t* d_in, size_t in_bytes,
     }
     static const uint32_t max_warps = [] {
         const char* v = std::getenv("DINT_B200_STRIP_WARPS");
-        return v && *v ? std::min(32u, std::max(1u, uint32_t(std::strtoul(v, nullptr, 10)))) : 24u;
+        return v && *v ? std::min(24u, std::max(1u, uint32_t(std::strtoul(v, nullptr, 10)))) : 24u;
     }();
     int warps = int(std::min<size_t>((budget - fixed) / per_warp, max_warps));
     const size_t smem = fixed + size_t(warps) * per_warp;
