@@ -223,6 +223,64 @@ def test_random_streams_property(golden, oracle, type_, seed):
     oracle.dict_free(ho)
 
 
+def _synthetic_packed_dictionary(n_classes, rows_per_class, seed):
+    """a single_packed (n_classes = 1) or multi_packed dictionary FILE whose entry lengths change from row to row, so
+    that every group of 32 rows is mixed: more mixed groups than the decoder's per-class detail table holds (246),
+    which forces the fall-back to the global 4-bit length table (no reference-built dictionary does that)"""
+    rng = np.random.default_rng(seed)
+    offsets, starts, table = [], [], [0] * 16
+    for c in range(n_classes):
+        starts.append(len(offsets))
+        offsets += [0, 0, 0xFF000000, 0x7F000000, 0x3F000000, 0x1F000000, 0x0F000000]  # single_dictionary.hpp:43-55
+        for i in range(7, rows_per_class):
+            ln = (1, 2, 4, 8, 16)[int(rng.integers(0, 5))]
+            offsets.append(((ln - 1) << 24) | len(table))
+            # distinct tuples: the first value identifies (class, row); keep them < 65536 so that the greedy test
+            # encoder never confuses an entry with an exception payload
+            table += [(i * 7 + c) % 65521] + rng.integers(0, 50, ln - 1).tolist()
+    table += [0] * 16
+    if n_classes == 1:
+        hdr = [rows_per_class, len(offsets), len(table)]
+    else:
+        hdr = [rows_per_class, n_classes, len(offsets), len(table)] + starts
+    return np.array(hdr + offsets + table, dtype="<u4").tobytes()
+
+
+@pytest.mark.parametrize("type_,n_classes", (("single_packed_dint", 1), ("multi_packed_dint", 6)))
+def test_dictionary_with_mixed_lengths_in_every_group(oracle, type_, n_classes):
+    """cold rows whose lengths come from the per-class detail table AND from the global length table"""
+    dict_bytes = _synthetic_packed_dictionary(n_classes, 20000, 3)
+    kind = capi.KIND_OF_TYPE[type_]
+    di = sb.DictImage(kind, dict_bytes)
+    rng = np.random.default_rng(4)
+    lists = []
+    for li in range(60):
+        vals = []
+        n = int(rng.choice([5, 40, 300, 2000]))
+        cls = int(rng.integers(0, n_classes))
+        while len(vals) < n:
+            row = int(rng.integers(7, 20000))  # mostly beyond the hot rows, all over the group table
+            vals.extend(di.classes[cls][row])
+            if rng.integers(0, 8) == 0:
+                vals.extend([0] * int(rng.choice([3, 16, 40])))
+            if rng.integers(0, 8) == 0:
+                vals.append(int(rng.integers(65536, 1 << 32)))
+        lists.append(vals[:n])
+    want = np.concatenate([np.asarray(v, dtype=np.uint32) for v in lists])
+    ho = oracle.dict_parse(KINDS[type_], dict_bytes)
+    sels = [0, 1, 2, 3, 4, 5, 7, 9] if n_classes > 1 else None
+    for engine in ENGINES:
+        out, data, vf = _decode_lists(type_, dict_bytes, lists, engine=engine, selectors=sels)
+        o, _ = oracle.vroom_decode_file(ho, data, len(want), len(lists))
+        assert np.array_equal(o, want)
+        assert np.array_equal(out, want), engine
+        exp = np.concatenate([(np.cumsum(np.asarray(v, dtype=np.uint64) + 1) - 1).astype(np.uint32) for v in lists])
+        assert np.array_equal(_np(vf.decode(mode=capi.MODE_DOCIDS)), exp), engine
+    cs = vf.plan.codeword_stats
+    assert cs["u16_codewords"] > 1000 and min(cs[k] for k in ("len1", "len2", "len4", "len8", "len16")) > 50
+    oracle.dict_free(ho)
+
+
 @pytest.mark.parametrize("type_", ("single_packed_dint", "multi_packed_dint"))
 @pytest.mark.parametrize("shift", (1, 2, 3))
 def test_strips_unaligned_output_and_input(golden, type_, shift):
