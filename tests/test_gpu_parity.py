@@ -301,6 +301,32 @@ def test_strips_unaligned_output_and_input(golden, type_, shift):
     assert np.all(got[:shift] == 0xFFFFFFFF) and np.all(got[shift + vf.n_ints:] == 0xFFFFFFFF)
 
 
+def test_strips_rejects_units_beyond_the_limits(golden, vroom_files):
+    """a unit the decoder cannot hold (corrupt table: too many integers / bytes / strips, or input past the end)
+    is skipped: its slice of the output stays untouched, every other unit decodes, nothing faults"""
+    vf = vroom_files("single_packed_dint", "docs")
+    good = _np(vf.decode(mode=capi.MODE_DOCIDS))
+    U = vf.plan.strip_units.copy()
+    lim = capi.strip_limits()
+    bad = {3: ("n_ints", lim["unit_ints"] + 4), 10: ("in_len", lim["unit_bytes"] + 1), 17: ("n_strips", 33),
+           25: ("in_off", vf.plan.in_bytes), 40: ("n_ints", 0)}
+    for i, (field, value) in bad.items():
+        U[field][i] = value
+    d_units = torch.from_numpy(U.view(np.uint8).reshape(-1)).cuda()
+    out = torch.full((vf.n_ints,), -559038737, dtype=torch.int32, device="cuda")  # 0xDEADBEEF
+    capi.decode_strips(vf.dict, vf.d_in.data_ptr(), vf.plan.in_bytes, d_units.data_ptr(), len(U), out.data_ptr(),
+                       capi.MODE_DOCIDS, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    got = _np(out)
+    orig = vf.plan.strip_units
+    skipped = np.zeros(vf.n_ints, dtype=bool)
+    for i in bad:
+        o, n = int(orig["out_off"][i]), int(orig["n_ints"][i])
+        skipped[o:o + n] = True
+    assert np.all(got[skipped] == 0xDEADBEEF)
+    assert np.array_equal(got[~skipped], good[~skipped])
+
+
 def test_empty_batch_and_empty_file(golden):
     dict_bytes = golden.bytes(golden.dict_name("single_packed_dint", "docs"))
     vf = driver.VroomFile("single_packed_dint", b"", dict_bytes)
