@@ -53,7 +53,7 @@
 extern "C" {
 #endif
 
-#define DINT_B200_ABI_VERSION 3
+#define DINT_B200_ABI_VERSION 4 /* 4: dint_strip_unit.flags (DINT_UNIT_HAS_RUNS) is REQUIRED for units with run codewords */
 
 /* dictionary kinds == the reference's three dictionary types */
 enum {
