@@ -269,67 +269,51 @@ struct walker {
     const dint_dict* d;
     const uint8_t* bin;
     const uint8_t* end;
-    // walks `count` integers of u16 codewords of class `cls` starting at p; returns the end
-    // pointer or nullptr. acc accumulates sum(v + 1). cut: emit chunk boundaries.
-    template <typename Cut>
-    const uint8_t* walk16(const uint8_t* p, uint32_t cls, uint64_t count, uint32_t& acc, Cut&& cut) const {
+    // Walks `count` integers of SB-byte codewords (2: u16, 1: u8) of class `cls` starting at p; returns the end
+    // pointer or nullptr. acc accumulates sum(v + 1). cut(q, i, acc, symbol, length) is called after every
+    // codeword. The body is written without data-dependent branches: in a d-gap stream every other codeword is an
+    // exception, which a branch predictor cannot learn.
+    template <unsigned SB, typename Cut>
+    const uint8_t* walk(const uint8_t* p, uint32_t cls, uint64_t count, uint32_t& acc, Cut&& cut) const {
         const uint32_t base = d->class_base[cls], csize = d->class_size[cls];
+        const uint8_t* lens = d->h_lens.data() + base;
+        const uint32_t* sums = d->h_sums.data() + base;
+        const uint8_t* safe = end - std::min<size_t>(size_t(end - bin), SB + 4);  // SB + 4 readable bytes from here back
         uint64_t i = 0;
+        uint32_t a = acc;
         while (i < count) {
-            if (p + 2 > end) return nullptr;
-            uint32_t w = rd16(p);
-            uint32_t len;
-            if (w >= 2) {
-                if (w >= csize) return nullptr;
-                len = uint32_t(d->h_lens[base + w]) + 1;
-                acc += d->h_sums[base + w];
-                p += 2;
-            } else if (w == 1) {
-                if (p + 6 > end) return nullptr;
-                acc += rd32(p + 2) + 1;
-                len = 1;
-                p += 6;
-            } else {
-                if (p + 4 > end) return nullptr;
-                acc += uint32_t(rd16(p + 2)) + 1;
-                len = 1;
-                p += 4;
+            uint32_t w, pay;
+            if (p <= safe) {
+                w = SB == 2 ? rd16(p) : uint32_t(*p);
+                pay = rd32(p + SB);
+            } else {  // the last few bytes of the file: bounded reads
+                if (p + SB > end) return nullptr;
+                w = SB == 2 ? rd16(p) : uint32_t(*p);
+                const uint32_t need = w < 2 ? 2u + 2u * w : 0u;
+                if (p + SB + need > end) return nullptr;
+                pay = 0;
+                for (uint32_t k = 0; k < need; ++k) pay |= uint32_t(p[SB + k]) << (8 * k);
             }
+            if (w >= csize) return nullptr;
+            const bool exc = w < 2;
+            const uint32_t value = w ? pay : (pay & 0xFFFFu);       // what an exception codeword carries
+            const uint32_t len = exc ? 1u : uint32_t(lens[w]) + 1u;  // rows 0 and 1 are never dictionary entries
+            a += exc ? value + 1u : sums[w];
+            p += SB + (exc ? 2u + 2u * w : 0u);
             i += len;
             if (i > count) return nullptr;  // entries must tile the list exactly (`i != n` loop)
-            cut(p, i, acc);
+            cut(p, i, a, w, len);
         }
+        acc = a;
         return p;
     }
     template <typename Cut>
+    const uint8_t* walk16(const uint8_t* p, uint32_t cls, uint64_t count, uint32_t& acc, Cut&& cut) const {
+        return walk<2>(p, cls, count, acc, cut);
+    }
+    template <typename Cut>
     const uint8_t* walk8(const uint8_t* p, uint32_t cls, uint64_t count, uint32_t& acc, Cut&& cut) const {
-        const uint32_t base = d->class_base[cls], csize = d->class_size[cls];
-        uint64_t i = 0;
-        while (i < count) {
-            if (p + 1 > end) return nullptr;
-            uint32_t w = *p;
-            uint32_t len;
-            if (w >= 2) {
-                if (w >= csize) return nullptr;
-                len = uint32_t(d->h_lens[base + w]) + 1;
-                acc += d->h_sums[base + w];
-                p += 1;
-            } else if (w == 1) {
-                if (p + 5 > end) return nullptr;
-                acc += rd32(p + 1) + 1;
-                len = 1;
-                p += 5;
-            } else {
-                if (p + 3 > end) return nullptr;
-                acc += uint32_t(rd16(p + 1)) + 1;
-                len = 1;
-                p += 3;
-            }
-            i += len;
-            if (i > count) return nullptr;
-            cut(p, i, acc);
-        }
-        return p;
+        return walk<1>(p, cls, count, acc, cut);
     }
 };
 
@@ -348,8 +332,6 @@ struct strip_builder {
     bool s_list_start = false, s_has_run = false;
     // codeword statistics (dint_vroom_plan_codeword_stats)
     uint64_t* hist = nullptr;
-    const uint8_t* c_ptr = nullptr;
-    uint64_t c_out = 0;
     uint32_t u_max_cw = 0;
 
     strip_builder(const uint8_t* b, std::vector<dint_strip_unit>& u) : lim(dint::get_strip_limits()), bin(b), units(u) {
@@ -364,26 +346,19 @@ struct strip_builder {
         s_sel = sel;
         s_list_start = list_start;
         s_has_run = false;
-        c_ptr = p;
-        c_out = out_idx;
     }
     // one codeword was walked: the stream is now at q, out_idx integers are out, acc = sum(v + 1) of the list so far
-    void codeword(const uint8_t* q, uint64_t out_idx, uint32_t acc, bool stream_end) {
+    void codeword(const uint8_t* q, uint64_t out_idx, uint32_t acc, bool stream_end, uint32_t sym, uint32_t len) {
         {
-            const bool narrow = s_sel >= kSelectors;
-            const uint32_t sym = narrow ? uint32_t(*c_ptr) : uint32_t(c_ptr[0]) | (uint32_t(c_ptr[1]) << 8);
-            const uint64_t len = out_idx - c_out;
-            uint32_t k = sym == 0 ? 0u : sym == 1 ? 1u : sym < kReserved ? 2u : 3u;
-            if (k == 2u) s_has_run = true;
+            const uint32_t run = uint32_t(sym - 2u < kReserved - 2u);  // symbols 2..6
+            s_has_run |= run != 0;
             if (hist) {
-                if (k == 3u) for (uint64_t l = len; l > 1; l >>= 1) ++k;  // 3..7: entries of 1, 2, 4, 8, 16 integers
+                // 0, 1: exceptions; 2: runs; 3..7: entries of 1, 2, 4, 8, 16 integers
+                const uint32_t k = sym < 2 ? sym : run ? 2u : 3u + uint32_t(__builtin_ctz(len));
                 ++hist[k];
-                ++hist[narrow ? 8 : 9];
-                if (k == 2u) hist[10] += len;  // integers produced by run codewords
+                hist[10] += run ? len : 0u;  // integers produced by run codewords
             }
         }
-        c_ptr = q;
-        c_out = out_idx;
         ++s_cw;
         if (stream_end || s_cw >= lim.strip_codewords || out_idx - s_out >= lim.strip_ints) {
             emit(q, out_idx);
@@ -415,6 +390,7 @@ struct strip_builder {
             open = true;
         }
         u_max_cw = std::max(u_max_cw, s_cw);
+        if (hist) hist[s_sel >= kSelectors ? 8 : 9] += s_cw;
         const uint32_t k = cur.n_strips;
         cur.strip[k] = uint32_t(in0 - cur.in_off) | (uint32_t(cur.n_ints) << 13) | (s_sel << 25);
         if (k && s_list_start) cur.list_starts |= 1u << k;
@@ -462,8 +438,8 @@ int dint_vroom_plan_create(const dint_dict* d, const void* bin_, size_t len, uin
             uint64_t seg_i = 0;
             uint32_t seg_base = 0;
             sb.begin_stream(p, out_off, 0, 0, true);
-            auto cut = [&](const uint8_t* q, uint64_t i, uint32_t a) {
-                sb.codeword(q, out_off + i, a, i == n);
+            auto cut = [&](const uint8_t* q, uint64_t i, uint32_t a, uint32_t sym, uint32_t ln) {
+                sb.codeword(q, out_off + i, a, i == n, sym, ln);
                 if (i - seg_i >= chunk_ints && i < n) {
                     plan->segments.push_back({uint64_t(seg_p - bin), out_off + seg_i, uint32_t(i - seg_i), seg_base,
                                               uint32_t(q - seg_p), a - seg_base});
@@ -497,7 +473,9 @@ int dint_vroom_plan_create(const dint_dict* d, const void* bin_, size_t len, uin
                 }
                 const uint32_t acc0 = acc;
                 sb.begin_stream(p + 1, out_off + done, sel, acc, done == 0);
-                auto cut = [&](const uint8_t* qq, uint64_t i, uint32_t a) { sb.codeword(qq, out_off + done + i, a, i == size); };
+                auto cut = [&](const uint8_t* qq, uint64_t i, uint32_t a, uint32_t sym, uint32_t ln) {
+                    sb.codeword(qq, out_off + done + i, a, i == size, sym, ln);
+                };
                 const uint8_t* q = sel < kSelectors ? wk.walk16(p + 1, sel, size, acc, cut)
                                                     : wk.walk8(p + 1, sel - kSelectors, size, acc, cut);
                 if (!q) {
