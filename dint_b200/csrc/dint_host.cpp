@@ -273,14 +273,15 @@ struct walker {
     // pointer or nullptr. acc accumulates sum(v + 1). cut(q, i, acc, symbol, length) is called after every
     // codeword. The body is written without data-dependent branches: in a d-gap stream every other codeword is an
     // exception, which a branch predictor cannot learn.
-    template <unsigned SB, typename Cut>
-    const uint8_t* walk(const uint8_t* p, uint32_t cls, uint64_t count, uint32_t& acc, Cut&& cut) const {
+    template <unsigned SB, typename Strip, typename Each>
+    const uint8_t* walk(const uint8_t* p, uint32_t cls, uint64_t count, uint32_t& acc, uint32_t strip_codewords,
+                        uint64_t strip_ints, uint64_t* __restrict hist, Strip&& strip, Each&& each) const {
         const uint32_t base = d->class_base[cls], csize = d->class_size[cls];
         const uint8_t* lens = d->h_lens.data() + base;
         const uint32_t* sums = d->h_sums.data() + base;
         const uint8_t* safe = end - std::min<size_t>(size_t(end - bin), SB + 4);  // SB + 4 readable bytes from here back
-        uint64_t i = 0;
-        uint32_t a = acc;
+        uint64_t i = 0, s_i = 0;         // integers walked; integers at the start of the open strip
+        uint32_t a = acc, cw = 0, has_run = 0;
         while (i < count) {
             uint32_t w, pay;
             if (p <= safe) {
@@ -302,18 +303,22 @@ struct walker {
             p += SB + (exc ? 2u + 2u * w : 0u);
             i += len;
             if (i > count) return nullptr;  // entries must tile the list exactly (`i != n` loop)
-            cut(p, i, a, w, len);
+            const uint32_t run = uint32_t(w - 2u < kReserved - 2u);  // symbols 2..6
+            has_run |= run;
+            ++cw;
+            // 0, 1: exceptions; 2: runs; 3..7: entries of 1, 2, 4, 8, 16 integers; 10: integers produced by runs
+            ++hist[exc ? w : run ? 2u : 3u + uint32_t(__builtin_ctz(len))];
+            hist[10] += run ? len : 0u;
+            each(p, i, a);
+            if (i == count || cw >= strip_codewords || i - s_i >= strip_ints) {
+                strip(p, i, a, cw, has_run != 0);
+                cw = 0;
+                has_run = 0;
+                s_i = i;
+            }
         }
         acc = a;
         return p;
-    }
-    template <typename Cut>
-    const uint8_t* walk16(const uint8_t* p, uint32_t cls, uint64_t count, uint32_t& acc, Cut&& cut) const {
-        return walk<2>(p, cls, count, acc, cut);
-    }
-    template <typename Cut>
-    const uint8_t* walk8(const uint8_t* p, uint32_t cls, uint64_t count, uint32_t& acc, Cut&& cut) const {
-        return walk<1>(p, cls, count, acc, cut);
     }
 };
 
@@ -347,23 +352,12 @@ struct strip_builder {
         s_list_start = list_start;
         s_has_run = false;
     }
-    // one codeword was walked: the stream is now at q, out_idx integers are out, acc = sum(v + 1) of the list so far
-    void codeword(const uint8_t* q, uint64_t out_idx, uint32_t acc, bool stream_end, uint32_t sym, uint32_t len) {
-        {
-            const uint32_t run = uint32_t(sym - 2u < kReserved - 2u);  // symbols 2..6
-            s_has_run |= run != 0;
-            if (hist) {
-                // 0, 1: exceptions; 2: runs; 3..7: entries of 1, 2, 4, 8, 16 integers
-                const uint32_t k = sym < 2 ? sym : run ? 2u : 3u + uint32_t(__builtin_ctz(len));
-                ++hist[k];
-                hist[10] += run ? len : 0u;  // integers produced by run codewords
-            }
-        }
-        ++s_cw;
-        if (stream_end || s_cw >= lim.strip_codewords || out_idx - s_out >= lim.strip_ints) {
-            emit(q, out_idx);
-            begin_stream(q, out_idx, s_sel, acc, false);
-        }
+    // a strip of `codewords` codewords ends at q: out_idx integers are out, acc = sum(v + 1) of the list so far
+    void strip(const uint8_t* q, uint64_t out_idx, uint32_t acc, uint32_t codewords, bool has_run) {
+        s_cw = codewords;
+        s_has_run = has_run;
+        emit(q, out_idx);
+        begin_stream(q, out_idx, s_sel, acc, false);
     }
     void close_unit() {
         if (!open) return;
@@ -438,8 +432,10 @@ int dint_vroom_plan_create(const dint_dict* d, const void* bin_, size_t len, uin
             uint64_t seg_i = 0;
             uint32_t seg_base = 0;
             sb.begin_stream(p, out_off, 0, 0, true);
-            auto cut = [&](const uint8_t* q, uint64_t i, uint32_t a, uint32_t sym, uint32_t ln) {
-                sb.codeword(q, out_off + i, a, i == n, sym, ln);
+            auto strip = [&](const uint8_t* q, uint64_t i, uint32_t a, uint32_t cw, bool has_run) {
+                sb.strip(q, out_off + i, a, cw, has_run);
+            };
+            auto each = [&](const uint8_t* q, uint64_t i, uint32_t a) {  // chunks of a long list for the tile decoder
                 if (i - seg_i >= chunk_ints && i < n) {
                     plan->segments.push_back({uint64_t(seg_p - bin), out_off + seg_i, uint32_t(i - seg_i), seg_base,
                                               uint32_t(q - seg_p), a - seg_base});
@@ -448,7 +444,7 @@ int dint_vroom_plan_create(const dint_dict* d, const void* bin_, size_t len, uin
                     seg_base = a;
                 }
             };
-            p = wk.walk16(p, 0, n, acc, cut);
+            p = wk.walk<2>(p, 0, n, acc, sb.lim.strip_codewords, sb.lim.strip_ints, plan->cw_stats, strip, each);
             if (!p) {
                 set_error("vroom .bin: codeword stream does not tile the list");
                 return DINT_E_FORMAT;
@@ -473,11 +469,15 @@ int dint_vroom_plan_create(const dint_dict* d, const void* bin_, size_t len, uin
                 }
                 const uint32_t acc0 = acc;
                 sb.begin_stream(p + 1, out_off + done, sel, acc, done == 0);
-                auto cut = [&](const uint8_t* qq, uint64_t i, uint32_t a, uint32_t sym, uint32_t ln) {
-                    sb.codeword(qq, out_off + done + i, a, i == size, sym, ln);
+                auto strip = [&](const uint8_t* qq, uint64_t i, uint32_t a, uint32_t cw, bool has_run) {
+                    sb.strip(qq, out_off + done + i, a, cw, has_run);
                 };
-                const uint8_t* q = sel < kSelectors ? wk.walk16(p + 1, sel, size, acc, cut)
-                                                    : wk.walk8(p + 1, sel - kSelectors, size, acc, cut);
+                auto each = [](const uint8_t*, uint64_t, uint32_t) {};
+                const uint8_t* q =
+                    sel < kSelectors
+                        ? wk.walk<2>(p + 1, sel, size, acc, sb.lim.strip_codewords, sb.lim.strip_ints, plan->cw_stats, strip, each)
+                        : wk.walk<1>(p + 1, sel - kSelectors, size, acc, sb.lim.strip_codewords, sb.lim.strip_ints,
+                                     plan->cw_stats, strip, each);
                 if (!q) {
                     set_error("vroom .bin: codeword stream does not tile the block");
                     return DINT_E_FORMAT;
