@@ -41,6 +41,12 @@ SYMBOLS = [
     "dint_decode_segments", "dint_decode_units", "dint_decode_index", "dint_checksum_lists", "dint_decode_list_host",
     "dint_vroom_ctx_create", "dint_vroom_ctx_destroy", "dint_vroom_ctx_device_output", "dint_vroom_decode_host",
     "dint_vroom_decode_resident", "dint_vroom_ctx_sync",
+    "dint_vroom_discover", "dint_index_discover", "dint_device_plan_destroy", "dint_device_plan_num_lists",
+    "dint_device_plan_num_ints", "dint_device_plan_num_units", "dint_device_plan_num_chains",
+    "dint_device_plan_num_sync_found", "dint_device_plan_retries", "dint_device_plan_discover_ms",
+    "dint_device_plan_units", "dint_device_plan_list_offsets", "dint_device_plan_list_byte_offsets",
+    "dint_decode_index_planned", "dint_vroom_ctx_create_discover", "dint_vroom_ctx_num_lists",
+    "dint_vroom_ctx_num_ints", "dint_vroom_ctx_device_plan", "dint_vroom_ctx_results",
 ]
 
 
@@ -109,6 +115,29 @@ def lib():
         L.dint_vroom_decode_host.argtypes = [vp, vp, sz, i32, vp, vp, vp]
         L.dint_vroom_decode_resident.argtypes = [vp, i32, vp]
         L.dint_vroom_ctx_sync.argtypes = [vp, vp]
+        L.dint_vroom_discover.argtypes = [vp, vp, sz, u32, vp, sz, u64, vp, C.POINTER(vp)]
+        L.dint_index_discover.argtypes = [vp, vp, vp, sz, vp, sz, u32, vp, C.POINTER(vp), C.POINTER(vp)]
+        L.dint_device_plan_destroy.argtypes = [vp]
+        L.dint_device_plan_destroy.restype = None
+        for f in ("num_lists", "num_ints", "num_units", "num_chains", "num_sync_found"):
+            getattr(L, "dint_device_plan_" + f).argtypes = [vp]
+            getattr(L, "dint_device_plan_" + f).restype = u64
+        L.dint_device_plan_retries.argtypes = [vp]
+        L.dint_device_plan_retries.restype = u32
+        L.dint_device_plan_discover_ms.argtypes = [vp]
+        L.dint_device_plan_discover_ms.restype = C.c_double
+        for f in ("units", "list_offsets", "list_byte_offsets"):
+            getattr(L, "dint_device_plan_" + f).argtypes = [vp]
+            getattr(L, "dint_device_plan_" + f).restype = vp
+        L.dint_decode_index_planned.argtypes = [vp, vp, vp, sz, vp, vp, vp, sz, u32, vp, vp, vp]
+        L.dint_vroom_ctx_create_discover.argtypes = [vp, vp, sz, u32, vp, sz, u64, vp, C.POINTER(vp)]
+        L.dint_vroom_ctx_num_lists.argtypes = [vp]
+        L.dint_vroom_ctx_num_lists.restype = u64
+        L.dint_vroom_ctx_num_ints.argtypes = [vp]
+        L.dint_vroom_ctx_num_ints.restype = u64
+        L.dint_vroom_ctx_device_plan.argtypes = [vp]
+        L.dint_vroom_ctx_device_plan.restype = vp
+        L.dint_vroom_ctx_results.argtypes = [vp, vp, vp, vp]
         _lib = L
     return _lib
 
@@ -218,6 +247,63 @@ class VroomPlan:
             pass
 
 
+NO_SYNC_SEARCH = 0xFFFFFFFFFFFFFFFF  # sync_stride: use only the caller's list starts
+
+
+def _sync_args(sync_offsets):
+    if sync_offsets is None or len(sync_offsets) == 0:
+        return None, 0, None
+    a = np.ascontiguousarray(sync_offsets, dtype=np.uint64)
+    return _np_ptr(a), len(a), a
+
+
+class DevicePlan:
+    """Strip table (+ list offsets) the GPU found itself; everything stays in HBM (dint_device_plan)."""
+
+    def __init__(self, handle, owned=True):
+        L = lib()
+        self.handle = handle
+        self.owned = owned
+        self.n_lists = L.dint_device_plan_num_lists(handle)
+        self.n_ints = L.dint_device_plan_num_ints(handle)
+        self.n_units = L.dint_device_plan_num_units(handle)
+        self.n_chains = L.dint_device_plan_num_chains(handle)
+        self.n_sync_found = L.dint_device_plan_num_sync_found(handle)
+        self.retries = L.dint_device_plan_retries(handle)
+        self.discover_ms = L.dint_device_plan_discover_ms(handle)
+        self.units_ptr = L.dint_device_plan_units(handle)
+        self.list_offsets_ptr = L.dint_device_plan_list_offsets(handle)
+        self.list_byte_offsets_ptr = L.dint_device_plan_list_byte_offsets(handle)
+
+    @classmethod
+    def discover_vroom(cls, dictionary, d_in_ptr, in_bytes, block_size=256, sync_offsets=None, sync_stride=0, stream=0):
+        """dint_vroom_discover: restart points of a vroom .bin that is already in HBM (no host plan)."""
+        h = C.c_void_p()
+        p, n, keep = _sync_args(sync_offsets)
+        check(lib().dint_vroom_discover(dictionary.handle, d_in_ptr, in_bytes, block_size, p, n, sync_stride, stream,
+                                        C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def discover_index(cls, docs_dict, freqs_dict, d_lists_ptr, lists_bytes, d_blocks_ptr, n_blocks, block_size=256, stream=0):
+        """dint_index_discover: (docs plan, freqs plan) for the full blocks of a frozen index"""
+        hd, hf = C.c_void_p(), C.c_void_p()
+        check(lib().dint_index_discover(docs_dict.handle, freqs_dict.handle, d_lists_ptr, lists_bytes, d_blocks_ptr, n_blocks,
+                                        block_size, stream, C.byref(hd), C.byref(hf)))
+        return cls(hd), cls(hf)
+
+    def close(self):
+        if getattr(self, "handle", None) and self.owned:
+            lib().dint_device_plan_destroy(self.handle)
+        self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class VroomHostDecoder:
     """Host-buffer batch decode of whole vroom .bin files that share one plan
     (vroom_env/decode.cpp:139-150 as one call): H2D, decode, checksums / output D2H."""
@@ -227,6 +313,31 @@ class VroomHostDecoder:
         h = C.c_void_p()
         check(lib().dint_vroom_ctx_create(plan.dictionary.handle, plan.handle, block_size, C.byref(h)))
         self.handle = h
+
+    @classmethod
+    def discover(cls, dictionary, h_bin_ptr, nbytes, block_size=256, sync_offsets=None, sync_stride=0, stream=0):
+        """cold path: no host plan — H2D of the file + device-side discovery (dint_vroom_ctx_create_discover)"""
+        self = cls.__new__(cls)
+        self.plan = None
+        self.dictionary = dictionary
+        h = C.c_void_p()
+        p, n, keep = _sync_args(sync_offsets)
+        check(lib().dint_vroom_ctx_create_discover(dictionary.handle, h_bin_ptr, nbytes, block_size, p, n, sync_stride,
+                                                   stream, C.byref(h)))
+        self.handle = h
+        self.device_plan = DevicePlan(lib().dint_vroom_ctx_device_plan(h), owned=False)
+        return self
+
+    @property
+    def n_lists(self):
+        return lib().dint_vroom_ctx_num_lists(self.handle)
+
+    @property
+    def n_ints(self):
+        return lib().dint_vroom_ctx_num_ints(self.handle)
+
+    def results(self, h_out_ptr=None, h_sums_ptr=None, stream=0):
+        check(lib().dint_vroom_ctx_results(self.handle, h_out_ptr, h_sums_ptr, stream))
 
     def decode(self, h_bin_ptr, nbytes, mode=MODE_RAW, h_out_ptr=None, h_sums_ptr=None, stream=0):
         check(lib().dint_vroom_decode_host(self.handle, h_bin_ptr, nbytes, mode, h_out_ptr, h_sums_ptr, stream))
@@ -300,6 +411,13 @@ def decode_index(docs_dict, freqs_dict, d_lists_ptr, lists_bytes, d_blocks_ptr, 
                  d_freqs_ptr, stream=0):
     check(lib().dint_decode_index(docs_dict.handle, freqs_dict.handle, d_lists_ptr, lists_bytes, d_blocks_ptr, n_blocks,
                                   block_size, d_docids_ptr, d_freqs_ptr, stream))
+
+
+def decode_index_planned(docs_dict, freqs_dict, d_lists_ptr, lists_bytes, docs_plan, freqs_plan, d_blocks_ptr, n_blocks,
+                         block_size, d_docids_ptr, d_freqs_ptr, stream=0):
+    check(lib().dint_decode_index_planned(docs_dict.handle, freqs_dict.handle, d_lists_ptr, lists_bytes, docs_plan.handle,
+                                          freqs_plan.handle, d_blocks_ptr, n_blocks, block_size, d_docids_ptr, d_freqs_ptr,
+                                          stream))
 
 
 def checksum_lists(d_values_ptr, d_list_offsets_ptr, n_lists, d_sums_ptr, stream=0):

@@ -1,0 +1,422 @@
+// dint_b200 — host side of the device-side discovery (dint_discover.cuh): picks the chains, runs the
+// count and emit passes, owns the resulting device-resident plan. Part of the C ABI (include/dint_b200.h).
+//
+// Replaces, for files that are already in HBM, the serial host walk of dint_vroom_plan_create: the only
+// host work left is O(chains) bookkeeping (a prefix sum over a few thousand chain totals).
+#include <algorithm>
+#include <memory>
+#include <vector>
+
+#include "dint_cuda_util.hpp"
+#include "dint_discover.cuh"
+
+using namespace dintk;
+
+namespace {
+
+struct dev_buf {  // cold-path scratch, freed on scope exit
+    void* p = nullptr;
+    ~dev_buf() {
+        if (p) cudaFree(p);
+    }
+    template <typename T>
+    T* as() const {
+        return static_cast<T*>(p);
+    }
+};
+
+uint32_t strip_shift_of(const dint::strip_limits& lim) {
+    // a strip also ends where the output crosses a multiple of 2^shift integers, so that a strip of run codewords
+    // (256 integers each) stays below unit_ints: (2^shift - 1) + 256 <= unit_ints
+    uint32_t s = 9;
+    while (s > 4 && (1u << s) + 255u > lim.unit_ints) --s;
+    return s;
+}
+
+size_t walk_smem(const dint_dict* d, int warps) {
+    dint_dict_view v = d->view();
+    return size_t(walk_tables_bytes(v)) + kWalkClassBytes + size_t(warps) * kWalkWarpSmem;
+}
+
+template <typename K>
+int walk_grid(K kernel, const dint_dict* d, int warps, uint64_t want_warps, int* grid, size_t* smem) {
+    device_info di;
+    int rc = get_device_info(d->device, &di);
+    if (rc) return rc;
+    *smem = walk_smem(d, warps);
+    if (*smem > size_t(di.max_smem_optin)) {
+        dint::set_error("discovery: length tables do not fit in shared memory");
+        return DINT_E_ARG;
+    }
+    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(*smem)));
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, warps * 32, *smem));
+    if (per_sm < 1) per_sm = 1;
+    const uint64_t want = (want_warps + warps - 1) / warps;
+    *grid = int(std::max<uint64_t>(1, std::min<uint64_t>(want, uint64_t(di.sms) * per_sm)));
+    return DINT_OK;
+}
+
+constexpr int kWalkWarps = 16;
+
+}  // namespace
+
+extern "C" {
+
+void dint_device_plan_destroy(dint_device_plan* p) {
+    if (!p) return;
+    {
+        device_guard g(p->device);
+        cudaFree(p->d_units);
+        cudaFree(p->d_list_offsets);
+        cudaFree(p->d_list_byte_offsets);
+    }
+    delete p;
+}
+uint64_t dint_device_plan_num_lists(const dint_device_plan* p) { return p ? p->n_lists : 0; }
+uint64_t dint_device_plan_num_ints(const dint_device_plan* p) { return p ? p->n_ints : 0; }
+uint64_t dint_device_plan_num_units(const dint_device_plan* p) { return p ? p->n_units : 0; }
+uint64_t dint_device_plan_num_chains(const dint_device_plan* p) { return p ? p->n_chains : 0; }
+uint64_t dint_device_plan_num_sync_found(const dint_device_plan* p) { return p ? p->n_sync_found : 0; }
+uint32_t dint_device_plan_retries(const dint_device_plan* p) { return p ? p->retries : 0; }
+double dint_device_plan_discover_ms(const dint_device_plan* p) { return p ? double(p->discover_ms) : 0.0; }
+const dint_strip_unit* dint_device_plan_units(const dint_device_plan* p) { return p ? p->d_units : nullptr; }
+const uint64_t* dint_device_plan_list_offsets(const dint_device_plan* p) { return p ? p->d_list_offsets : nullptr; }
+const uint64_t* dint_device_plan_list_byte_offsets(const dint_device_plan* p) { return p ? p->d_list_byte_offsets : nullptr; }
+
+int dint_vroom_discover(const dint_dict* d, const uint8_t* d_in, size_t in_bytes, uint32_t block_size,
+                        const uint64_t* sync_offsets, size_t n_sync, uint64_t sync_stride, void* stream,
+                        dint_device_plan** out) {
+    if (!d || !out || (!d_in && in_bytes) || (!sync_offsets && n_sync)) return DINT_E_ARG;
+    if (!d->d_rows || !d->d_sums) {
+        dint::set_error("dictionary is not device resident (no CPU fallback)");
+        return DINT_E_NODEVICE;
+    }
+    if (!block_size) block_size = dint::kDefaultBlock;
+    device_guard g(d->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    device_info di;
+    int rc = get_device_info(d->device, &di);
+    if (rc) return rc;
+    std::unique_ptr<dint_device_plan, void (*)(dint_device_plan*)> plan(new (std::nothrow) dint_device_plan, dint_device_plan_destroy);
+    if (!plan) return DINT_E_NOMEM;
+    plan->device = d->device;
+    plan->in_bytes = in_bytes;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    CUDA_TRY(cudaEventCreate(&ev0));
+    CUDA_TRY(cudaEventCreate(&ev1));
+    struct ev_guard {
+        cudaEvent_t a, b;
+        ~ev_guard() {
+            cudaEventDestroy(a);
+            cudaEventDestroy(b);
+        }
+    } evg{ev0, ev1};
+    CUDA_TRY(cudaEventRecord(ev0, st));
+    const dint::strip_limits& lim = dint::get_strip_limits();
+    const bool multi = d->kind == DINT_DICT_MULTI;
+
+    // ---- chain starts: byte 0, the caller's list starts, and what the speculative search finds ---------------
+    std::vector<uint64_t> sync;
+    try {
+        sync.push_back(0);
+        for (size_t i = 0; i < n_sync; ++i)
+            if (sync_offsets[i] > 0 && sync_offsets[i] < in_bytes) sync.push_back(sync_offsets[i]);
+        if (sync_stride != ~uint64_t(0) && in_bytes > 0) {
+            // default: about two chains per resident walking warp, never closer than 16 KB
+            uint64_t stride = sync_stride ? sync_stride : std::max<uint64_t>(16384, in_bytes / (uint64_t(di.sms) * 64));
+            stride = std::max<uint64_t>(stride, 1024);
+            const uint64_t n_targets = (in_bytes - 1) / stride;
+            if (n_targets) {
+                dev_buf found;
+                CUDA_TRY(cudaMalloc(&found.p, n_targets * 8));
+                find_sync_params F;
+                F.dv = d->view();
+                F.sums = d->d_sums;
+                F.in = d_in;
+                F.in_bytes = in_bytes;
+                F.block_size = block_size;
+                F.multi = multi;
+                F.stride = stride;
+                F.n_targets = n_targets;
+                F.window = uint32_t(std::min<uint64_t>(stride, 8192) & ~uint64_t(31));
+                F.depth = 3;
+                F.max_n = 4096;
+                F.found = found.as<uint64_t>();
+                const size_t smem = walk_smem(d, 0);
+                CUDA_TRY(cudaFuncSetAttribute(find_sync_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+                const int grid = int(std::max<uint64_t>(1, std::min<uint64_t>((n_targets + 7) / 8, uint64_t(di.sms) * 4)));
+                find_sync_kernel<<<grid, 256, smem, st>>>(F);
+                ++g_launches;
+                CUDA_TRY(cudaGetLastError());
+                std::vector<uint64_t> h(n_targets);
+                CUDA_TRY(cudaMemcpyAsync(h.data(), found.p, n_targets * 8, cudaMemcpyDeviceToHost, st));
+                CUDA_TRY(cudaStreamSynchronize(st));
+                for (uint64_t v : h)
+                    if (v != ~uint64_t(0) && v > 0 && v < in_bytes) {
+                        sync.push_back(v);
+                        ++plan->n_sync_found;
+                    }
+            }
+        }
+        std::sort(sync.begin(), sync.end());
+        sync.erase(std::unique(sync.begin(), sync.end()), sync.end());
+    } catch (const std::bad_alloc&) {
+        return DINT_E_NOMEM;
+    }
+
+    vroom_walk_params P;
+    P.dv = d->view();
+    P.sums = d->d_sums;
+    P.in = d_in;
+    P.in_bytes = in_bytes;
+    P.block_size = block_size;
+    P.multi = multi;
+    P.unit_ints = lim.unit_ints;
+    P.unit_bytes = lim.unit_bytes;
+    P.strip_cw = lim.strip_codewords;
+    P.strip_shift = strip_shift_of(lim);
+    P.units = nullptr;
+    P.units_cap = 0;
+    P.list_offsets = P.list_byte_offsets = nullptr;
+    P.bases = nullptr;
+
+    // ---- count pass (repeated while a sync point turns out not to be a list start) ----------------------------
+    dev_buf d_chain, d_counts, d_status;
+    std::vector<uint64_t> counts;
+    CUDA_TRY(cudaMalloc(&d_status.p, 16));
+    try {
+        for (uint32_t attempt = 0;; ++attempt) {
+            if (in_bytes == 0) sync.clear();
+            const uint64_t nc = sync.size();
+            std::vector<uint64_t> starts(sync);
+            starts.push_back(in_bytes);
+            counts.assign(nc * 4, 0);
+            if (nc == 0) break;
+            if (d_chain.p) cudaFree(d_chain.p), d_chain.p = nullptr;
+            if (d_counts.p) cudaFree(d_counts.p), d_counts.p = nullptr;
+            CUDA_TRY(cudaMalloc(&d_chain.p, (nc + 1) * 8));
+            CUDA_TRY(cudaMalloc(&d_counts.p, nc * 32));
+            CUDA_TRY(cudaMemcpyAsync(d_chain.p, starts.data(), (nc + 1) * 8, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaMemsetAsync(d_status.p, 0, 16, st));
+            P.chain_start = d_chain.as<uint64_t>();
+            P.n_chains = nc;
+            P.counts = d_counts.as<uint64_t>();
+            P.status = d_status.as<uint32_t>();
+            int grid = 0;
+            size_t smem = 0;
+            rc = walk_grid(vroom_walk_kernel<false>, d, kWalkWarps, nc, &grid, &smem);
+            if (rc) return rc;
+            vroom_walk_kernel<false><<<grid, kWalkWarps * 32, smem, st>>>(P);
+            ++g_launches;
+            CUDA_TRY(cudaGetLastError());
+            CUDA_TRY(cudaMemcpyAsync(counts.data(), d_counts.p, nc * 32, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            // a chain that starts at a true list start only ever stops at true list starts: walk the chains in file
+            // order, trusting a start only once its predecessor has landed on it
+            bool changed = false;
+            std::vector<uint64_t> good;
+            for (uint64_t i = 0; i < nc;) {
+                good.push_back(sync[i]);
+                const uint32_t status = uint32_t(counts[4 * i + 3] & 0xFF);
+                const uint64_t reached = counts[4 * i + 3] >> 8;
+                if (status == WALK_MALFORMED) {
+                    dint::set_error("vroom .bin: malformed list (device walk), chain at byte " + std::to_string(sync[i]));
+                    return DINT_E_FORMAT;
+                }
+                if (status == WALK_OK) {
+                    ++i;
+                    continue;
+                }
+                // overshoot: the sync points this chain ran over are not list starts; where it stopped is one
+                changed = true;
+                uint64_t j = i + 1;
+                while (j < nc && sync[j] < reached) ++j;
+                if (j < nc && sync[j] == reached) {  // it landed on a later sync point: that one is a list start
+                    i = j;
+                    continue;
+                }
+                // nothing is known about the points behind `reached` until a chain that starts there has run
+                if (reached < in_bytes) good.push_back(reached);
+                for (; j < nc; ++j) good.push_back(sync[j]);
+                break;
+            }
+            if (!changed) break;
+            if (attempt >= 16) {  // give up on speculation: one chain
+                good.assign(1, 0);
+            }
+            std::sort(good.begin(), good.end());
+            good.erase(std::unique(good.begin(), good.end()), good.end());
+            sync.swap(good);
+            ++plan->retries;
+        }
+        // ---- bases of every chain (host: a few thousand additions) ----------------------------------------------
+        const uint64_t nc = sync.size();
+        std::vector<uint64_t> bases(nc * 4 + 4, 0);
+        uint64_t lists = 0, ints = 0, units = 0;
+        for (uint64_t i = 0; i < nc; ++i) {
+            bases[4 * i] = lists;
+            bases[4 * i + 1] = ints;
+            bases[4 * i + 2] = units;
+            lists += counts[4 * i];
+            ints += counts[4 * i + 1];
+            units += counts[4 * i + 2];
+        }
+        plan->n_lists = lists;
+        plan->n_ints = ints;
+        plan->n_units = units;
+        plan->n_chains = nc;
+        CUDA_TRY(cudaMalloc(&plan->d_units, (units + 1) * sizeof(dint_strip_unit)));
+        CUDA_TRY(cudaMalloc(&plan->d_list_offsets, (lists + 1) * 8));
+        CUDA_TRY(cudaMalloc(&plan->d_list_byte_offsets, (lists + 1) * 8));
+        if (nc) {
+            dev_buf d_bases;
+            CUDA_TRY(cudaMalloc(&d_bases.p, nc * 32));
+            CUDA_TRY(cudaMemcpyAsync(d_bases.p, bases.data(), nc * 32, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaMemsetAsync(d_status.p, 0, 16, st));
+            P.bases = d_bases.as<uint64_t>();
+            P.units = plan->d_units;
+            P.units_cap = units;
+            P.list_offsets = plan->d_list_offsets;
+            P.list_byte_offsets = plan->d_list_byte_offsets;
+            int grid = 0;
+            size_t smem = 0;
+            rc = walk_grid(vroom_walk_kernel<true>, d, kWalkWarps, nc, &grid, &smem);
+            if (rc) return rc;
+            vroom_walk_kernel<true><<<grid, kWalkWarps * 32, smem, st>>>(P);
+            ++g_launches;
+            CUDA_TRY(cudaGetLastError());
+            uint32_t h_status = 0;
+            CUDA_TRY(cudaMemcpyAsync(&h_status, d_status.p, 4, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            if (h_status != WALK_OK) {
+                dint::set_error("vroom .bin: the emit pass of the device walk disagrees with the count pass");
+                return DINT_E_FORMAT;
+            }
+        }
+        const uint64_t tail[2] = {ints, uint64_t(in_bytes)};
+        CUDA_TRY(cudaMemcpyAsync(plan->d_list_offsets + lists, &tail[0], 8, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(plan->d_list_byte_offsets + lists, &tail[1], 8, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaEventRecord(ev1, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        CUDA_TRY(cudaEventElapsedTime(&plan->discover_ms, ev0, ev1));
+    } catch (const std::bad_alloc&) {
+        return DINT_E_NOMEM;
+    }
+    *out = plan.release();
+    return DINT_OK;
+}
+
+int dint_index_discover(const dint_dict* docs_dict, const dint_dict* freqs_dict, const uint8_t* d_lists, size_t lists_bytes,
+                        const dint_block* d_blocks, size_t n_blocks, uint32_t block_size, void* stream,
+                        dint_device_plan** docs_plan, dint_device_plan** freqs_plan) {
+    if (!docs_dict || !freqs_dict || !docs_plan || !freqs_plan) return DINT_E_ARG;
+    if (!docs_dict->d_rows || !freqs_dict->d_rows || !docs_dict->d_sums || !freqs_dict->d_sums) {
+        dint::set_error("dictionary is not device resident (no CPU fallback)");
+        return DINT_E_NODEVICE;
+    }
+    if (docs_dict->device != freqs_dict->device || docs_dict->kind != freqs_dict->kind) return DINT_E_ARG;
+    if (n_blocks && (!d_lists || !d_blocks || (reinterpret_cast<uintptr_t>(d_blocks) & 15))) return DINT_E_ARG;
+    if (!block_size) block_size = dint::kDefaultBlock;
+    device_guard g(docs_dict->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const dint::strip_limits& lim = dint::get_strip_limits();
+    if (block_size > lim.unit_ints) {
+        dint::set_error("index discovery: block_size exceeds the strip decoder's unit size");
+        return DINT_E_ARG;
+    }
+    using plan_ptr = std::unique_ptr<dint_device_plan, void (*)(dint_device_plan*)>;
+    plan_ptr plans[2] = {plan_ptr(new (std::nothrow) dint_device_plan, dint_device_plan_destroy),
+                         plan_ptr(new (std::nothrow) dint_device_plan, dint_device_plan_destroy)};
+    if (!plans[0] || !plans[1]) return DINT_E_NOMEM;
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    for (auto& e : ev) CUDA_TRY(cudaEventCreate(&e));
+    struct ev_guard {
+        cudaEvent_t* e;
+        ~ev_guard() {
+            for (int i = 0; i < 3; ++i) cudaEventDestroy(e[i]);
+        }
+    } evg{ev};
+    dev_buf d_docs_len, d_ctr;
+    CUDA_TRY(cudaMalloc(&d_docs_len.p, (n_blocks + 1) * 4));
+    CUDA_TRY(cudaMalloc(&d_ctr.p, 64));
+    CUDA_TRY(cudaMemsetAsync(d_ctr.p, 0, 64, st));
+    CUDA_TRY(cudaMemsetAsync(d_docs_len.p, 0, (n_blocks + 1) * 4, st));
+    const uint64_t n_groups = (n_blocks + kIndexGroup - 1) / kIndexGroup;
+    CUDA_TRY(cudaEventRecord(ev[0], st));
+    for (int pass = 0; pass < 2; ++pass) {
+        const dint_dict* d = pass ? freqs_dict : docs_dict;
+        dint_device_plan* plan = plans[pass].get();
+        plan->device = d->device;
+        plan->in_bytes = lists_bytes;
+        plan->n_chains = n_groups;
+        CUDA_TRY(cudaMalloc(&plan->d_units, (n_blocks + 1) * sizeof(dint_strip_unit)));
+        index_walk_params P;
+        P.dv = d->view();
+        P.sums = d->d_sums;
+        P.lists = d_lists;
+        P.lists_bytes = lists_bytes;
+        P.blocks = d_blocks;
+        P.n_blocks = n_blocks;
+        P.block_size = block_size;
+        P.multi = d->kind == DINT_DICT_MULTI;
+        P.docs_len = d_docs_len.as<uint32_t>();
+        P.units = plan->d_units;
+        P.units_cap = n_blocks;
+        P.counter = d_ctr.as<unsigned long long>() + pass;
+        P.status = d_ctr.as<uint32_t>() + 8 + pass;
+        P.unit_ints = lim.unit_ints;
+        P.unit_bytes = lim.unit_bytes;
+        P.strip_cw = lim.strip_codewords;
+        P.strip_shift = strip_shift_of(lim);
+        if (n_groups) {
+            int grid = 0;
+            size_t smem = 0;
+            int rc;
+            if (pass == 0) {
+                rc = walk_grid(index_walk_kernel<0>, d, kWalkWarps, n_groups, &grid, &smem);
+                if (rc) return rc;
+                index_walk_kernel<0><<<grid, kWalkWarps * 32, smem, st>>>(P);
+            } else {
+                rc = walk_grid(index_walk_kernel<1>, d, kWalkWarps, n_groups, &grid, &smem);
+                if (rc) return rc;
+                index_walk_kernel<1><<<grid, kWalkWarps * 32, smem, st>>>(P);
+            }
+            ++g_launches;
+            CUDA_TRY(cudaGetLastError());
+        }
+        CUDA_TRY(cudaEventRecord(ev[1 + pass], st));
+    }
+    uint64_t h[8] = {0};
+    CUDA_TRY(cudaMemcpyAsync(h, d_ctr.p, 64, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    const uint32_t* hs = reinterpret_cast<const uint32_t*>(h) + 8;
+    for (int pass = 0; pass < 2; ++pass) {
+        if (hs[pass] != WALK_OK) {
+            dint::set_error(std::string("index .bin: malformed ") + (pass ? "freqs" : "docs") + " block (device walk)");
+            return DINT_E_FORMAT;
+        }
+        dint_device_plan* plan = plans[pass].get();
+        plan->n_units = h[pass];
+        CUDA_TRY(cudaEventElapsedTime(&plan->discover_ms, ev[pass], ev[1 + pass]));
+        // the table was sized for one unit per block: give the slack back
+        if (plan->n_units + 1 < (n_blocks + 1) / 4 * 3) {
+            dint_strip_unit* tight = nullptr;
+            CUDA_TRY(cudaMalloc(&tight, (plan->n_units + 1) * sizeof(dint_strip_unit)));
+            cudaError_t e = cudaMemcpyAsync(tight, plan->d_units, plan->n_units * sizeof(dint_strip_unit), cudaMemcpyDeviceToDevice, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) {
+                cudaFree(tight);
+                dint::set_error(std::string("index discovery: ") + cudaGetErrorString(e));
+                return DINT_E_CUDA;
+            }
+            cudaFree(plan->d_units);
+            plan->d_units = tight;
+        }
+    }
+    *docs_plan = plans[0].release();
+    *freqs_plan = plans[1].release();
+    return DINT_OK;
+}
+
+}  // extern "C"

@@ -109,10 +109,19 @@ static int build_packed(dint_dict* d, const uint8_t* starts, uint32_t n_starts, 
         d->n_classes = n_starts;
         for (uint32_t c = 0; c < n_starts; ++c) {
             d->class_base[c] = rd32(starts + 4 * c);
-            if (d->class_base[c] > n_offsets) return DINT_E_FORMAT;
+            if (d->class_base[c] > n_offsets || (c && d->class_base[c] < d->class_base[c - 1])) {
+                set_error("multi dictionary: class start offsets are not monotone");
+                return DINT_E_FORMAT;
+            }
         }
-        for (uint32_t c = 0; c < n_starts; ++c)
+        for (uint32_t c = 0; c < n_starts; ++c) {
             d->class_size[c] = (c + 1 < n_starts ? d->class_base[c + 1] : n_offsets) - d->class_base[c];
+            // multi_dictionary.hpp:159-167: a class holds at most num_entries entries + its reserved slots
+            if (d->class_size[c] > kNumEntries + kReserved) {
+                set_error("multi dictionary: class larger than 65536 + 7 entries");
+                return DINT_E_FORMAT;
+            }
+        }
     } else {
         d->n_classes = 1;
         d->class_size[0] = n_offsets;
@@ -194,6 +203,19 @@ static int validate(dint_dict* d) {
                 return DINT_E_FORMAT;
             }
         }
+        if (d->h_lens[b] != 0 || d->h_lens[b + 1] != 0) {
+            set_error("dictionary: the exception codewords 0 and 1 must have length 1");
+            return DINT_E_FORMAT;
+        }
+        // every other entry is one of constants::target_sizes (dint_configuration.hpp:25): the device tables
+        // store log2(length), so anything else would decode differently from the reference
+        for (uint32_t i = kReserved; i < d->class_size[c]; ++i) {
+            const uint32_t len = uint32_t(d->h_lens[b + i]) + 1;
+            if (len > kEntry || (len & (len - 1)) != 0) {
+                set_error("dictionary: entry length is not one of 1, 2, 4, 8, 16");
+                return DINT_E_FORMAT;
+            }
+        }
     }
     return DINT_OK;
 }
@@ -221,6 +243,7 @@ static int dict_finish(dint_dict* d, int rc, int device, dint_dict** out) {
     }
     if (rc != DINT_OK) {
         if (rc == DINT_E_FORMAT && g_error.empty()) set_error("malformed dictionary");
+        dint_dict_release_device(d);  // a failed upload may have left some of the tables allocated
         delete d;
         return rc;
     }
@@ -234,7 +257,14 @@ int dint_dict_create(int kind, const void* file_bytes, size_t len, int device, d
     dint_dict* d = new (std::nothrow) dint_dict;
     if (!d) return DINT_E_NOMEM;
     d->kind = kind;
-    return dict_finish(d, parse_file(d, kind, static_cast<const uint8_t*>(file_bytes), len), device, out);
+    try {
+        return dict_finish(d, parse_file(d, kind, static_cast<const uint8_t*>(file_bytes), len), device, out);
+    } catch (const std::exception&) {  // bad_alloc / length_error from a corrupt size field: never through the C boundary
+        dint_dict_release_device(d);
+        delete d;
+        set_error("dictionary: out of memory");
+        return DINT_E_NOMEM;
+    }
 }
 
 int dint_dict_create_mapped(int kind, const void* bytes, size_t len, int device, dint_dict** out, size_t* consumed) {
@@ -243,7 +273,14 @@ int dint_dict_create_mapped(int kind, const void* bytes, size_t len, int device,
     dint_dict* d = new (std::nothrow) dint_dict;
     if (!d) return DINT_E_NOMEM;
     d->kind = kind;
-    return dict_finish(d, parse_mapped(d, kind, static_cast<const uint8_t*>(bytes), len, consumed), device, out);
+    try {
+        return dict_finish(d, parse_mapped(d, kind, static_cast<const uint8_t*>(bytes), len, consumed), device, out);
+    } catch (const std::exception&) {
+        dint_dict_release_device(d);
+        delete d;
+        set_error("dictionary: out of memory");
+        return DINT_E_NOMEM;
+    }
 }
 
 void dint_dict_destroy(dint_dict* d) {
@@ -399,8 +436,19 @@ struct strip_builder {
 
 extern "C" {
 
+static int vroom_plan_create_impl(const dint_dict* d, const void* bin_, size_t len, uint32_t block_size, uint32_t chunk_ints,
+                                  dint_vroom_plan** out);
 int dint_vroom_plan_create(const dint_dict* d, const void* bin_, size_t len, uint32_t block_size, uint32_t chunk_ints,
                            dint_vroom_plan** out) {
+    try {
+        return vroom_plan_create_impl(d, bin_, len, block_size, chunk_ints, out);
+    } catch (const std::exception&) {
+        set_error("vroom .bin: out of memory while building the plan");
+        return DINT_E_NOMEM;
+    }
+}
+static int vroom_plan_create_impl(const dint_dict* d, const void* bin_, size_t len, uint32_t block_size, uint32_t chunk_ints,
+                                  dint_vroom_plan** out) {
     if (!d || (!bin_ && len) || !out) return DINT_E_ARG;
     g_error.clear();
     if (!block_size) block_size = kDefaultBlock;
@@ -542,7 +590,16 @@ static inline uint64_t get_bits(const uint8_t* words, uint64_t pos, uint32_t len
     return len == 64 ? lo : lo & ((uint64_t(1) << len) - 1);
 }
 
+static int index_plan_create_impl(int kind, const void* bin_, size_t len, uint32_t block_size, dint_index_plan** out);
 int dint_index_plan_create(int kind, const void* bin_, size_t len, uint32_t block_size, dint_index_plan** out) {
+    try {
+        return index_plan_create_impl(kind, bin_, len, block_size, out);
+    } catch (const std::exception&) {
+        set_error("index .bin: out of memory while building the plan");
+        return DINT_E_NOMEM;
+    }
+}
+static int index_plan_create_impl(int kind, const void* bin_, size_t len, uint32_t block_size, dint_index_plan** out) {
     if (!bin_ || !out || kind < 0 || kind > 2) return DINT_E_ARG;
     g_error.clear();
     if (!block_size) block_size = kDefaultBlock;
@@ -590,6 +647,9 @@ int dint_index_plan_create(int kind, const void* bin_, size_t len, uint32_t bloc
     // Elias-Fano of the n_lists list start offsets, universe = m_lists.size()
     // (dict_freq_index.hpp:96-99; compact_elias_fano.hpp:14-61)
     const uint64_t n = plan->n_lists, universe = plan->lists_len;
+    // every list takes at least one byte of m_lists and one bit of the Elias-Fano vector: bound the (untrusted)
+    // count before anything is sized by it
+    if (n > universe || n > ef_bits) return bad("list count out of range");
     plan->endpoints.assign(n + 1, 0);
     if (n) {
         const uint64_t l = universe > n ? msb64(universe / n) : 0;
@@ -629,10 +689,12 @@ int dint_index_plan_create(int kind, const void* bin_, size_t len, uint32_t bloc
         const uint8_t* base = vbyte(data, lists_end, &ln);
         if (!base || !ln) return bad("bad list header");
         const uint64_t blocks = (uint64_t(ln) + block_size - 1) / block_size;
+        // offsets are compared as integers: a corrupt n must not move a pointer past the buffer first
+        const uint64_t tables = 4 * blocks + 4 * (blocks - 1);
+        if (tables > uint64_t(lists_end - base)) return bad("block tables out of range");
         const uint8_t* maxs = base;
         const uint8_t* eps = maxs + 4 * blocks;
         const uint8_t* blocks_data = eps + 4 * (blocks - 1);
-        if (blocks_data > lists_end) return bad("block tables out of range");
         plan->list_offsets[t] = postings;
         for (uint64_t b = 0; b < blocks; ++b) {
             dint_block blk;

@@ -5,6 +5,7 @@
 #include <cstddef>
 #include <cstdint>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -79,6 +80,7 @@ struct dint_dict {
     uint32_t* d_rows = nullptr;
     uint8_t* d_lens = nullptr;
     uint8_t* d_lens_cls = nullptr;
+    uint32_t* d_sums = nullptr;    // h_sums in HBM (device-side discovery: docID prefix of every strip)
     uint32_t lens_cls_off[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     uint32_t lut_rows = 0;
     uint8_t* d_strip_tables = nullptr;
@@ -86,6 +88,20 @@ struct dint_dict {
     uint32_t hot_rows = 0;
     uint32_t group_off[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     uint32_t detail_off[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    // launch shape of the strip decoder for this dictionary (set once by dint_dict_upload)
+    int strip_warps = 0, strip_sms = 0, strip_variant = -1;
+    size_t strip_smem = 0;
+    // device scratch of dint_decode_list_host (grown on demand, reused by every call)
+    struct host_scratch {
+        std::mutex mu;
+        uint8_t* d_in = nullptr;
+        size_t in_cap = 0;
+        uint32_t* d_out = nullptr;
+        size_t out_cap = 0;
+        uint64_t* d_cons = nullptr;
+        bool attr_set = false;
+    };
+    mutable host_scratch scratch;
     dint_dict_view view() const {
         dint_dict_view v;
         v.rows = d_rows;
@@ -125,6 +141,18 @@ struct dint_index_plan {
     std::vector<dint_block> blocks;
     std::vector<uint64_t> list_offsets;  // n_lists + 1 (postings)
     std::vector<uint64_t> endpoints;     // n_lists + 1 (bytes in m_lists)
+};
+
+// Strip table + list offsets found on the device (dint_discover.cu); everything lives in HBM.
+struct dint_device_plan {
+    int device = -1;
+    uint64_t n_lists = 0, n_ints = 0, n_units = 0, n_chains = 0, in_bytes = 0;
+    dint_strip_unit* d_units = nullptr;
+    uint64_t* d_list_offsets = nullptr;       // n_lists + 1 (vroom plans only)
+    uint64_t* d_list_byte_offsets = nullptr;  // n_lists + 1 (vroom plans only)
+    float discover_ms = 0.f;                  // device timeline of the discovery (CUDA events)
+    uint32_t retries = 0;                     // count passes repeated because a speculative sync point was wrong
+    uint64_t n_sync_found = 0;                // sync points the speculative search contributed
 };
 
 // implemented in dint_kernels.cu

@@ -17,9 +17,14 @@
 #include <mutex>
 #include <string>
 
+#include "dint_cuda_util.hpp"
 #include "dint_decoder.cuh"
 #include "dint_strips.cuh"
 #include "dint_internal.hpp"
+
+namespace dintk {
+std::atomic<uint64_t> g_launches{0};
+}
 
 namespace {
 
@@ -28,17 +33,6 @@ using namespace dintk;
 constexpr int kWarpsPerCta = 16;
 constexpr int kThreads = kWarpsPerCta * 32;
 constexpr uint32_t kImplicitUnit = 8;  // segments per work unit when the caller passes no unit table
-
-std::atomic<uint64_t> g_launches{0};
-
-#define CUDA_TRY(expr)                                                                    \
-    do {                                                                                  \
-        cudaError_t e__ = (expr);                                                         \
-        if (e__ != cudaSuccess) {                                                         \
-            dint::set_error(std::string(#expr) + ": " + cudaGetErrorString(e__));         \
-            return DINT_E_CUDA;                                                           \
-        }                                                                                 \
-    } while (0)
 
 extern __shared__ __align__(16) uint8_t g_smem[];
 
@@ -96,8 +90,8 @@ decode_units_kernel(dint_dict_view dv, uint32_t lut_bytes, const uint8_t* __rest
     const class_info* classes = cta_setup(dv, lut_bytes, in, in_bytes, out, ws);
     const unsigned lane = lane_id();
     const uint64_t in_base = reinterpret_cast<uint64_t>(in);
-    const uint64_t gwarp = uint64_t(blockIdx.x) * W + (threadIdx.x >> 5);
-    const uint64_t nwarps = uint64_t(gridDim.x) * W;
+    const uint64_t gwarp = uint64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint64_t nwarps = uint64_t(gridDim.x) * (blockDim.x >> 5);
     for (uint64_t u = gwarp; u < n_units; u += nwarps) {
         uint64_t s0, s1;
         if (unit_first) {
@@ -208,8 +202,8 @@ index_docs_kernel(dint_dict_view dv, uint32_t lut_bytes, int multi, const uint8_
     const class_info* classes = cta_setup(dv, lut_bytes, lists, lists_bytes, docids, ws);
     const unsigned lane = lane_id();
     const uint64_t base = reinterpret_cast<uint64_t>(lists);
-    const uint64_t gwarp = uint64_t(blockIdx.x) * kWarpsPerCta + (threadIdx.x >> 5);
-    const uint64_t nwarps = uint64_t(gridDim.x) * kWarpsPerCta;
+    const uint64_t gwarp = uint64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint64_t nwarps = uint64_t(gridDim.x) * (blockDim.x >> 5);
     for (uint64_t i = gwarp; i < n_blocks; i += nwarps) {
         const dint_block b = blocks[i];
         if (b.size != block_size) continue;  // partial block: interpolative, index_tails_kernel
@@ -235,8 +229,8 @@ index_freqs_kernel(dint_dict_view dv, uint32_t lut_bytes, int multi, const uint8
     const class_info* classes = cta_setup(dv, lut_bytes, lists, lists_bytes, freqs, ws);
     const unsigned lane = lane_id();
     const uint64_t base = reinterpret_cast<uint64_t>(lists);
-    const uint64_t gwarp = uint64_t(blockIdx.x) * kWarpsPerCta + (threadIdx.x >> 5);
-    const uint64_t nwarps = uint64_t(gridDim.x) * kWarpsPerCta;
+    const uint64_t gwarp = uint64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint64_t nwarps = uint64_t(gridDim.x) * (blockDim.x >> 5);
     for (uint64_t i = gwarp; i < n_blocks; i += nwarps) {
         const dint_block b = blocks[i];
         if (b.size != block_size) continue;
@@ -501,12 +495,9 @@ decode_list_kernel(dint_dict_view dv, uint32_t lut_bytes, int multi, const uint8
 }
 
 // ---- launch helpers -------------------------------------------------------------------------
-struct device_info {
-    int sms = 0;
-    int max_smem_optin = 0;
-};
+}  // namespace
 
-int get_device_info(int device, device_info* di) {
+int dintk::get_device_info(int device, device_info* di) {
     static std::mutex mu;
     static device_info cache[64];
     static bool have[64] = {false};
@@ -521,28 +512,33 @@ int get_device_info(int device, device_info* di) {
     return DINT_OK;
 }
 
+namespace {
+
 // 4-bit log2(length) per dictionary row, padded to 16 bytes
 uint32_t lut_bytes_of(const dint_dict* d) { return ((d->n_rows + 1u) / 2u + 15u) & ~15u; }
 size_t smem_bytes_of(const dint_dict* d, int warps) {
     return size_t(lut_bytes_of(d)) + kClassBytes + size_t(warps) * kWarpSmem;
 }
 
-// persistent grid: as many CTAs as fit (shared memory bound), never more than the work needs
+// persistent grid: as many CTAs as fit (shared memory bound), never more than the work needs. A dictionary whose
+// 4-bit length table leaves no room for `warps` rings gets a smaller CTA (*warps is lowered; the kernels take
+// their warp count from blockDim), down to one warp.
 template <typename K>
-int plan_grid(K kernel, const dint_dict* d, uint64_t n_units, int* grid, size_t* smem, int warps = kWarpsPerCta) {
+int plan_grid(K kernel, const dint_dict* d, uint64_t n_units, int* grid, size_t* smem, int* warps) {
     device_info di;
     int rc = get_device_info(d->device, &di);
     if (rc) return rc;
-    *smem = smem_bytes_of(d, warps);
+    while (*warps > 1 && smem_bytes_of(d, *warps) > size_t(di.max_smem_optin)) --*warps;
+    *smem = smem_bytes_of(d, *warps);
     if (*smem > size_t(di.max_smem_optin)) {
         dint::set_error("dictionary length table does not fit in shared memory");
         return DINT_E_ARG;
     }
     CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(*smem)));
     int per_sm = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, warps * 32, *smem));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, *warps * 32, *smem));
     if (per_sm < 1) per_sm = 1;
-    uint64_t want = (n_units + warps - 1) / warps;
+    uint64_t want = (n_units + *warps - 1) / *warps;
     uint64_t cap = uint64_t(di.sms) * per_sm;
     *grid = int(std::max<uint64_t>(1, std::min(want, cap)));
     return DINT_OK;
@@ -553,18 +549,11 @@ uint32_t env_u32_k(const char* name, uint32_t dflt) {
     return v && *v ? uint32_t(std::strtoul(v, nullptr, 10)) : dflt;
 }
 
-struct device_guard {
-    int prev = -1;
-    bool ok = false;
-    explicit device_guard(int dev) {
-        if (cudaGetDevice(&prev) == cudaSuccess && cudaSetDevice(dev) == cudaSuccess) ok = true;
-    }
-    ~device_guard() {
-        if (prev >= 0) cudaSetDevice(prev);
-    }
-};
-
 }  // namespace
+
+extern "C" {
+static int strip_launch_setup(dint_dict* d);
+}
 
 // ---- dictionary upload ------------------------------------------------------------------------
 int dint_dict_upload(dint_dict* d) {
@@ -616,6 +605,8 @@ int dint_dict_upload(dint_dict* d) {
         }
     CUDA_TRY(cudaMalloc(&d->d_lens_cls, lut_cls.size()));
     CUDA_TRY(cudaMemcpy(d->d_lens_cls, lut_cls.data(), lut_cls.size(), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&d->d_sums, size_t(d->n_rows) * 4 + 16));
+    CUDA_TRY(cudaMemcpy(d->d_sums, d->h_sums.data(), size_t(d->n_rows) * 4, cudaMemcpyHostToDevice));
     // shared-memory image of the lane-sequential decoder (dint_dict_view::strip_tables). A multi dictionary
     // keeps the 256 rows of every class that u8 codewords can address (they are also the most frequent
     // ones, the builder sorts by frequency); a single dictionary keeps its first 2048 rows.
@@ -685,16 +676,26 @@ int dint_dict_upload(dint_dict* d) {
         CUDA_TRY(cudaMalloc(&d->d_strip_tables, total));
         CUDA_TRY(cudaMemcpy(d->d_strip_tables, img.data(), total, cudaMemcpyHostToDevice));
     }
-    return DINT_OK;
+    return strip_launch_setup(d);
 }
 
 void dint_dict_release_device(dint_dict* d) {
-    if (d->d_rows || d->d_lens || d->d_lens_cls || d->d_strip_tables) {
+    if (d->d_rows || d->d_lens || d->d_lens_cls || d->d_strip_tables || d->d_sums || d->scratch.d_in || d->scratch.d_out ||
+        d->scratch.d_cons) {
         device_guard g(d->device);
         cudaFree(d->d_rows);
         cudaFree(d->d_lens);
         cudaFree(d->d_lens_cls);
         cudaFree(d->d_strip_tables);
+        cudaFree(d->d_sums);
+        cudaFree(d->scratch.d_in);
+        cudaFree(d->scratch.d_out);
+        cudaFree(d->scratch.d_cons);
+        d->scratch.d_in = nullptr;
+        d->scratch.d_out = nullptr;
+        d->scratch.d_cons = nullptr;
+        d->scratch.in_cap = d->scratch.out_cap = 0;
+        d->d_sums = nullptr;
         d->d_strip_tables = nullptr;
         d->d_rows = nullptr;
         d->d_lens = nullptr;
@@ -736,16 +737,17 @@ int dint_decode_units(const dint_dict* d, const uint8_t* d_in, size_t in_bytes, 
     device_guard g(d->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool multi = d->kind == DINT_DICT_MULTI;
-    int grid = 0;
+    int grid = 0, warps = 0;
     size_t smem = 0;
     int rc;
     // single dictionaries: 32 KB table, two 16-warp CTAs per SM; multi_packed: ~70 KB table shared by
     // one 32-warp CTA per SM
 #define LAUNCH_SEG(MU, M, W)                                                                                       \
-    rc = plan_grid(decode_units_kernel<MU, M, W>, d, n_units, &grid, &smem, W);                                    \
+    warps = W;                                                                                                     \
+    rc = plan_grid(decode_units_kernel<MU, M, W>, d, n_units, &grid, &smem, &warps);                               \
     if (rc) return rc;                                                                                             \
-    decode_units_kernel<MU, M, W><<<grid, W * 32, smem, st>>>(d->view(), lut_bytes_of(d), d_in, in_bytes, d_segs,    \
-                                                             n_segs, d_unit_first, n_units, d_out);
+    decode_units_kernel<MU, M, W><<<grid, warps * 32, smem, st>>>(d->view(), lut_bytes_of(d), d_in, in_bytes, d_segs, \
+                                                                 n_segs, d_unit_first, n_units, d_out);
     if (multi) {
         if (mode == DINT_MODE_RAW) { LAUNCH_SEG(true, OUT_RAW, 32) }
         else if (mode == DINT_MODE_DOCIDS) { LAUNCH_SEG(true, OUT_DOCIDS, 32) }
@@ -761,6 +763,46 @@ int dint_decode_units(const dint_dict* d, const uint8_t* d_in, size_t in_bytes, 
     return DINT_OK;
 }
 
+// Launch shape of the strip decoder for one dictionary: computed once, when the dictionary is uploaded
+// (dint_dict_upload), so that the decode call itself does no getenv / cudaFuncSetAttribute work.
+static int strip_launch_setup(dint_dict* d) {
+    device_info di;
+    int rc = get_device_info(d->device, &di);
+    if (rc) return rc;
+    const dint::strip_limits& lim = dint::get_strip_limits();
+    // one persistent CTA per SM: as many warps as the shared-memory budget holds next to the length table
+    // (all of the 227 KB a CTA may have: the 24th warp is worth more than the L1 left for the colder dictionary rows)
+    const size_t fixed = size_t(d->strip_tables_bytes) + kStripClassBytes;
+    const size_t per_warp = strip_warp_smem(lim.unit_ints, lim.unit_bytes);
+    const size_t budget = std::min(size_t(env_u32_k("DINT_B200_STRIP_SMEM_KB", 227)) * 1024, size_t(di.max_smem_optin));
+    d->strip_warps = 0;
+    if (fixed + per_warp > budget) return DINT_OK;  // reported by dint_decode_strips
+    const uint32_t max_warps = std::min(24u, std::max(1u, env_u32_k("DINT_B200_STRIP_WARPS", 24)));
+    d->strip_warps = int(std::min<size_t>((budget - fixed) / per_warp, max_warps));
+    d->strip_smem = fixed + size_t(d->strip_warps) * per_warp;
+    d->strip_sms = di.sms;
+    const char* v = std::getenv("DINT_B200_STRIP_VARIANT");
+    d->strip_variant = v && *v ? int(std::strtoul(v, nullptr, 10)) & 3 : -1;
+    // opt every instance in to the device's maximum once per device
+    static std::mutex mu;
+    static bool done[64] = {false};
+    std::lock_guard<std::mutex> lk(mu);
+    if (!done[d->device]) {
+        const int mx = di.max_smem_optin;
+#define OPT_IN(M)                                                                                              \
+    CUDA_TRY(cudaFuncSetAttribute(decode_strips_kernel<M, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx)); \
+    CUDA_TRY(cudaFuncSetAttribute(decode_strips_kernel<M, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx)); \
+    CUDA_TRY(cudaFuncSetAttribute(decode_strips_kernel<M, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx)); \
+    CUDA_TRY(cudaFuncSetAttribute(decode_strips_kernel<M, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+        OPT_IN(OUT_RAW)
+        OPT_IN(OUT_DOCIDS)
+        OPT_IN(OUT_FREQS)
+#undef OPT_IN
+        done[d->device] = true;
+    }
+    return DINT_OK;
+}
+
 int dint_decode_strips(const dint_dict* d, const uint8_t* d_in, size_t in_bytes, const dint_strip_unit* d_units,
                        size_t n_units, uint32_t* d_out, int mode, void* stream) {
     if (!d || mode < DINT_MODE_RAW || mode > DINT_MODE_FREQS) return DINT_E_ARG;
@@ -770,11 +812,12 @@ int dint_decode_strips(const dint_dict* d, const uint8_t* d_in, size_t in_bytes,
     }
     if (n_units == 0) return DINT_OK;
     if (!d_in || !d_units || !d_out || (reinterpret_cast<uintptr_t>(d_units) & 15)) return DINT_E_ARG;
+    if (d->strip_warps < 1) {
+        dint::set_error("strip decoder: shared-memory budget too small for one warp");
+        return DINT_E_ARG;
+    }
     device_guard g(d->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    device_info di;
-    int rc = get_device_info(d->device, &di);
-    if (rc) return rc;
     const dint::strip_limits& lim = dint::get_strip_limits();
     strip_params P;
     P.dv = d->view();
@@ -788,35 +831,12 @@ int dint_decode_strips(const dint_dict* d, const uint8_t* d_in, size_t in_bytes,
     P.image_words = strip_image_words(lim.unit_ints);
     P.bits_words = strip_bits_words(lim.unit_ints);
     P.inbuf_bytes = strip_inbuf_bytes(lim.unit_bytes);
-    // one persistent CTA per SM: as many warps as the shared-memory budget holds next to the length table
-    // (all of the 227 KB a CTA may have: the 24th warp is worth more than the L1 left for the colder dictionary rows)
-    const size_t fixed = size_t(P.dv.strip_tables_bytes) + kStripClassBytes;
-    const size_t per_warp = strip_warp_smem(lim.unit_ints, lim.unit_bytes);
-    static const uint32_t budget_kb = [] {
-        const char* v = std::getenv("DINT_B200_STRIP_SMEM_KB");
-        return v && *v ? uint32_t(std::strtoul(v, nullptr, 10)) : 227u;
-    }();
-    const size_t budget = std::min(size_t(budget_kb) * 1024, size_t(di.max_smem_optin));
-    if (fixed + per_warp > budget) {
-        dint::set_error("strip decoder: shared-memory budget too small for one warp");
-        return DINT_E_ARG;
-    }
-    static const uint32_t max_warps = [] {
-        const char* v = std::getenv("DINT_B200_STRIP_WARPS");
-        return v && *v ? std::min(24u, std::max(1u, uint32_t(std::strtoul(v, nullptr, 10)))) : 24u;
-    }();
-    int warps = int(std::min<size_t>((budget - fixed) / per_warp, max_warps));
-    const size_t smem = fixed + size_t(warps) * per_warp;
-    const int grid = int(std::max<uint64_t>(1, std::min<uint64_t>((n_units + warps - 1) / warps, uint64_t(di.sms))));
+    const int warps = d->strip_warps;
+    const size_t smem = d->strip_smem;
+    const int grid = int(std::max<uint64_t>(1, std::min<uint64_t>((n_units + warps - 1) / warps, uint64_t(d->strip_sms))));
     // kernel variant (see decode_strips_kernel): d-gap streams 0, frequency streams 3; DINT_B200_STRIP_VARIANT overrides
-    static const int forced = [] {
-        const char* v = std::getenv("DINT_B200_STRIP_VARIANT");
-        return v && *v ? int(std::strtoul(v, nullptr, 10)) & 3 : -1;
-    }();
-    const int variant = forced >= 0 ? forced : (mode == DINT_MODE_FREQS ? 3 : 0);
-#define LAUNCH_STRIPS_V(M, V)                                                                                   \
-    CUDA_TRY(cudaFuncSetAttribute(decode_strips_kernel<M, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))); \
-    decode_strips_kernel<M, V><<<grid, warps * 32, smem, st>>>(P);
+    const int variant = d->strip_variant >= 0 ? d->strip_variant : (mode == DINT_MODE_FREQS ? 3 : 0);
+#define LAUNCH_STRIPS_V(M, V) decode_strips_kernel<M, V><<<grid, warps * 32, smem, st>>>(P);
 #define LAUNCH_STRIPS(M)                                                                   \
     if (variant == 0) { LAUNCH_STRIPS_V(M, 0) } else if (variant == 1) { LAUNCH_STRIPS_V(M, 1) } \
     else if (variant == 2) { LAUNCH_STRIPS_V(M, 2) } else { LAUNCH_STRIPS_V(M, 3) }
@@ -832,8 +852,33 @@ int dint_decode_strips(const dint_dict* d, const uint8_t* d_in, size_t in_bytes,
 
 int dint_decode_segments(const dint_dict* d, const uint8_t* d_in, size_t in_bytes, const dint_segment* d_segs,
                          size_t n_segs, uint32_t block_size, uint32_t* d_out, int mode, void* stream) {
-    (void)block_size;
+    // Every segment of a multi_packed list already IS one block (the plan cut it with this block size), so the
+    // value only has to be sane: a segment never holds more integers than a block.
+    if (block_size > 65536u) {
+        dint::set_error("dint_decode_segments: block_size out of range");
+        return DINT_E_ARG;
+    }
     return dint_decode_units(d, d_in, in_bytes, d_segs, n_segs, nullptr, 0, d_out, mode, stream);
+}
+
+static int launch_index_tails(int device, const uint8_t* d_lists, size_t lists_bytes, const dint_block* d_blocks,
+                              size_t n_blocks, uint32_t block_size, uint32_t* d_docids, uint32_t* d_freqs, cudaStream_t st) {
+    device_info di;
+    int rc = get_device_info(device, &di);
+    if (rc) return rc;
+    uint64_t want = (n_blocks + kTailThreads - 1) / kTailThreads;
+    int tgrid = int(std::max<uint64_t>(1, std::min<uint64_t>(want, uint64_t(di.sms) * 16)));
+    index_tails_kernel<<<tgrid, kTailThreads, 0, st>>>(d_lists, lists_bytes, d_blocks, n_blocks, block_size, d_docids, d_freqs);
+    ++g_launches;
+    CUDA_TRY(cudaGetLastError());
+    return DINT_OK;
+}
+
+// the tile decoder's staging ring and the tail kernel's explicit stack are sized for blocks of up to 256 postings
+static bool index_block_size_ok(uint32_t block_size) {
+    if (block_size >= 1 && block_size <= 256) return true;
+    dint::set_error("dint_decode_index: block_size must be in 1..256");
+    return false;
 }
 
 int dint_decode_index(const dint_dict* docs_dict, const dint_dict* freqs_dict, const uint8_t* d_lists,
@@ -848,46 +893,65 @@ int dint_decode_index(const dint_dict* docs_dict, const dint_dict* freqs_dict, c
     if (n_blocks == 0) return DINT_OK;
     if (!d_lists || !d_blocks || (!d_docids && !d_freqs)) return DINT_E_ARG;
     if (!block_size) block_size = dint::kDefaultBlock;
+    if (!index_block_size_ok(block_size)) return DINT_E_ARG;
     device_guard g(docs_dict->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int multi = docs_dict->kind == DINT_DICT_MULTI;
-    int grid = 0;
+    int grid = 0, warps = kWarpsPerCta;
     size_t smem = 0;
     int rc;
     if (d_docids) {
-        rc = plan_grid(index_docs_kernel<OUT_DOCIDS>, docs_dict, n_blocks, &grid, &smem);
+        rc = plan_grid(index_docs_kernel<OUT_DOCIDS>, docs_dict, n_blocks, &grid, &smem, &warps);
         if (rc) return rc;
-        index_docs_kernel<OUT_DOCIDS><<<grid, kThreads, smem, st>>>(docs_dict->view(), lut_bytes_of(docs_dict), multi,
-                                                                   d_lists, lists_bytes, d_blocks, n_blocks, block_size,
-                                                                   d_docids, d_freqs);
+        index_docs_kernel<OUT_DOCIDS><<<grid, warps * 32, smem, st>>>(docs_dict->view(), lut_bytes_of(docs_dict), multi,
+                                                                     d_lists, lists_bytes, d_blocks, n_blocks, block_size,
+                                                                     d_docids, d_freqs);
     } else {
-        rc = plan_grid(index_docs_kernel<OUT_SKIP>, docs_dict, n_blocks, &grid, &smem);
+        rc = plan_grid(index_docs_kernel<OUT_SKIP>, docs_dict, n_blocks, &grid, &smem, &warps);
         if (rc) return rc;
-        index_docs_kernel<OUT_SKIP><<<grid, kThreads, smem, st>>>(docs_dict->view(), lut_bytes_of(docs_dict), multi,
-                                                                 d_lists, lists_bytes, d_blocks, n_blocks, block_size,
-                                                                 nullptr, d_freqs);
+        index_docs_kernel<OUT_SKIP><<<grid, warps * 32, smem, st>>>(docs_dict->view(), lut_bytes_of(docs_dict), multi,
+                                                                   d_lists, lists_bytes, d_blocks, n_blocks, block_size,
+                                                                   nullptr, d_freqs);
     }
     ++g_launches;
     CUDA_TRY(cudaGetLastError());
     if (d_freqs) {
-        rc = plan_grid(index_freqs_kernel, freqs_dict, n_blocks, &grid, &smem);
+        warps = kWarpsPerCta;
+        rc = plan_grid(index_freqs_kernel, freqs_dict, n_blocks, &grid, &smem, &warps);
         if (rc) return rc;
-        index_freqs_kernel<<<grid, kThreads, smem, st>>>(freqs_dict->view(), lut_bytes_of(freqs_dict), multi, d_lists,
-                                                         lists_bytes, d_blocks, n_blocks, block_size, d_freqs);
+        index_freqs_kernel<<<grid, warps * 32, smem, st>>>(freqs_dict->view(), lut_bytes_of(freqs_dict), multi, d_lists,
+                                                          lists_bytes, d_blocks, n_blocks, block_size, d_freqs);
         ++g_launches;
         CUDA_TRY(cudaGetLastError());
     }
-    {
-        device_info di;
-        rc = get_device_info(docs_dict->device, &di);
+    return launch_index_tails(docs_dict->device, d_lists, lists_bytes, d_blocks, n_blocks, block_size, d_docids, d_freqs, st);
+}
+
+int dint_decode_index_planned(const dint_dict* docs_dict, const dint_dict* freqs_dict, const uint8_t* d_lists,
+                              size_t lists_bytes, const dint_device_plan* docs_plan, const dint_device_plan* freqs_plan,
+                              const dint_block* d_blocks, size_t n_blocks, uint32_t block_size, uint32_t* d_docids,
+                              uint32_t* d_freqs, void* stream) {
+    if (!docs_dict || !freqs_dict || !docs_plan || !freqs_plan) return DINT_E_ARG;
+    if (n_blocks == 0) return DINT_OK;
+    if (!d_lists || !d_blocks || (!d_docids && !d_freqs)) return DINT_E_ARG;
+    if (!block_size) block_size = dint::kDefaultBlock;
+    if (!index_block_size_ok(block_size)) return DINT_E_ARG;
+    int rc;
+    // full blocks: the lane-sequential decoder over the strip tables dint_index_discover built
+    if (d_docids && docs_plan->n_units) {
+        rc = dint_decode_strips(docs_dict, d_lists, lists_bytes, docs_plan->d_units, docs_plan->n_units, d_docids,
+                                DINT_MODE_DOCIDS, stream);
         if (rc) return rc;
-        uint64_t want = (n_blocks + 127) / 128;
-        int tgrid = int(std::max<uint64_t>(1, std::min<uint64_t>(want, uint64_t(di.sms) * 16)));
-        index_tails_kernel<<<tgrid, 128, 0, st>>>(d_lists, lists_bytes, d_blocks, n_blocks, block_size, d_docids, d_freqs);
-        ++g_launches;
-        CUDA_TRY(cudaGetLastError());
     }
-    return DINT_OK;
+    if (d_freqs && freqs_plan->n_units) {
+        rc = dint_decode_strips(freqs_dict, d_lists, lists_bytes, freqs_plan->d_units, freqs_plan->n_units, d_freqs,
+                                DINT_MODE_FREQS, stream);
+        if (rc) return rc;
+    }
+    // partial blocks: interpolative
+    device_guard g(docs_dict->device);
+    return launch_index_tails(docs_dict->device, d_lists, lists_bytes, d_blocks, n_blocks, block_size, d_docids, d_freqs,
+                              static_cast<cudaStream_t>(stream));
 }
 
 int dint_checksum_lists(const uint32_t* d_values, const uint64_t* d_list_offsets, size_t n_lists, uint64_t* d_sums,
@@ -916,10 +980,14 @@ struct dint_vroom_ctx {
     uint32_t block_size = 0;
     uint64_t n_lists = 0, n_ints = 0, n_units = 0, in_bytes = 0;
     uint8_t* d_in = nullptr;
-    dint_strip_unit* d_units = nullptr;
-    uint64_t* d_list_offsets = nullptr;
+    const dint_strip_unit* d_units = nullptr;
+    const uint64_t* d_list_offsets = nullptr;
     uint32_t* d_out = nullptr;
     uint64_t* d_sums = nullptr;
+    // exactly one of the two owns the tables above
+    dint_strip_unit* own_units = nullptr;
+    uint64_t* own_list_offsets = nullptr;
+    dint_device_plan* plan = nullptr;  // dint_vroom_ctx_create_discover
 };
 
 int dint_vroom_ctx_create(const dint_dict* d, const dint_vroom_plan* plan, uint32_t block_size, dint_vroom_ctx** out) {
@@ -944,32 +1012,88 @@ int dint_vroom_ctx_create(const dint_dict* d, const dint_vroom_plan* plan, uint3
     };
     cudaError_t e;
     if ((e = cudaMalloc(&c->d_in, c->in_bytes + 16)) != cudaSuccess) return fail(e);
-    if ((e = cudaMalloc(&c->d_units, (c->n_units + 1) * sizeof(dint_strip_unit))) != cudaSuccess) return fail(e);
-    if ((e = cudaMalloc(&c->d_list_offsets, (c->n_lists + 1) * 8)) != cudaSuccess) return fail(e);
+    if ((e = cudaMalloc(&c->own_units, (c->n_units + 1) * sizeof(dint_strip_unit))) != cudaSuccess) return fail(e);
+    if ((e = cudaMalloc(&c->own_list_offsets, (c->n_lists + 1) * 8)) != cudaSuccess) return fail(e);
     if ((e = cudaMalloc(&c->d_out, (c->n_ints + 1) * 4)) != cudaSuccess) return fail(e);
     if ((e = cudaMalloc(&c->d_sums, (c->n_lists + 1) * 8)) != cudaSuccess) return fail(e);
-    if (c->n_units && (e = cudaMemcpy(c->d_units, plan->strip_units.data(), c->n_units * sizeof(dint_strip_unit),
+    if (c->n_units && (e = cudaMemcpy(c->own_units, plan->strip_units.data(), c->n_units * sizeof(dint_strip_unit),
                                       cudaMemcpyHostToDevice)) != cudaSuccess)
         return fail(e);
-    if ((e = cudaMemcpy(c->d_list_offsets, plan->list_offsets.data(), (c->n_lists + 1) * 8, cudaMemcpyHostToDevice)) !=
+    if ((e = cudaMemcpy(c->own_list_offsets, plan->list_offsets.data(), (c->n_lists + 1) * 8, cudaMemcpyHostToDevice)) !=
         cudaSuccess)
         return fail(e);
+    c->d_units = c->own_units;
+    c->d_list_offsets = c->own_list_offsets;
+    *out = c;
+    return DINT_OK;
+}
+
+int dint_vroom_ctx_create_discover(const dint_dict* d, const void* h_bin, size_t len, uint32_t block_size,
+                                   const uint64_t* sync_offsets, size_t n_sync, uint64_t sync_stride, void* stream,
+                                   dint_vroom_ctx** out) {
+    if (!d || !out || (!h_bin && len)) return DINT_E_ARG;
+    if (!d->d_rows) {
+        dint::set_error("dictionary is not device resident (no CPU fallback)");
+        return DINT_E_NODEVICE;
+    }
+    device_guard g(d->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    dint_vroom_ctx* c = new (std::nothrow) dint_vroom_ctx;
+    if (!c) return DINT_E_NOMEM;
+    c->dict = d;
+    c->block_size = block_size ? block_size : dint::kDefaultBlock;
+    c->in_bytes = len;
+    auto fail = [&](int rc, cudaError_t e) {
+        if (e != cudaSuccess) dint::set_error(std::string("dint_vroom_ctx_create_discover: ") + cudaGetErrorString(e));
+        dint_vroom_ctx_destroy(c);
+        return rc;
+    };
+    cudaError_t e;
+    if ((e = cudaMalloc(&c->d_in, len + 16)) != cudaSuccess) return fail(DINT_E_CUDA, e);
+    if (len && (e = cudaMemcpyAsync(c->d_in, h_bin, len, cudaMemcpyHostToDevice, st)) != cudaSuccess) return fail(DINT_E_CUDA, e);
+    int rc = dint_vroom_discover(d, c->d_in, len, c->block_size, sync_offsets, n_sync, sync_stride, stream, &c->plan);
+    if (rc) return fail(rc, cudaSuccess);
+    c->n_lists = c->plan->n_lists;
+    c->n_ints = c->plan->n_ints;
+    c->n_units = c->plan->n_units;
+    c->d_units = c->plan->d_units;
+    c->d_list_offsets = c->plan->d_list_offsets;
+    if ((e = cudaMalloc(&c->d_out, (c->n_ints + 1) * 4)) != cudaSuccess) return fail(DINT_E_CUDA, e);
+    if ((e = cudaMalloc(&c->d_sums, (c->n_lists + 1) * 8)) != cudaSuccess) return fail(DINT_E_CUDA, e);
     *out = c;
     return DINT_OK;
 }
 
 void dint_vroom_ctx_destroy(dint_vroom_ctx* c) {
     if (!c) return;
-    device_guard g(c->dict->device);
-    cudaFree(c->d_in);
-    cudaFree(c->d_units);
-    cudaFree(c->d_list_offsets);
-    cudaFree(c->d_out);
-    cudaFree(c->d_sums);
+    {
+        device_guard g(c->dict->device);
+        cudaFree(c->d_in);
+        cudaFree(c->own_units);
+        cudaFree(c->own_list_offsets);
+        cudaFree(c->d_out);
+        cudaFree(c->d_sums);
+    }
+    dint_device_plan_destroy(c->plan);
     delete c;
 }
 
 uint32_t* dint_vroom_ctx_device_output(const dint_vroom_ctx* c) { return c ? c->d_out : nullptr; }
+uint64_t dint_vroom_ctx_num_lists(const dint_vroom_ctx* c) { return c ? c->n_lists : 0; }
+uint64_t dint_vroom_ctx_num_ints(const dint_vroom_ctx* c) { return c ? c->n_ints : 0; }
+const dint_device_plan* dint_vroom_ctx_device_plan(const dint_vroom_ctx* c) { return c ? c->plan : nullptr; }
+
+// checksums / decoded integers of the last decode back to the host
+static int ctx_results(dint_vroom_ctx* c, uint32_t* h_out, uint64_t* h_sums, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (h_sums && c->n_lists) {
+        int rc = dint_checksum_lists(c->d_out, c->d_list_offsets, c->n_lists, c->d_sums, stream);
+        if (rc) return rc;
+        CUDA_TRY(cudaMemcpyAsync(h_sums, c->d_sums, c->n_lists * 8, cudaMemcpyDeviceToHost, st));
+    }
+    if (h_out && c->n_ints) CUDA_TRY(cudaMemcpyAsync(h_out, c->d_out, c->n_ints * 4, cudaMemcpyDeviceToHost, st));
+    return DINT_OK;
+}
 
 int dint_vroom_decode_host(dint_vroom_ctx* c, const void* h_bin, size_t len, int mode, uint32_t* h_out,
                            uint64_t* h_sums, void* stream) {
@@ -983,13 +1107,7 @@ int dint_vroom_decode_host(dint_vroom_ctx* c, const void* h_bin, size_t len, int
     if (len) CUDA_TRY(cudaMemcpyAsync(c->d_in, h_bin, len, cudaMemcpyHostToDevice, st));
     int rc = dint_decode_strips(c->dict, c->d_in, len, c->d_units, c->n_units, c->d_out, mode, stream);
     if (rc) return rc;
-    if (h_sums && c->n_lists) {
-        rc = dint_checksum_lists(c->d_out, c->d_list_offsets, c->n_lists, c->d_sums, stream);
-        if (rc) return rc;
-        CUDA_TRY(cudaMemcpyAsync(h_sums, c->d_sums, c->n_lists * 8, cudaMemcpyDeviceToHost, st));
-    }
-    if (h_out && c->n_ints) CUDA_TRY(cudaMemcpyAsync(h_out, c->d_out, c->n_ints * 4, cudaMemcpyDeviceToHost, st));
-    return DINT_OK;
+    return ctx_results(c, h_out, h_sums, stream);
 }
 
 int dint_vroom_decode_resident(dint_vroom_ctx* c, int mode, void* stream) {
@@ -997,10 +1115,40 @@ int dint_vroom_decode_resident(dint_vroom_ctx* c, int mode, void* stream) {
     return dint_decode_strips(c->dict, c->d_in, c->in_bytes, c->d_units, c->n_units, c->d_out, mode, stream);
 }
 
+int dint_vroom_ctx_results(dint_vroom_ctx* c, uint32_t* h_out, uint64_t* h_sums, void* stream) {
+    if (!c) return DINT_E_ARG;
+    device_guard g(c->dict->device);
+    return ctx_results(c, h_out, h_sums, stream);
+}
+
 int dint_vroom_ctx_sync(dint_vroom_ctx* c, void* stream) {
     if (!c) return DINT_E_ARG;
     device_guard g(c->dict->device);
     CUDA_TRY(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    return DINT_OK;
+}
+
+// Scratch of dint_decode_list_host, kept with the dictionary and grown on demand: after the first call of a
+// given size the call allocates nothing (it is the literal Decoder::decode drop-in, called once per list).
+static int list_scratch(const dint_dict* d, size_t in_bytes, size_t out_ints) {
+    dint_dict::host_scratch& s = d->scratch;
+    if (s.in_cap < in_bytes) {
+        cudaFree(s.d_in);
+        s.d_in = nullptr;
+        s.in_cap = 0;
+        const size_t cap = std::max<size_t>(in_bytes * 2, 1u << 16);
+        CUDA_TRY(cudaMalloc(&s.d_in, cap));
+        s.in_cap = cap;
+    }
+    if (s.out_cap < out_ints) {
+        cudaFree(s.d_out);
+        s.d_out = nullptr;
+        s.out_cap = 0;
+        const size_t cap = std::max<size_t>(out_ints * 2, 1u << 14);
+        CUDA_TRY(cudaMalloc(&s.d_out, cap * 4));
+        s.out_cap = cap;
+    }
+    if (!s.d_cons) CUDA_TRY(cudaMalloc(&s.d_cons, 8));
     return DINT_OK;
 }
 
@@ -1020,38 +1168,26 @@ int dint_decode_list_host(const dint_dict* d, const uint8_t* in, size_t in_avail
     // a list never needs more than 6 bytes per integer plus one selector byte per block
     size_t need = size_t(n) * 6 + (size_t(n) / block_size + 2) + 16;
     size_t nbytes = std::min(in_avail, need);
-    uint8_t* d_in = nullptr;
-    uint32_t* d_out = nullptr;
-    uint64_t* d_cons = nullptr;
-    int rc = DINT_OK;
-    cudaError_t e;
-    auto fail = [&](const char* what, cudaError_t err) {
-        dint::set_error(std::string(what) + ": " + cudaGetErrorString(err));
-        rc = DINT_E_CUDA;
-    };
-    if ((e = cudaMalloc(&d_in, nbytes + 16)) != cudaSuccess) fail("cudaMalloc", e);
-    if (!rc && (e = cudaMalloc(&d_out, size_t(n) * 4)) != cudaSuccess) fail("cudaMalloc", e);
-    if (!rc && (e = cudaMalloc(&d_cons, 8)) != cudaSuccess) fail("cudaMalloc", e);
-    if (!rc && (e = cudaMemcpy(d_in, in, nbytes, cudaMemcpyHostToDevice)) != cudaSuccess) fail("cudaMemcpy H2D", e);
-    if (!rc) {
-        size_t smem = smem_bytes_of(d, 1);
-        e = cudaFuncSetAttribute(decode_list_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-        if (e != cudaSuccess) fail("cudaFuncSetAttribute", e);
-        if (!rc) {
-            decode_list_kernel<<<1, 32, smem>>>(d->view(), lut_bytes_of(d), d->kind == DINT_DICT_MULTI, d_in, nbytes, n,
-                                                block_size, d_out, d_cons);
-            ++g_launches;
-            if ((e = cudaGetLastError()) != cudaSuccess) fail("decode_list_kernel", e);
-        }
+    std::lock_guard<std::mutex> lk(d->scratch.mu);
+    int rc = list_scratch(d, nbytes + 16, n);
+    if (rc) return rc;
+    dint_dict::host_scratch& s = d->scratch;
+    CUDA_TRY(cudaMemcpy(s.d_in, in, nbytes, cudaMemcpyHostToDevice));
+    int warps = 1;
+    const size_t smem = smem_bytes_of(d, warps);
+    if (!s.attr_set) {
+        CUDA_TRY(cudaFuncSetAttribute(decode_list_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        s.attr_set = true;
     }
+    decode_list_kernel<<<1, 32, smem>>>(d->view(), lut_bytes_of(d), d->kind == DINT_DICT_MULTI, s.d_in, nbytes, n, block_size,
+                                        s.d_out, s.d_cons);
+    ++g_launches;
+    CUDA_TRY(cudaGetLastError());
     uint64_t cons = 0;
-    if (!rc && (e = cudaMemcpy(out, d_out, size_t(n) * 4, cudaMemcpyDeviceToHost)) != cudaSuccess) fail("cudaMemcpy D2H", e);
-    if (!rc && (e = cudaMemcpy(&cons, d_cons, 8, cudaMemcpyDeviceToHost)) != cudaSuccess) fail("cudaMemcpy D2H", e);
-    cudaFree(d_in);
-    cudaFree(d_out);
-    cudaFree(d_cons);
-    if (!rc && consumed) *consumed = size_t(cons);
-    return rc;
+    CUDA_TRY(cudaMemcpy(out, s.d_out, size_t(n) * 4, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(&cons, s.d_cons, 8, cudaMemcpyDeviceToHost));
+    if (consumed) *consumed = size_t(cons);
+    return DINT_OK;
 }
 
 }  // extern "C"

@@ -42,16 +42,56 @@ def _structured_to_device(arr, dev):
     return raw.to(dev)
 
 
-class VroomFile:
-    """A vroom-encoded .bin + its dictionary, resident on one GPU, ready for batch decode."""
+class _DeviceArray:
+    """zero-copy torch view of library-owned device memory (__cuda_array_interface__)"""
 
-    def __init__(self, type_, bin_bytes, dict_bytes, device=0, block_size=256, chunk_ints=0, engine="strips"):
+    def __init__(self, ptr, count, typestr):
+        self.__cuda_array_interface__ = {"shape": (int(count),), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+def device_view(ptr, count, typestr, dev):
+    if not count:
+        return torch.empty(0, dtype={"<i8": torch.int64, "|u1": torch.uint8}[typestr], device=dev)
+    return torch.as_tensor(_DeviceArray(ptr, count, typestr), device=dev)
+
+
+class VroomFile:
+    """A vroom-encoded .bin + its dictionary, resident on one GPU, ready for batch decode.
+
+    plan="host": the restart points come from the serial host walk (dint_vroom_plan_create);
+    plan="device": no host plan at all — the GPU finds them in the bytes it already holds
+    (dint_vroom_discover; sync_offsets / sync_stride as documented in include/dint_b200.h)."""
+
+    def __init__(self, type_, bin_bytes, dict_bytes, device=0, block_size=256, chunk_ints=0, engine="strips", plan="host",
+                 sync_offsets=None, sync_stride=0):
         if type_ not in capi.KIND_OF_TYPE:
             raise ValueError(f"unknown type '{type_}'")  # decode.cpp:259 logs "ERROR: unknown type"
         self.type = type_
         self.dev = _require_cuda(device)
         self.block_size = block_size
         self.dict = capi.Dictionary(capi.KIND_OF_TYPE[type_], dict_bytes, device=device)
+        if plan == "device":
+            if engine != "strips":
+                raise ValueError("plan='device' produces strip tables: engine must be 'strips'")
+            self.engine = engine
+            self.plan = None
+            self.in_bytes = len(bin_bytes)
+            self.d_in = _to_device_bytes(bin_bytes, self.dev)
+            with torch.cuda.device(self.dev):
+                st = torch.cuda.current_stream(self.dev).cuda_stream
+                self.dplan = capi.DevicePlan.discover_vroom(self.dict, self.d_in.data_ptr(), self.in_bytes, block_size,
+                                                            sync_offsets, sync_stride, stream=st)
+            self.n_ints = int(self.dplan.n_ints)
+            self.n_lists = int(self.dplan.n_lists)
+            self.n_strip_units = int(self.dplan.n_units)
+            self.units_ptr = self.dplan.units_ptr
+            self.d_list_offsets = device_view(self.dplan.list_offsets_ptr, self.n_lists + 1, "<i8", self.dev)
+            self.d_list_byte_offsets = device_view(self.dplan.list_byte_offsets_ptr, self.n_lists + 1, "<i8", self.dev)
+            return
+        if plan != "host":
+            raise ValueError(f"unknown plan '{plan}'")
+        self.dplan = None
+        self.in_bytes = len(bin_bytes)
         self.plan = capi.VroomPlan(self.dict, bin_bytes, block_size=block_size, chunk_ints=chunk_ints)
         # engine: "strips" = lane-sequential decoder over the plan's strip table (dint_decode_strips, the
         # fast path); "units" = warp-per-work-unit tile decoder over the segment table (dint_decode_units)
@@ -65,6 +105,8 @@ class VroomFile:
         self.d_list_offsets = torch.from_numpy(self.plan.list_offsets.astype(np.int64)).to(self.dev)
         self.n_ints = int(self.plan.n_ints)
         self.n_lists = int(self.plan.n_lists)
+        self.n_strip_units = int(self.plan.n_strip_units)
+        self.units_ptr = self.d_strip_units.data_ptr()
 
     def decode(self, out=None, mode=capi.MODE_RAW, stream=None):
         """Decode every list of the file into one packed int32 tensor of n_ints values."""
@@ -72,8 +114,8 @@ class VroomFile:
             out = torch.empty(self.n_ints, dtype=torch.int32, device=self.dev)
         st = (stream or torch.cuda.current_stream(self.dev)).cuda_stream
         if self.engine == "strips":
-            capi.decode_strips(self.dict, self.d_in.data_ptr(), self.plan.in_bytes, self.d_strip_units.data_ptr(),
-                               int(self.plan.n_strip_units), out.data_ptr(), mode, stream=st)
+            capi.decode_strips(self.dict, self.d_in.data_ptr(), self.in_bytes, self.units_ptr, self.n_strip_units,
+                               out.data_ptr(), mode, stream=st)
             return out
         capi.decode_units(self.dict, self.d_in.data_ptr(), self.plan.in_bytes, self.d_segs.data_ptr(),
                           int(self.plan.n_segments), self.d_unit_first.data_ptr(), int(self.plan.n_units),
@@ -125,15 +167,36 @@ class IndexFile:
         self.d_list_offsets = torch.from_numpy(p.list_offsets.astype(np.int64)).to(self.dev)
         self.n_postings = int(p.n_postings)
         self.n_lists = int(p.n_lists)
+        self.docs_plan = self.freqs_plan = None
 
-    def scan(self, docids=None, freqs=None, want_docs=True, want_freqs=True, stream=None):
-        """docid() and freq() of every posting of every list, packed list after list."""
+    def discover(self, stream=None):
+        """strip tables of the full blocks, found on the device from the file's own block endpoints
+        (dint_index_discover); scan(engine="strips") then runs the lane-sequential decoder"""
+        if self.docs_plan is None:
+            st = (stream or torch.cuda.current_stream(self.dev)).cuda_stream
+            p = self.plan
+            with torch.cuda.device(self.dev):
+                self.docs_plan, self.freqs_plan = capi.DevicePlan.discover_index(
+                    self.docs_dict, self.freqs_dict, self.d_bin.data_ptr() + p.lists_off, p.lists_len, self.d_blocks.data_ptr(),
+                    int(p.n_blocks), self.block_size, stream=st)
+        return self.docs_plan, self.freqs_plan
+
+    def scan(self, docids=None, freqs=None, want_docs=True, want_freqs=True, stream=None, engine="tiles"):
+        """docid() and freq() of every posting of every list, packed list after list.
+        engine="tiles": warp-per-block tile decoder (dint_decode_index); "strips": dint_decode_index_planned."""
         if want_docs and docids is None:
             docids = torch.empty(self.n_postings, dtype=torch.int32, device=self.dev)
         if want_freqs and freqs is None:
             freqs = torch.empty(self.n_postings, dtype=torch.int32, device=self.dev)
         st = (stream or torch.cuda.current_stream(self.dev)).cuda_stream
         p = self.plan
+        if engine == "strips":
+            dp, fp = self.discover(stream)
+            capi.decode_index_planned(self.docs_dict, self.freqs_dict, self.d_bin.data_ptr() + p.lists_off, p.lists_len, dp, fp,
+                                      self.d_blocks.data_ptr(), int(p.n_blocks), self.block_size,
+                                      docids.data_ptr() if want_docs else None, freqs.data_ptr() if want_freqs else None,
+                                      stream=st)
+            return docids, freqs
         capi.decode_index(self.docs_dict, self.freqs_dict, self.d_bin.data_ptr() + p.lists_off, p.lists_len,
                           self.d_blocks.data_ptr(), int(p.n_blocks), self.block_size,
                           docids.data_ptr() if want_docs else None, freqs.data_ptr() if want_freqs else None, stream=st)

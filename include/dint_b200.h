@@ -53,7 +53,7 @@
 extern "C" {
 #endif
 
-#define DINT_B200_ABI_VERSION 4 /* 4: dint_strip_unit.flags (DINT_UNIT_HAS_RUNS) is REQUIRED for units with run codewords */
+#define DINT_B200_ABI_VERSION 5 /* 5: device-side discovery (dint_vroom_discover, dint_index_discover, dint_device_plan_*) */
 
 /* dictionary kinds == the reference's three dictionary types */
 enum {
@@ -145,6 +145,7 @@ typedef struct dint_dict dint_dict;
 typedef struct dint_vroom_plan dint_vroom_plan;
 typedef struct dint_index_plan dint_index_plan;
 typedef struct dint_vroom_ctx dint_vroom_ctx;
+typedef struct dint_device_plan dint_device_plan;
 
 const char* dint_last_error(void);
 int dint_abi_version(void);
@@ -211,10 +212,48 @@ const uint64_t* dint_index_plan_endpoints(const dint_index_plan* p);    /* n_lis
 int dint_index_plan_layout(const dint_index_plan* p, uint64_t* lists_off, uint64_t* lists_len, uint64_t* docs_dict_off,
                            uint64_t* freqs_dict_off, uint64_t* end_off);
 
+/* ---- device-side discovery of the restart points (no host codeword walk) ------------------ */
+/* What dint_vroom_plan_create learns by walking every codeword on one host thread is found here by the
+ * GPU from the bytes already in HBM (d_in: DEVICE pointer to the .bin image). The file is cut into CHAINS
+ * at list starts; one warp walks one chain exactly like vroom_env/decode.cpp:139-150 does (header::read,
+ * then codewords until n integers are out: vroom_env/dint_codecs.hpp:45-101, 530-611), 32 symbols per step,
+ * without copying dictionary entries; a count pass sizes the tables and an emit pass fills them.
+ * Chain starts = byte 0 + sync_offsets[0..n_sync) (HOST array of byte offsets the caller knows to be list
+ * starts, e.g. where shard files were concatenated; may be NULL) + list starts a speculative search finds
+ * every sync_stride bytes (0 = library default, ~0 = no search): a position is taken when it parses as
+ * three consecutive lists whose values sum to the `universe` field of their headers (vroom_env/jobs.hpp:76-85).
+ * Every chain must END exactly on the next chain's start; a start that is not landed on is dropped and the
+ * count pass repeated, so neither a wrong hint nor a wrong guess can change the result.
+ * Synchronises `stream` (this is a load-time call). */
+int dint_vroom_discover(const dint_dict* d, const uint8_t* d_in, size_t in_bytes, uint32_t block_size,
+                        const uint64_t* sync_offsets, size_t n_sync, uint64_t sync_stride, void* stream,
+                        dint_device_plan** out);
+/* The same for the full blocks of a frozen dict_freq_index: block starts come from the file's own endpoint
+ * tables (d_blocks: DEVICE dint_block table, 16-byte aligned, e.g. dint_index_plan_blocks uploaded), the docs
+ * stream of a block is walked first, the freqs stream starts where it ends (dict_posting_list.hpp:311-318).
+ * Two strip tables come back: docs (DINT_MODE_DOCIDS, block bases folded in) and freqs. */
+int dint_index_discover(const dint_dict* docs_dict, const dint_dict* freqs_dict, const uint8_t* d_lists, size_t lists_bytes,
+                        const dint_block* d_blocks, size_t n_blocks, uint32_t block_size, void* stream,
+                        dint_device_plan** docs_plan, dint_device_plan** freqs_plan);
+void dint_device_plan_destroy(dint_device_plan* p);
+uint64_t dint_device_plan_num_lists(const dint_device_plan* p);
+uint64_t dint_device_plan_num_ints(const dint_device_plan* p);
+uint64_t dint_device_plan_num_units(const dint_device_plan* p);
+uint64_t dint_device_plan_num_chains(const dint_device_plan* p);
+uint64_t dint_device_plan_num_sync_found(const dint_device_plan* p); /* list starts the speculative search contributed */
+uint32_t dint_device_plan_retries(const dint_device_plan* p);        /* count passes repeated after a wrong sync point */
+double dint_device_plan_discover_ms(const dint_device_plan* p);      /* device timeline of the discovery, CUDA events */
+/* DEVICE pointers owned by the plan: num_units strip units (input of dint_decode_strips); num_lists + 1
+ * offsets into the packed output / into the file (vroom plans only, NULL for index plans) */
+const dint_strip_unit* dint_device_plan_units(const dint_device_plan* p);
+const uint64_t* dint_device_plan_list_offsets(const dint_device_plan* p);
+const uint64_t* dint_device_plan_list_byte_offsets(const dint_device_plan* p);
+
 /* ---- device decode (stream ordered; all pointers are DEVICE pointers) ------------------ */
 /* d_in: the .bin bytes as they are on disk (in_bytes of them; no padding required).
  * d_segs: n_segs descriptors. d_out: packed output, at least max(out_off + n) ints.
- * stream: a cudaStream_t (0 = default stream). */
+ * stream: a cudaStream_t (0 = default stream). block_size: the segments of a multi_packed list already are
+ * the blocks the plan cut with this value, so it is only checked for sanity (<= 65536). */
 int dint_decode_segments(const dint_dict* d, const uint8_t* d_in, size_t in_bytes, const dint_segment* d_segs,
                          size_t n_segs, uint32_t block_size, uint32_t* d_out, int mode, void* stream);
 /* Same with an explicit work-unit table (d_unit_first: n_units + 1 DEVICE uint32, see
@@ -238,6 +277,14 @@ int dint_decode_index(const dint_dict* docs_dict, const dint_dict* freqs_dict, c
                       size_t lists_bytes, const dint_block* d_blocks, size_t n_blocks, uint32_t block_size,
                       uint32_t* d_docids, uint32_t* d_freqs, void* stream);
 
+/* The same result from the strip tables dint_index_discover built: full blocks go through the lane-sequential
+ * decoder (dint_decode_strips: docs with the block bases folded into the docID prefix sum, freqs with +1),
+ * partial blocks through the interpolative kernel. d_blocks is still needed for the partial blocks. */
+int dint_decode_index_planned(const dint_dict* docs_dict, const dint_dict* freqs_dict, const uint8_t* d_lists,
+                              size_t lists_bytes, const dint_device_plan* docs_plan, const dint_device_plan* freqs_plan,
+                              const dint_block* d_blocks, size_t n_blocks, uint32_t block_size, uint32_t* d_docids,
+                              uint32_t* d_freqs, void* stream);
+
 /* sums[i] = sum_{j in list i} (value_j + 1) * (j + 1)  mod 2^64 */
 int dint_checksum_lists(const uint32_t* d_values, const uint64_t* d_list_offsets, size_t n_lists, uint64_t* d_sums,
                         void* stream);
@@ -253,7 +300,17 @@ int dint_decode_list_host(const dint_dict* d, const uint8_t* in, size_t in_avail
  * segment table and list offsets, input / output / checksum buffers): create once, reuse for
  * every call, so the call itself allocates nothing. */
 int dint_vroom_ctx_create(const dint_dict* d, const dint_vroom_plan* plan, uint32_t block_size, dint_vroom_ctx** out);
+/* The same workspace for a file NO host plan exists for (the cold path): copies h_bin (HOST pointer, len bytes)
+ * to the device on `stream`, finds its restart points there (dint_vroom_discover; sync_* as documented
+ * there) and sizes the output from what the walk counted. Synchronises `stream`. */
+int dint_vroom_ctx_create_discover(const dint_dict* d, const void* h_bin, size_t len, uint32_t block_size,
+                                   const uint64_t* sync_offsets, size_t n_sync, uint64_t sync_stride, void* stream,
+                                   dint_vroom_ctx** out);
 void dint_vroom_ctx_destroy(dint_vroom_ctx* c);
+uint64_t dint_vroom_ctx_num_lists(const dint_vroom_ctx* c);
+uint64_t dint_vroom_ctx_num_ints(const dint_vroom_ctx* c);
+/* the device plan of a ctx made by dint_vroom_ctx_create_discover (NULL otherwise); owned by the ctx */
+const dint_device_plan* dint_vroom_ctx_device_plan(const dint_vroom_ctx* c);
 /* device pointer of the ctx's packed output (num_ints values, valid after a decode) */
 uint32_t* dint_vroom_ctx_device_output(const dint_vroom_ctx* c);
 /* h_bin: HOST pointer to the .bin image the plan was made from (pinned memory makes the
@@ -265,6 +322,9 @@ int dint_vroom_decode_host(dint_vroom_ctx* c, const void* h_bin, size_t len, int
 /* Decodes again from the bytes the last dint_vroom_decode_host call left in HBM (no copies):
  * what the reference's decode loop does once the file is mapped. */
 int dint_vroom_decode_resident(dint_vroom_ctx* c, int mode, void* stream);
+/* Enqueues what dint_vroom_decode_host does after the decode: (h_sums != NULL) per-list checksums + D2H of
+ * num_lists uint64, (h_out != NULL) D2H of all decoded integers of the ctx's last decode. */
+int dint_vroom_ctx_results(dint_vroom_ctx* c, uint32_t* h_out, uint64_t* h_sums, void* stream);
 /* Blocks until everything enqueued on `stream` of the ctx's device has finished. */
 int dint_vroom_ctx_sync(dint_vroom_ctx* c, void* stream);
 

@@ -1,0 +1,186 @@
+"""Device-side discovery of the decode restart points (dint_vroom_discover / dint_index_discover):
+files decoded with NO host plan must give what the reference decoders give, and the tables the GPU finds
+must agree with the serial host walk (dint_vroom_plan_create) on everything that is comparable
+(lists, integers, list offsets in the output and in the file)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import golden_data as g
+import stream_builder as sb
+from dint_b200 import capi, driver
+from oracle_lib import KINDS
+from test_gpu_parity import EDGE_LISTS, _random_lists
+
+pytestmark = pytest.mark.gpu
+
+
+def _np(t):
+    return t.cpu().numpy().view(np.uint32)
+
+
+# sync_stride variants: library default / every 16 KB / no speculative search at all (one chain)
+STRIDES = (0, 16384, capi.NO_SYNC_SEARCH)
+
+
+@pytest.mark.parametrize("stride", STRIDES)
+@pytest.mark.parametrize("type_", g.TYPES)
+@pytest.mark.parametrize("part,raw_key,fused_key,mode", (("docs", "vroom_docs_gaps_sha256", "docids_sha256", capi.MODE_DOCIDS),
+                                                         ("freqs", "vroom_freqs_minus1_sha256", "freqs_sha256", capi.MODE_FREQS)))
+def test_vroom_without_host_plan(golden, type_, part, raw_key, fused_key, mode, stride):
+    """config 1 decoded from a file no host code has walked: sha256 of the reference decoder's output"""
+    bin_ = golden.bytes(golden.vroom_name(type_, part))
+    dict_bytes = golden.bytes(golden.dict_name(type_, part))
+    vf = driver.VroomFile(type_, bin_, dict_bytes, plan="device", sync_stride=stride)
+    assert vf.plan is None and vf.n_lists == golden.n_lists and vf.n_ints == golden.n_postings
+    assert g.sha(_np(vf.decode(mode=capi.MODE_RAW)).tobytes()) == golden.sha[raw_key]
+    assert g.sha(_np(vf.decode(mode=mode)).tobytes()) == golden.sha[fused_key]
+    # list offsets (output and file) == the host walk's
+    host = capi.VroomPlan(capi.Dictionary(KINDS[type_], dict_bytes), bin_)
+    assert np.array_equal(vf.d_list_offsets.cpu().numpy().astype(np.uint64), host.list_offsets)
+    assert np.array_equal(vf.d_list_byte_offsets.cpu().numpy().astype(np.uint64), host.list_byte_offsets)
+    if stride == capi.NO_SYNC_SEARCH:
+        assert vf.dplan.n_chains == 1 and vf.dplan.n_sync_found == 0
+    elif stride:
+        assert vf.dplan.n_chains > 8  # the speculative search found list starts to cut the file at
+    assert vf.dplan.retries == 0
+
+
+@pytest.mark.parametrize("type_", g.TYPES)
+def test_sync_hints_right_and_wrong(golden, type_):
+    """caller-provided list starts are used; offsets that are NOT list starts are dropped (the previous chain does
+    not land on them) and the result is unchanged"""
+    bin_ = golden.bytes(golden.vroom_name(type_, "docs"))
+    dict_bytes = golden.bytes(golden.dict_name(type_, "docs"))
+    host = capi.VroomPlan(capi.Dictionary(KINDS[type_], dict_bytes), bin_)
+    starts = host.list_byte_offsets
+    good = starts[[1000, 5000, 50000, 100000]]
+    vf = driver.VroomFile(type_, bin_, dict_bytes, plan="device", sync_offsets=good, sync_stride=capi.NO_SYNC_SEARCH)
+    assert vf.dplan.n_chains == 5 and vf.dplan.retries == 0
+    assert g.sha(_np(vf.decode(mode=capi.MODE_DOCIDS)).tobytes()) == golden.sha["docids_sha256"]
+    bad = np.array([starts[1000], starts[5000] + 1, starts[50000] + 3, starts[100000], len(bin_) - 2], dtype=np.uint64)
+    vf = driver.VroomFile(type_, bin_, dict_bytes, plan="device", sync_offsets=bad, sync_stride=capi.NO_SYNC_SEARCH)
+    assert vf.dplan.retries >= 1
+    assert vf.n_lists == golden.n_lists and vf.n_ints == golden.n_postings
+    assert g.sha(_np(vf.decode(mode=capi.MODE_DOCIDS)).tobytes()) == golden.sha["docids_sha256"]
+    assert np.array_equal(vf.d_list_offsets.cpu().numpy().astype(np.uint64), host.list_offsets)
+
+
+@pytest.mark.parametrize("type_", g.TYPES)
+def test_discover_edge_streams(golden, oracle, type_):
+    """32-bit exceptions, payload equal to 0/1, exceptions straddling tiles, runs, 1-integer lists, u8 blocks,
+    a 60 000-integer list: device-found tables decode to what was encoded, in every mode"""
+    rng = np.random.default_rng(11)
+    dict_bytes = golden.bytes(golden.dict_name(type_, "docs"))
+    di = sb.DictImage(capi.KIND_OF_TYPE[type_], dict_bytes)
+    lists = EDGE_LISTS + _random_lists(di, rng, 150, 60000)
+    want = np.concatenate([np.asarray(v, dtype=np.uint32) for v in lists])
+    exp_docs = np.concatenate([(np.cumsum(np.asarray(v, dtype=np.uint64) + 1) - 1).astype(np.uint32) for v in lists])
+    ho = oracle.dict_parse(KINDS[type_], dict_bytes)
+    for sels in ([0, 6, 3, 9, 1, 7], [8], [2], rng.integers(0, 12, 64).tolist()):
+        data = b"".join(sb.encode_vroom_list(di, v, block_size=256, selectors=sels) for v in lists)
+        o, _ = oracle.vroom_decode_file(ho, data, len(want), len(lists))
+        assert np.array_equal(o, want)
+        for stride in (4096, capi.NO_SYNC_SEARCH):
+            vf = driver.VroomFile(type_, data, dict_bytes, plan="device", sync_stride=stride)
+            assert vf.n_lists == len(lists) and vf.n_ints == len(want)
+            assert np.array_equal(_np(vf.decode(mode=capi.MODE_RAW)), want), (sels[:6], stride)
+            assert np.array_equal(_np(vf.decode(mode=capi.MODE_DOCIDS)), exp_docs), (sels[:6], stride)
+            assert np.array_equal(_np(vf.decode(mode=capi.MODE_FREQS)), want + np.uint32(1)), (sels[:6], stride)
+    oracle.dict_free(ho)
+
+
+def test_discover_rejects_malformed_files(golden):
+    type_ = "single_packed_dint"
+    bin_ = golden.bytes(golden.vroom_name(type_, "docs"))
+    dict_bytes = golden.bytes(golden.dict_name(type_, "docs"))
+    with pytest.raises(capi.DintError) as e:
+        driver.VroomFile(type_, bin_[:len(bin_) - 5], dict_bytes, plan="device", sync_stride=capi.NO_SYNC_SEARCH)
+    assert e.value.code == -2
+    # an empty file is fine: nothing to decode
+    vf = driver.VroomFile(type_, b"", dict_bytes, plan="device")
+    assert vf.n_lists == 0 and vf.n_ints == 0
+
+
+@pytest.mark.parametrize("type_", g.TYPES)
+def test_cold_host_call_equals_planned_call(golden, type_):
+    """dint_vroom_ctx_create_discover (H2D + device-side discovery, no host plan) then decode + checksums:
+    the per-list checksums are those of the host-planned path and of the collection itself"""
+    bin_ = golden.bytes(golden.vroom_name(type_, "docs"))
+    dict_bytes = golden.bytes(golden.dict_name(type_, "docs"))
+    d = capi.Dictionary(KINDS[type_], dict_bytes, device=0)
+    h_bin = torch.frombuffer(bytearray(bin_), dtype=torch.uint8).pin_memory()
+    st = torch.cuda.current_stream().cuda_stream
+    dec = capi.VroomHostDecoder.discover(d, h_bin.data_ptr(), h_bin.numel(), stream=st)
+    assert dec.n_lists == golden.n_lists and dec.n_ints == golden.n_postings
+    dec.decode_resident(mode=capi.MODE_DOCIDS, stream=st)
+    sums = torch.empty(dec.n_lists, dtype=torch.int64).pin_memory()
+    out = torch.empty(dec.n_ints, dtype=torch.int32).pin_memory()
+    dec.results(h_out_ptr=out.data_ptr(), h_sums_ptr=sums.data_ptr(), stream=st)
+    dec.sync(st)
+    assert g.sha(out.numpy().view(np.uint32).tobytes()) == golden.sha["docids_sha256"]
+    plan = capi.VroomPlan(d, bin_)
+    ref = capi.VroomHostDecoder(plan)
+    sums2 = torch.empty(dec.n_lists, dtype=torch.int64).pin_memory()
+    ref.decode(h_bin.data_ptr(), h_bin.numel(), mode=capi.MODE_DOCIDS, h_sums_ptr=sums2.data_ptr(), stream=st)
+    ref.sync(st)
+    assert torch.equal(sums, sums2)
+    lens = np.diff(plan.list_offsets.astype(np.int64))
+    want = g.checksum_lists(out.numpy().view(np.uint32), lens)
+    assert np.array_equal(sums.numpy().view(np.uint64), want)
+
+
+@pytest.mark.parametrize("type_", g.TYPES)
+def test_index_scan_with_discovered_strips(golden, oracle, type_):
+    """config 2 through the lane-sequential decoder: the full blocks' strip tables come from dint_index_discover
+    (block starts from the file's own endpoints, codeword boundaries found on the device)"""
+    idx = driver.IndexFile(type_, golden.bytes(golden.index_name(type_)))
+    d, f = idx.scan(engine="strips")
+    d, f = _np(d), _np(f)
+    assert g.sha(d.tobytes()) == golden.sha["docids_sha256"]
+    assert g.sha(f.tobytes()) == golden.sha["freqs_sha256"]
+    assert idx.docs_plan.n_units > 0 and idx.freqs_plan.n_units > 0
+    d2, _ = idx.scan(engine="strips", want_freqs=False)
+    _, f2 = idx.scan(engine="strips", want_docs=False)
+    assert np.array_equal(_np(d2), d) and np.array_equal(_np(f2), f)
+
+
+@pytest.mark.parametrize("type_", ("single_rect_dint", "single_packed_dint"))
+def test_index_discovered_strips_block128(golden128, type_):
+    data = golden128.bytes(golden128.index_name(type_))
+    idx = driver.IndexFile(type_, data, block_size=128)
+    d, f = idx.scan(engine="strips")
+    assert g.sha(_np(d).tobytes()) == golden128.sha["docids_sha256"]
+    assert g.sha(_np(f).tobytes()) == golden128.sha["freqs_sha256"]
+
+
+def test_index_discover_subset_of_blocks(golden):
+    """a ragged block table (every third list): units must not carry a docID prefix across a gap"""
+    type_ = "single_packed_dint"
+    idx = driver.IndexFile(type_, golden.bytes(golden.index_name(type_)))
+    full_d, full_f = idx.scan()
+    full_d, full_f = _np(full_d), _np(full_f)
+    p = idx.plan
+    blocks = p.blocks
+    list_of = np.searchsorted(p.list_offsets, blocks["out_off"], side="right") - 1
+    long_lists = np.unique(list_of[blocks["size"] == 256])
+    pick = blocks[np.isin(list_of, long_lists[::3])].copy()
+    # drop every 5th block as well, and pack the outputs
+    pick = pick[np.arange(len(pick)) % 5 != 2].copy()
+    src = pick["out_off"].astype(np.int64)
+    n = pick["size"].astype(np.int64)
+    new_off = np.concatenate([[0], np.cumsum(n)])
+    pick["out_off"] = new_off[:-1]
+    d_blocks = torch.from_numpy(pick.view(np.uint8).reshape(-1)).cuda()
+    st = torch.cuda.current_stream().cuda_stream
+    dp, fp = capi.DevicePlan.discover_index(idx.docs_dict, idx.freqs_dict, idx.d_bin.data_ptr() + p.lists_off, p.lists_len,
+                                            d_blocks.data_ptr(), len(pick), 256, stream=st)
+    dd = torch.zeros(int(new_off[-1]), dtype=torch.int32, device="cuda")
+    ff = torch.zeros_like(dd)
+    capi.decode_index_planned(idx.docs_dict, idx.freqs_dict, idx.d_bin.data_ptr() + p.lists_off, p.lists_len, dp, fp,
+                              d_blocks.data_ptr(), len(pick), 256, dd.data_ptr(), ff.data_ptr(), stream=st)
+    want_d = np.concatenate([full_d[s:s + k] for s, k in zip(src, n)])
+    want_f = np.concatenate([full_f[s:s + k] for s, k in zip(src, n)])
+    assert np.array_equal(_np(dd), want_d) and np.array_equal(_np(ff), want_f)
