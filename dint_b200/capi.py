@@ -43,7 +43,7 @@ SYMBOLS = [
     "dint_vroom_decode_resident", "dint_vroom_ctx_sync",
     "dint_vroom_discover", "dint_index_discover", "dint_device_plan_destroy", "dint_device_plan_num_lists",
     "dint_device_plan_num_ints", "dint_device_plan_num_units", "dint_device_plan_num_chains",
-    "dint_device_plan_num_sync_found", "dint_device_plan_retries", "dint_device_plan_discover_ms",
+    "dint_device_plan_num_sync_found", "dint_device_plan_retries", "dint_device_plan_discover_ms", "dint_device_plan_phase_ms",
     "dint_device_plan_units", "dint_device_plan_list_offsets", "dint_device_plan_list_byte_offsets",
     "dint_decode_index_planned", "dint_vroom_ctx_create_discover", "dint_vroom_ctx_num_lists",
     "dint_vroom_ctx_num_ints", "dint_vroom_ctx_device_plan", "dint_vroom_ctx_results",
@@ -126,6 +126,8 @@ def lib():
         L.dint_device_plan_retries.restype = u32
         L.dint_device_plan_discover_ms.argtypes = [vp]
         L.dint_device_plan_discover_ms.restype = C.c_double
+        L.dint_device_plan_phase_ms.argtypes = [vp, i32]
+        L.dint_device_plan_phase_ms.restype = C.c_double
         for f in ("units", "list_offsets", "list_byte_offsets"):
             getattr(L, "dint_device_plan_" + f).argtypes = [vp]
             getattr(L, "dint_device_plan_" + f).restype = vp
@@ -271,6 +273,7 @@ class DevicePlan:
         self.n_sync_found = L.dint_device_plan_num_sync_found(handle)
         self.retries = L.dint_device_plan_retries(handle)
         self.discover_ms = L.dint_device_plan_discover_ms(handle)
+        self.phase_ms = [L.dint_device_plan_phase_ms(handle, i) for i in range(3)]
         self.units_ptr = L.dint_device_plan_units(handle)
         self.list_offsets_ptr = L.dint_device_plan_list_offsets(handle)
         self.list_byte_offsets_ptr = L.dint_device_plan_list_byte_offsets(handle)

@@ -80,6 +80,9 @@ uint64_t dint_device_plan_num_chains(const dint_device_plan* p) { return p ? p->
 uint64_t dint_device_plan_num_sync_found(const dint_device_plan* p) { return p ? p->n_sync_found : 0; }
 uint32_t dint_device_plan_retries(const dint_device_plan* p) { return p ? p->retries : 0; }
 double dint_device_plan_discover_ms(const dint_device_plan* p) { return p ? double(p->discover_ms) : 0.0; }
+double dint_device_plan_phase_ms(const dint_device_plan* p, int phase) {
+    return p && phase >= 0 && phase < 3 ? double(p->phase_ms[phase]) : 0.0;
+}
 const dint_strip_unit* dint_device_plan_units(const dint_device_plan* p) { return p ? p->d_units : nullptr; }
 const uint64_t* dint_device_plan_list_offsets(const dint_device_plan* p) { return p ? p->d_list_offsets : nullptr; }
 const uint64_t* dint_device_plan_list_byte_offsets(const dint_device_plan* p) { return p ? p->d_list_byte_offsets : nullptr; }
@@ -102,16 +105,20 @@ int dint_vroom_discover(const dint_dict* d, const uint8_t* d_in, size_t in_bytes
     if (!plan) return DINT_E_NOMEM;
     plan->device = d->device;
     plan->in_bytes = in_bytes;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evs = nullptr, evc = nullptr;
     CUDA_TRY(cudaEventCreate(&ev0));
     CUDA_TRY(cudaEventCreate(&ev1));
+    CUDA_TRY(cudaEventCreate(&evs));
+    CUDA_TRY(cudaEventCreate(&evc));
     struct ev_guard {
-        cudaEvent_t a, b;
+        cudaEvent_t a, b, c, d;
         ~ev_guard() {
             cudaEventDestroy(a);
             cudaEventDestroy(b);
+            cudaEventDestroy(c);
+            cudaEventDestroy(d);
         }
-    } evg{ev0, ev1};
+    } evg{ev0, ev1, evs, evc};
     CUDA_TRY(cudaEventRecord(ev0, st));
     const dint::strip_limits& lim = dint::get_strip_limits();
     const bool multi = d->kind == DINT_DICT_MULTI;
@@ -123,8 +130,8 @@ int dint_vroom_discover(const dint_dict* d, const uint8_t* d_in, size_t in_bytes
         for (size_t i = 0; i < n_sync; ++i)
             if (sync_offsets[i] > 0 && sync_offsets[i] < in_bytes) sync.push_back(sync_offsets[i]);
         if (sync_stride != ~uint64_t(0) && in_bytes > 0) {
-            // default: about two chains per resident walking warp, never closer than 16 KB
-            uint64_t stride = sync_stride ? sync_stride : std::max<uint64_t>(16384, in_bytes / (uint64_t(di.sms) * 64));
+            // default: about one chain per resident walking THREAD (1024 per SM), never closer than 4 KB
+            uint64_t stride = sync_stride ? sync_stride : std::max<uint64_t>(4096, in_bytes / (uint64_t(di.sms) * 1024));
             stride = std::max<uint64_t>(stride, 1024);
             const uint64_t n_targets = (in_bytes - 1) / stride;
             if (n_targets) {
@@ -139,9 +146,9 @@ int dint_vroom_discover(const dint_dict* d, const uint8_t* d_in, size_t in_bytes
                 F.multi = multi;
                 F.stride = stride;
                 F.n_targets = n_targets;
-                F.window = uint32_t(std::min<uint64_t>(stride, 8192) & ~uint64_t(31));
+                F.window = uint32_t(std::min<uint64_t>(stride, 2048) & ~uint64_t(31));
                 F.depth = 3;
-                F.max_n = 4096;
+                F.max_n = 256;  // evidence = three consecutive short lists (cheap to check; a Zipfian collection is full of them)
                 F.found = found.as<uint64_t>();
                 const size_t smem = walk_smem(d, 0);
                 CUDA_TRY(cudaFuncSetAttribute(find_sync_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
@@ -165,6 +172,7 @@ int dint_vroom_discover(const dint_dict* d, const uint8_t* d_in, size_t in_bytes
         return DINT_E_NOMEM;
     }
 
+    CUDA_TRY(cudaEventRecord(evs, st));
     vroom_walk_params P;
     P.dv = d->view();
     P.sums = d->d_sums;
@@ -176,119 +184,229 @@ int dint_vroom_discover(const dint_dict* d, const uint8_t* d_in, size_t in_bytes
     P.unit_bytes = lim.unit_bytes;
     P.strip_cw = lim.strip_codewords;
     P.strip_shift = strip_shift_of(lim);
+    P.strip_ints = lim.strip_ints;
     P.units = nullptr;
     P.units_cap = 0;
     P.list_offsets = P.list_byte_offsets = nullptr;
     P.bases = nullptr;
-
-    // ---- count pass (repeated while a sync point turns out not to be a list start) ----------------------------
-    dev_buf d_chain, d_counts, d_status;
-    std::vector<uint64_t> counts;
+    dev_buf d_status;
     CUDA_TRY(cudaMalloc(&d_status.p, 16));
-    try {
-        for (uint32_t attempt = 0;; ++attempt) {
-            if (in_bytes == 0) sync.clear();
-            const uint64_t nc = sync.size();
-            std::vector<uint64_t> starts(sync);
-            starts.push_back(in_bytes);
-            counts.assign(nc * 4, 0);
-            if (nc == 0) break;
-            if (d_chain.p) cudaFree(d_chain.p), d_chain.p = nullptr;
-            if (d_counts.p) cudaFree(d_counts.p), d_counts.p = nullptr;
-            CUDA_TRY(cudaMalloc(&d_chain.p, (nc + 1) * 8));
-            CUDA_TRY(cudaMalloc(&d_counts.p, nc * 32));
-            CUDA_TRY(cudaMemcpyAsync(d_chain.p, starts.data(), (nc + 1) * 8, cudaMemcpyHostToDevice, st));
-            CUDA_TRY(cudaMemsetAsync(d_status.p, 0, 16, st));
-            P.chain_start = d_chain.as<uint64_t>();
-            P.n_chains = nc;
-            P.counts = d_counts.as<uint64_t>();
-            P.status = d_status.as<uint32_t>();
-            int grid = 0;
-            size_t smem = 0;
-            rc = walk_grid(vroom_walk_kernel<false>, d, kWalkWarps, nc, &grid, &smem);
-            if (rc) return rc;
-            vroom_walk_kernel<false><<<grid, kWalkWarps * 32, smem, st>>>(P);
+    P.status = d_status.as<uint32_t>();
+
+    // One chain = one candidate list start + where the walk from it has to stop. Chains up to kLongChain bytes are
+    // walked by one thread each, longer ones (stretches without a sync point: very long lists) and the few chains of a
+    // repair round by one warp each. A chain keeps its walker: the two passes must pack its units identically.
+    constexpr uint64_t kLongChain = 96 * 1024;
+    struct chain {
+        uint64_t start, end;             // walk from start to the first list start >= end
+        uint64_t lists, ints, units, reached;
+        uint32_t status;
+        bool by_warp, counted;
+    };
+    // runs one pass over chains[ids]: device arrays are indexed by the position in ids
+    auto run_pass = [&](std::vector<chain>& chains, const std::vector<uint32_t>& ids, bool emit, const std::vector<uint64_t>* bases) -> int {
+        const uint64_t n = ids.size();
+        if (!n) return DINT_OK;
+        std::vector<uint64_t> se(2 * n + 2), cnt(4 * n, 0);
+        std::vector<uint32_t> order(n);
+        uint64_t n_short = 0, n_long = 0;
+        // walk_params wants chain c = [chain_start[c], chain_start[c + 1]): give every chain its own pair
+        for (uint64_t k = 0; k < n; ++k) {
+            se[2 * k] = chains[ids[k]].start;
+            se[2 * k + 1] = chains[ids[k]].end;
+        }
+        for (uint64_t k = 0; k < n; ++k)
+            if (!chains[ids[k]].by_warp) order[n_short++] = uint32_t(2 * k);
+        for (uint64_t k = 0; k < n; ++k)
+            if (chains[ids[k]].by_warp) order[n_short + n_long++] = uint32_t(2 * k);
+        dev_buf d_se, d_cnt, d_order, d_bases;
+        CUDA_TRY(cudaMalloc(&d_se.p, se.size() * 8));
+        CUDA_TRY(cudaMalloc(&d_cnt.p, 8 * n * 8));  // indexed by 2k: [2k][4]
+        CUDA_TRY(cudaMalloc(&d_order.p, n * 4));
+        CUDA_TRY(cudaMemcpyAsync(d_se.p, se.data(), se.size() * 8, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(d_order.p, order.data(), n * 4, cudaMemcpyHostToDevice, st));
+        std::vector<uint64_t> wide;
+        if (emit) {  // counts of the count pass (checked by the emit pass) + bases, both at index 2k
+            wide.assign(8 * n, 0);
+            for (uint64_t k = 0; k < n; ++k) {
+                const chain& c = chains[ids[k]];
+                wide[8 * k] = c.lists;
+                wide[8 * k + 1] = c.ints;
+                wide[8 * k + 2] = c.units;
+            }
+            CUDA_TRY(cudaMemcpyAsync(d_cnt.p, wide.data(), 8 * n * 8, cudaMemcpyHostToDevice, st));
+            std::vector<uint64_t> b(8 * n, 0);
+            for (uint64_t k = 0; k < n; ++k)
+                for (int j = 0; j < 3; ++j) b[8 * k + j] = (*bases)[4 * ids[k] + j];
+            CUDA_TRY(cudaMalloc(&d_bases.p, 8 * n * 8));
+            CUDA_TRY(cudaMemcpyAsync(d_bases.p, b.data(), 8 * n * 8, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            P.bases = d_bases.as<uint64_t>();
+        }
+        P.chain_start = d_se.as<uint64_t>();
+        P.n_chains = 2 * n;
+        P.counts = d_cnt.as<uint64_t>();
+        CUDA_TRY(cudaMemsetAsync(d_status.p, 0, 16, st));
+        if (n_short) {
+            P.chain_ids = d_order.as<uint32_t>();
+            P.n_ids = n_short;
+            const size_t smem = walk_smem(d, 0);
+            const int grid = int((n_short + 255) / 256);
+            if (emit) {
+                CUDA_TRY(cudaFuncSetAttribute(vroom_thread_walk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+                vroom_thread_walk_kernel<true><<<grid, 256, smem, st>>>(P);
+            } else {
+                CUDA_TRY(cudaFuncSetAttribute(vroom_thread_walk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+                vroom_thread_walk_kernel<false><<<grid, 256, smem, st>>>(P);
+            }
             ++g_launches;
             CUDA_TRY(cudaGetLastError());
-            CUDA_TRY(cudaMemcpyAsync(counts.data(), d_counts.p, nc * 32, cudaMemcpyDeviceToHost, st));
+        }
+        if (n_long) {
+            P.chain_ids = d_order.as<uint32_t>() + n_short;
+            P.n_ids = n_long;
+            int grid = 0, rc2;
+            size_t smem = 0;
+            if (emit) {
+                rc2 = walk_grid(vroom_walk_kernel<true>, d, kWalkWarps, n_long, &grid, &smem);
+                if (rc2) return rc2;
+                vroom_walk_kernel<true><<<grid, kWalkWarps * 32, smem, st>>>(P);
+            } else {
+                rc2 = walk_grid(vroom_walk_kernel<false>, d, kWalkWarps, n_long, &grid, &smem);
+                if (rc2) return rc2;
+                vroom_walk_kernel<false><<<grid, kWalkWarps * 32, smem, st>>>(P);
+            }
+            ++g_launches;
+            CUDA_TRY(cudaGetLastError());
+        }
+        if (!emit) {
+            std::vector<uint64_t> h(8 * n);
+            CUDA_TRY(cudaMemcpyAsync(h.data(), d_cnt.p, 8 * n * 8, cudaMemcpyDeviceToHost, st));
             CUDA_TRY(cudaStreamSynchronize(st));
-            // a chain that starts at a true list start only ever stops at true list starts: walk the chains in file
-            // order, trusting a start only once its predecessor has landed on it
-            bool changed = false;
-            std::vector<uint64_t> good;
-            for (uint64_t i = 0; i < nc;) {
-                good.push_back(sync[i]);
-                const uint32_t status = uint32_t(counts[4 * i + 3] & 0xFF);
-                const uint64_t reached = counts[4 * i + 3] >> 8;
-                if (status == WALK_MALFORMED) {
-                    dint::set_error("vroom .bin: malformed list (device walk), chain at byte " + std::to_string(sync[i]));
+            for (uint64_t k = 0; k < n; ++k) {
+                chain& c = chains[ids[k]];
+                c.lists = h[8 * k];
+                c.ints = h[8 * k + 1];
+                c.units = h[8 * k + 2];
+                c.status = uint32_t(h[8 * k + 3] & 0xFF);
+                c.reached = h[8 * k + 3] >> 8;
+                c.counted = true;
+            }
+        } else {
+            CUDA_TRY(cudaStreamSynchronize(st));
+        }
+        return DINT_OK;
+    };
+
+    try {
+        // ---- count pass + repair rounds ------------------------------------------------------------------------------
+        // Every candidate start gets a chain that runs to the next candidate. A chain that starts at a true list start
+        // only ever stops at true list starts, so the file is then re-linked from byte 0: chain -> where it stopped ->
+        // the chain that starts there. A stop that no chain starts at (its target was a wrong guess of the speculative
+        // search, or a wrong hint) becomes a new chain, walked in the next round; chains nobody lands on are dropped.
+        if (in_bytes == 0) sync.clear();
+        std::vector<chain> chains;
+        chains.reserve(sync.size() + 64);
+        for (size_t i = 0; i < sync.size(); ++i) {
+            const uint64_t e = i + 1 < sync.size() ? sync[i + 1] : uint64_t(in_bytes);
+            chains.push_back(chain{sync[i], e, 0, 0, 0, 0, 0, e - sync[i] > kLongChain, false});
+        }
+        std::vector<uint32_t> todo(chains.size());
+        for (size_t i = 0; i < chains.size(); ++i) todo[i] = uint32_t(i);
+        std::vector<uint32_t> linked;  // the chains of the file, in order
+        for (uint32_t round = 0;; ++round) {
+            rc = run_pass(chains, todo, false, nullptr);
+            if (rc) return rc;
+            todo.clear();
+            // index of the chain that starts at a given byte: candidates are sorted by start, repairs are appended
+            std::vector<std::pair<uint64_t, uint32_t>> by_start(chains.size());
+            for (size_t i = 0; i < chains.size(); ++i) by_start[i] = {chains[i].start, uint32_t(i)};
+            std::sort(by_start.begin(), by_start.end());
+            auto find = [&](uint64_t off) -> int64_t {
+                auto it = std::lower_bound(by_start.begin(), by_start.end(), std::make_pair(off, uint32_t(0)));
+                return it != by_start.end() && it->first == off ? int64_t(it->second) : -1;
+            };
+            auto next_start = [&](uint64_t off) -> uint64_t {  // first candidate start > off
+                auto it = std::upper_bound(by_start.begin(), by_start.end(), std::make_pair(off, ~uint32_t(0)));
+                return it != by_start.end() ? it->first : uint64_t(in_bytes);
+            };
+            // every overshoot points at a list start nobody covers yet (if the chain itself is a true one): repair all
+            // of them in one round, not only the first one met from byte 0
+            for (size_t i = 0; i < chains.size(); ++i) {
+                const chain& c = chains[i];
+                if (c.counted && c.status == WALK_OVERSHOOT && c.reached < in_bytes && find(c.reached) < 0) {
+                    const uint64_t e = next_start(c.reached);
+                    chains.push_back(chain{c.reached, e, 0, 0, 0, 0, 0, true, false});
+                    by_start.insert(std::upper_bound(by_start.begin(), by_start.end(), std::make_pair(c.reached, uint32_t(0))),
+                                    {c.reached, uint32_t(chains.size() - 1)});
+                    todo.push_back(uint32_t(chains.size() - 1));
+                }
+            }
+            if (!todo.empty()) {
+                if (round >= 64) {
+                    dint::set_error("vroom .bin: the device walk did not converge");
                     return DINT_E_FORMAT;
                 }
-                if (status == WALK_OK) {
-                    ++i;
-                    continue;
-                }
-                // overshoot: the sync points this chain ran over are not list starts; where it stopped is one
-                changed = true;
-                uint64_t j = i + 1;
-                while (j < nc && sync[j] < reached) ++j;
-                if (j < nc && sync[j] == reached) {  // it landed on a later sync point: that one is a list start
-                    i = j;
-                    continue;
-                }
-                // nothing is known about the points behind `reached` until a chain that starts there has run
-                if (reached < in_bytes) good.push_back(reached);
-                for (; j < nc; ++j) good.push_back(sync[j]);
-                break;
+                ++plan->retries;
+                continue;
             }
-            if (!changed) break;
-            if (attempt >= 16) {  // give up on speculation: one chain
-                good.assign(1, 0);
+            // link from byte 0
+            linked.clear();
+            uint64_t off = 0;
+            bool complete = true;
+            while (off < in_bytes) {
+                const int64_t i = find(off);
+                if (i < 0) {  // cannot happen after the repairs above; be safe
+                    chains.push_back(chain{off, next_start(off), 0, 0, 0, 0, 0, true, false});
+                    todo.push_back(uint32_t(chains.size() - 1));
+                    complete = false;
+                    break;
+                }
+                const chain& c = chains[size_t(i)];
+                if (c.status == WALK_MALFORMED || c.status == WALK_TABLE_FULL || c.reached <= off) {
+                    dint::set_error("vroom .bin: malformed list (device walk), chain at byte " + std::to_string(off));
+                    return DINT_E_FORMAT;
+                }
+                linked.push_back(uint32_t(i));
+                off = c.reached;
             }
-            std::sort(good.begin(), good.end());
-            good.erase(std::unique(good.begin(), good.end()), good.end());
-            sync.swap(good);
+            if (complete) break;
+            if (round >= 64) {
+                dint::set_error("vroom .bin: the device walk did not converge");
+                return DINT_E_FORMAT;
+            }
             ++plan->retries;
         }
-        // ---- bases of every chain (host: a few thousand additions) ----------------------------------------------
-        const uint64_t nc = sync.size();
-        std::vector<uint64_t> bases(nc * 4 + 4, 0);
+        CUDA_TRY(cudaEventRecord(evc, st));
+        // ---- bases of every linked chain (host: one pass over the chain totals) ---------------------------------------
+        std::vector<uint64_t> bases(chains.size() * 4 + 4, 0);
         uint64_t lists = 0, ints = 0, units = 0;
-        for (uint64_t i = 0; i < nc; ++i) {
-            bases[4 * i] = lists;
-            bases[4 * i + 1] = ints;
-            bases[4 * i + 2] = units;
-            lists += counts[4 * i];
-            ints += counts[4 * i + 1];
-            units += counts[4 * i + 2];
+        for (uint32_t i : linked) {
+            chain& c = chains[i];
+            c.end = c.reached;  // the emit pass stops exactly where the count pass did
+            bases[4 * size_t(i)] = lists;
+            bases[4 * size_t(i) + 1] = ints;
+            bases[4 * size_t(i) + 2] = units;
+            lists += c.lists;
+            ints += c.ints;
+            units += c.units;
         }
         plan->n_lists = lists;
         plan->n_ints = ints;
         plan->n_units = units;
-        plan->n_chains = nc;
+        plan->n_chains = linked.size();
         CUDA_TRY(cudaMalloc(&plan->d_units, (units + 1) * sizeof(dint_strip_unit)));
         CUDA_TRY(cudaMalloc(&plan->d_list_offsets, (lists + 1) * 8));
         CUDA_TRY(cudaMalloc(&plan->d_list_byte_offsets, (lists + 1) * 8));
-        if (nc) {
-            dev_buf d_bases;
-            CUDA_TRY(cudaMalloc(&d_bases.p, nc * 32));
-            CUDA_TRY(cudaMemcpyAsync(d_bases.p, bases.data(), nc * 32, cudaMemcpyHostToDevice, st));
-            CUDA_TRY(cudaMemsetAsync(d_status.p, 0, 16, st));
-            P.bases = d_bases.as<uint64_t>();
+        if (!linked.empty()) {
             P.units = plan->d_units;
             P.units_cap = units;
             P.list_offsets = plan->d_list_offsets;
             P.list_byte_offsets = plan->d_list_byte_offsets;
-            int grid = 0;
-            size_t smem = 0;
-            rc = walk_grid(vroom_walk_kernel<true>, d, kWalkWarps, nc, &grid, &smem);
+            rc = run_pass(chains, linked, true, &bases);
             if (rc) return rc;
-            vroom_walk_kernel<true><<<grid, kWalkWarps * 32, smem, st>>>(P);
-            ++g_launches;
-            CUDA_TRY(cudaGetLastError());
             uint32_t h_status = 0;
-            CUDA_TRY(cudaMemcpyAsync(&h_status, d_status.p, 4, cudaMemcpyDeviceToHost, st));
-            CUDA_TRY(cudaStreamSynchronize(st));
+            CUDA_TRY(cudaMemcpy(&h_status, d_status.p, 4, cudaMemcpyDeviceToHost));
             if (h_status != WALK_OK) {
                 dint::set_error("vroom .bin: the emit pass of the device walk disagrees with the count pass");
                 return DINT_E_FORMAT;
@@ -300,6 +418,9 @@ int dint_vroom_discover(const dint_dict* d, const uint8_t* d_in, size_t in_bytes
         CUDA_TRY(cudaEventRecord(ev1, st));
         CUDA_TRY(cudaStreamSynchronize(st));
         CUDA_TRY(cudaEventElapsedTime(&plan->discover_ms, ev0, ev1));
+        CUDA_TRY(cudaEventElapsedTime(&plan->phase_ms[0], ev0, evs));
+        CUDA_TRY(cudaEventElapsedTime(&plan->phase_ms[1], evs, evc));
+        CUDA_TRY(cudaEventElapsedTime(&plan->phase_ms[2], evc, ev1));
     } catch (const std::bad_alloc&) {
         return DINT_E_NOMEM;
     }

@@ -327,6 +327,9 @@ struct vroom_walk_params {
     uint32_t block_size, multi;
     const uint64_t* chain_start;  // n_chains + 1 byte offsets, the last one = in_bytes
     uint64_t n_chains;
+    const uint32_t* chain_ids;    // the chains this launch walks (long ones: a warp each, the others: a thread each)
+    uint64_t n_ids;
+    uint32_t strip_ints;          // thread walker: a strip also closes once it holds this many integers
     uint64_t* counts;             // [n_chains][4] {lists, ints, units, status | end offset << 8}: written by the count pass
     const uint64_t* bases;        // [n_chains][4] {first list, first int, first unit, -}: read by the emit pass
     dint_strip_unit* units;
@@ -350,7 +353,8 @@ __global__ void __launch_bounds__(512, 2) vroom_walk_kernel(const vroom_walk_par
     walk_init_input(ws, ring_s, P.in, P.in_bytes);
     __syncthreads();
     const uint64_t in_base = reinterpret_cast<uint64_t>(P.in);
-    for (uint64_t c = uint64_t(blockIdx.x) * n_warps + warp; c < P.n_chains; c += uint64_t(gridDim.x) * n_warps) {
+    for (uint64_t ci = uint64_t(blockIdx.x) * n_warps + warp; ci < P.n_ids; ci += uint64_t(gridDim.x) * n_warps) {
+        const uint64_t c = P.chain_ids[ci];
         const uint64_t start = P.chain_start[c], end = P.chain_start[c + 1];
         uint64_t list_base = 0, int_base = 0, unit_base = 0;
         if (EMIT) {
@@ -426,6 +430,233 @@ __global__ void __launch_bounds__(512, 2) vroom_walk_kernel(const vroom_walk_par
         }
     }
     cp_async_wait_all();
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
+// vroom .bin: one THREAD per chain — the reference's scalar walk (vroom_env/decode.cpp:139-150 over
+// dint_codecs.hpp:45-101 / 530-611) run by tens of thousands of threads at once, each on its own stretch of the
+// file between two sync points. One loop trip handles one token (a codeword, or the switch to the next block /
+// list), so the lanes of a warp stay in the same code whatever the lengths of their lists are.
+// ---------------------------------------------------------------------------------------------------------
+template <bool EMIT>
+__global__ void __launch_bounds__(256, 4) vroom_thread_walk_kernel(const vroom_walk_params P) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    walk_tables wt;
+    walk_setup(P.dv, P.sums, smem, wt);
+    __syncthreads();
+    const uint64_t t = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= P.n_ids) return;
+    const uint64_t c = P.chain_ids[t];
+    const uint64_t start = P.chain_start[c], end = P.chain_start[c + 1];
+    uint64_t list_base = 0, int_base = 0, slot = 0;
+    if (EMIT) {
+        list_base = P.bases[4 * c];
+        int_base = P.bases[4 * c + 1];
+        slot = P.bases[4 * c + 2];
+    }
+    const uint64_t in_base = reinterpret_cast<uint64_t>(P.in);
+    const uint64_t in_hi4 = (in_base + P.in_bytes + 3) & ~uint64_t(3);
+    // the 8 bytes at file offset q (zeros behind the end of the buffer), any alignment
+    auto load8 = [&](uint64_t q) -> uint64_t {
+        const uint64_t a = in_base + q, a4 = a & ~uint64_t(3);
+        const uint32_t sh = uint32_t(a & 3) * 8u;
+        const uint32_t w0 = a4 < in_hi4 ? __ldg(reinterpret_cast<const uint32_t*>(a4)) : 0u;
+        const uint32_t w1 = a4 + 4 < in_hi4 ? __ldg(reinterpret_cast<const uint32_t*>(a4 + 4)) : 0u;
+        const uint32_t w2 = a4 + 8 < in_hi4 ? __ldg(reinterpret_cast<const uint32_t*>(a4 + 8)) : 0u;
+        return (uint64_t(__funnelshift_r(w1, w2, sh)) << 32) | __funnelshift_r(w0, w1, sh);
+    };
+    // ---- unit packer (unit_packer's rules; the strip words of the open unit live in local memory) ----------
+    uint32_t words[DINT_UNIT_STRIPS];
+    bool open = false, overflow = false;
+    uint64_t u_in = 0, u_out = 0, closed = 0;
+    uint32_t u_base = 0, u_starts = 0, u_ints = 0, u_strips = 0, u_len = 0, u_flags = 0;
+    auto close_unit = [&]() {
+        if (!open) return;
+        if (EMIT) {
+            if (slot < P.units_cap) {
+                uint4* up = reinterpret_cast<uint4*>(P.units + slot);
+                up[0] = make_uint4(uint32_t(u_in), uint32_t(u_in >> 32), uint32_t(u_out), uint32_t(u_out >> 32));
+                up[1] = make_uint4(u_base, u_starts, u_len | (u_ints << 16), u_strips | (u_flags << 8));
+#pragma unroll
+                for (uint32_t k = 0; k < DINT_UNIT_STRIPS; k += 4) {
+                    uint4 w;
+                    w.x = k < u_strips ? words[k] : (u_ints << 13);
+                    w.y = k + 1 < u_strips ? words[k + 1] : (u_ints << 13);
+                    w.z = k + 2 < u_strips ? words[k + 2] : (u_ints << 13);
+                    w.w = k + 3 < u_strips ? words[k + 3] : (u_ints << 13);
+                    up[2 + k / 4] = w;
+                }
+            } else {
+                overflow = true;
+            }
+            ++slot;
+        }
+        ++closed;
+        open = false;
+    };
+    auto add_strip = [&](uint64_t in0, uint64_t in1, uint64_t out0, uint32_t n, uint32_t base, uint32_t sel, bool ls, bool run) {
+        if (open && (u_strips >= uint32_t(DINT_UNIT_STRIPS) || in1 - u_in > P.unit_bytes || u_ints + n > P.unit_ints || out0 != u_out + u_ints))
+            close_unit();
+        if (!open) {
+            u_in = in0;
+            u_out = out0;
+            u_base = base;
+            u_starts = u_ints = u_strips = u_len = u_flags = 0;
+            open = true;
+        }
+        if (EMIT) words[u_strips] = uint32_t(in0 - u_in) | (u_ints << 13) | (sel << 25);
+        if (u_strips && ls) u_starts |= 1u << u_strips;
+        if (run) u_flags |= DINT_UNIT_HAS_RUNS;
+        u_ints += n;
+        u_len = uint32_t(in1 - u_in);
+        ++u_strips;
+    };
+
+    uint64_t pos = start, lists = 0, ints = 0;
+    uint32_t status = WALK_OK;
+    uint32_t list_rem = 0, str_rem = 0;  // integers of the list behind the current stream / left in the current stream
+    uint32_t acc = 0;                    // sum(v + 1) of the list so far
+    bool first_block = false;
+    // current stream
+    uint32_t sel = 0, sb = 2, last_row = 0, hotlen_s = 0, group_s = 0, detail_s = 0, row_base = 0, lut_g = 0;
+    // open strip
+    uint64_t s_pos = 0, s_out = 0;
+    uint32_t s_acc = 0, s_ints = 0, cw = 0;
+    bool s_ls = false, s_run = false;
+    for (;;) {
+        if (str_rem == 0u) {
+            if (list_rem == 0u) {
+                // ---- between two lists: header::read (vroom_env/codecs.hpp:117-123) ---------------------------------
+                if (pos >= end) break;
+                const uint64_t h = load8(pos);
+                uint32_t n = 0, k = 0, ok = 0;
+                for (; k < 5u; ++k) {
+                    const uint32_t b = uint32_t(h >> (8u * k)) & 0xFFu;
+                    n += (b & 127u) << (7u * k);
+                    if (b & 128u) {
+                        ok = 1;
+                        break;
+                    }
+                }
+                uint32_t hdr = k + 1u;
+                if (ok) {  // universe: only its length matters here
+                    const uint64_t h2 = load8(pos + hdr);
+                    ok = 0;
+                    for (k = 0; k < 5u; ++k)
+                        if ((h2 >> (8u * k)) & 128u) {
+                            ok = 1;
+                            break;
+                        }
+                    hdr += k + 1u;
+                }
+                if (!ok || pos + hdr > P.in_bytes) {
+                    status = WALK_MALFORMED;
+                    break;
+                }
+                if (EMIT) {
+                    P.list_offsets[list_base + lists] = int_base + ints;
+                    if (P.list_byte_offsets) P.list_byte_offsets[list_base + lists] = pos;
+                }
+                ++lists;
+                pos += hdr;
+                list_rem = n;
+                acc = 0;
+                first_block = true;
+                if (n == 0u) continue;
+            }
+            // ---- next stream of the list: a multi block behind its selector byte, or the whole single list -------
+            uint32_t size = list_rem;
+            sel = 0;
+            if (P.multi) {
+                size = min(size, P.block_size);
+                sel = uint32_t(load8(pos)) & 0xFFu;
+                if (pos >= P.in_bytes || sel >= 2u * dint::kSelectors || (sel % dint::kSelectors) >= wt.n_classes) {
+                    status = WALK_MALFORMED;
+                    break;
+                }
+                ++pos;
+            }
+            const bool narrow = sel >= dint::kSelectors;
+            const walk_class wc = load_walk_class(wt, narrow ? sel - dint::kSelectors : sel);
+            hotlen_s = wc.hotlen_s;
+            group_s = wc.group_s;
+            detail_s = wc.detail_s;
+            row_base = wc.row_base;
+            lut_g = wc.lut_g_off;
+            last_row = (narrow ? min(wc.rows, 256u) : wc.rows) - 1u;
+            sb = narrow ? 1u : 2u;
+            list_rem -= size;
+            str_rem = size;
+            s_pos = pos;
+            s_out = int_base + ints;
+            s_acc = acc;
+            s_ints = 0;
+            cw = 0;
+            s_ls = first_block;
+            s_run = false;
+            first_block = false;
+        }
+        // ---- one codeword ----------------------------------------------------------------------------------------
+        const uint64_t bits = load8(pos);
+        const uint32_t sym = uint32_t(bits) & (sb == 1u ? 0xFFu : 0xFFFFu);
+        uint32_t len = 1, sv, step = sb;
+        if (sym < 2u) {
+            uint32_t pay = uint32_t(bits >> (8u * sb));
+            if (sym == 0u) pay &= 0xFFFFu;
+            sv = pay + 1u;
+            step += 2u + 2u * sym;
+        } else {
+            if (sym > last_row) {
+                status = WALK_MALFORMED;
+                break;
+            }
+            uint32_t code;
+            if (sym < wt.hot_rows) {
+                code = lds_u8(hotlen_s + sym);
+            } else {
+                code = lds_u8(group_s + (sym >> 5));
+                if (code > 8u) {
+                    if (code != 0xFFu) code = lds_u8(detail_s + ((code - 9u) << 4) + ((sym & 31u) >> 1));
+                    else code = __ldg(wt.lens_cls + lut_g + (sym >> 1));
+                    code = (code >> ((sym & 1u) << 2)) & 15u;
+                }
+            }
+            len = 1u << code;
+            sv = __ldg(wt.sums + row_base + sym);
+            s_run = s_run || sym < dint::kReserved;
+        }
+        pos += step;
+        if (len > str_rem || pos > P.in_bytes) {  // entries must tile the stream exactly (`i != n` loop)
+            status = WALK_MALFORMED;
+            break;
+        }
+        acc += sv;
+        str_rem -= len;
+        s_ints += len;
+        ints += len;
+        ++cw;
+        if (str_rem == 0u || cw >= P.strip_cw || s_ints >= P.strip_ints) {
+            add_strip(s_pos, pos, s_out, s_ints, s_acc, sel, s_ls, s_run);
+            s_pos = pos;
+            s_out += s_ints;
+            s_acc = acc;
+            s_ints = 0;
+            cw = 0;
+            s_ls = s_run = false;
+        }
+    }
+    close_unit();
+    if (status == WALK_OK && pos != end) status = WALK_OVERSHOOT;
+    if (status == WALK_OK && overflow) status = WALK_TABLE_FULL;
+    if (!EMIT) {
+        P.counts[4 * c] = lists;
+        P.counts[4 * c + 1] = ints;
+        P.counts[4 * c + 2] = closed;
+        P.counts[4 * c + 3] = uint64_t(status) | (pos << 8);
+    } else if (status != WALK_OK || lists != P.counts[4 * c] || ints != P.counts[4 * c + 1] || closed != P.counts[4 * c + 2]) {
+        atomicMax(P.status, status ? status : uint32_t(WALK_MALFORMED));
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -151,6 +151,7 @@ struct dint_device_plan {
     uint64_t* d_list_offsets = nullptr;       // n_lists + 1 (vroom plans only)
     uint64_t* d_list_byte_offsets = nullptr;  // n_lists + 1 (vroom plans only)
     float discover_ms = 0.f;                  // device timeline of the discovery (CUDA events)
+    float phase_ms[3] = {0.f, 0.f, 0.f};      // sync search, count pass(es), emit pass
     uint32_t retries = 0;                     // count passes repeated because a speculative sync point was wrong
     uint64_t n_sync_found = 0;                // sync points the speculative search contributed
 };

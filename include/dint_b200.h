@@ -243,6 +243,7 @@ uint64_t dint_device_plan_num_chains(const dint_device_plan* p);
 uint64_t dint_device_plan_num_sync_found(const dint_device_plan* p); /* list starts the speculative search contributed */
 uint32_t dint_device_plan_retries(const dint_device_plan* p);        /* count passes repeated after a wrong sync point */
 double dint_device_plan_discover_ms(const dint_device_plan* p);      /* device timeline of the discovery, CUDA events */
+double dint_device_plan_phase_ms(const dint_device_plan* p, int phase); /* 0 sync search, 1 count pass(es), 2 emit pass */
 /* DEVICE pointers owned by the plan: num_units strip units (input of dint_decode_strips); num_lists + 1
  * offsets into the packed output / into the file (vroom plans only, NULL for index plans) */
 const dint_strip_unit* dint_device_plan_units(const dint_device_plan* p);

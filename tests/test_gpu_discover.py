@@ -45,7 +45,8 @@ def test_vroom_without_host_plan(golden, type_, part, raw_key, fused_key, mode, 
         assert vf.dplan.n_chains == 1 and vf.dplan.n_sync_found == 0
     elif stride:
         assert vf.dplan.n_chains > 8  # the speculative search found list starts to cut the file at
-    assert vf.dplan.retries == 0
+    # a speculative sync point may be wrong (it then costs a repair round of a few chains), never the result
+    assert vf.dplan.retries <= 3
 
 
 @pytest.mark.parametrize("type_", g.TYPES)
