@@ -125,6 +125,7 @@ int dint_vroom_discover(const dint_dict* d, const uint8_t* d_in, size_t in_bytes
 
     // ---- chain starts: byte 0, the caller's list starts, and what the speculative search finds ---------------
     std::vector<uint64_t> sync;
+    uint64_t used_stride = 0;
     try {
         sync.push_back(0);
         for (size_t i = 0; i < n_sync; ++i)
@@ -133,6 +134,7 @@ int dint_vroom_discover(const dint_dict* d, const uint8_t* d_in, size_t in_bytes
             // default: about one chain per resident walking THREAD (1024 per SM), never closer than 4 KB
             uint64_t stride = sync_stride ? sync_stride : std::max<uint64_t>(4096, in_bytes / (uint64_t(di.sms) * 1024));
             stride = std::max<uint64_t>(stride, 1024);
+            used_stride = stride;
             const uint64_t n_targets = (in_bytes - 1) / stride;
             if (n_targets) {
                 dev_buf found;
@@ -196,7 +198,8 @@ int dint_vroom_discover(const dint_dict* d, const uint8_t* d_in, size_t in_bytes
     // One chain = one candidate list start + where the walk from it has to stop. Chains up to kLongChain bytes are
     // walked by one thread each, longer ones (stretches without a sync point: very long lists) and the few chains of a
     // repair round by one warp each. A chain keeps its walker: the two passes must pack its units identically.
-    constexpr uint64_t kLongChain = 96 * 1024;
+    // (measured: a thread walks ~2-3 KB/ms, a warp ~7 KB/ms, and the longest chain of either kind bounds the pass)
+    const uint64_t kLongChain = std::max<uint64_t>(32 * 1024, std::min<uint64_t>(2 * used_stride, 96 * 1024));
     struct chain {
         uint64_t start, end;             // walk from start to the first list start >= end
         uint64_t lists, ints, units, reached;
@@ -250,7 +253,7 @@ int dint_vroom_discover(const dint_dict* d, const uint8_t* d_in, size_t in_bytes
         if (n_short) {
             P.chain_ids = d_order.as<uint32_t>();
             P.n_ids = n_short;
-            const size_t smem = walk_smem(d, 0);
+            const size_t smem = walk_smem(d, 0) + (emit ? walk_hotsum_bytes(d->view()) : 0);
             const int grid = int((n_short + 255) / 256);
             if (emit) {
                 CUDA_TRY(cudaFuncSetAttribute(vroom_thread_walk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));

@@ -60,6 +60,7 @@ struct walk_tables {
     uint32_t classes_s;
     uint32_t hot_rows;
     uint32_t n_classes;
+    uint32_t hotsum_s;  // shared address of sum(v + 1) of the hot rows, [n_classes][hot_rows] u32 (0: not staged)
     const uint8_t* lens_cls;
     const uint32_t* sums;
 };
@@ -67,8 +68,10 @@ struct walk_tables {
 // the part of the strip decoder's shared-memory image that holds lengths (everything behind hot0 / hot1)
 __host__ __device__ inline uint32_t walk_tables_skip(const dint_dict_view& dv) { return 2u * dv.n_classes * dv.hot_rows * 16u; }
 __host__ __device__ inline uint32_t walk_tables_bytes(const dint_dict_view& dv) { return dv.strip_tables_bytes - walk_tables_skip(dv); }
+__host__ __device__ inline uint32_t walk_hotsum_bytes(const dint_dict_view& dv) { return dv.n_classes * dv.hot_rows * 4u; }
 
 // Stages the length tables + class table at smem; returns the first free byte (16-byte aligned).
+template <bool HOTSUMS = false>
 __device__ __forceinline__ uint8_t* walk_setup(const dint_dict_view& dv, const uint32_t* sums, uint8_t* smem, walk_tables& wt) {
     const uint32_t skip = walk_tables_skip(dv), bytes = dv.strip_tables_bytes - skip;
     const uint4* src = reinterpret_cast<const uint4*>(dv.strip_tables + skip);
@@ -91,7 +94,18 @@ __device__ __forceinline__ uint8_t* walk_setup(const dint_dict_view& dv, const u
     wt.n_classes = dv.n_classes;
     wt.lens_cls = dv.lens_cls;
     wt.sums = sums;
-    return smem + bytes + kWalkClassBytes;
+    wt.hotsum_s = 0;
+    uint8_t* next = smem + bytes + kWalkClassBytes;
+    if (HOTSUMS) {
+        uint32_t* hs = reinterpret_cast<uint32_t*>(next);
+        for (uint32_t i = threadIdx.x; i < dv.n_classes * dv.hot_rows; i += blockDim.x) {
+            const uint32_t c = i / dv.hot_rows, r = i % dv.hot_rows;
+            hs[i] = r < dv.class_rows[c] ? __ldg(sums + dv.class_base[c] + r) : 0u;
+        }
+        wt.hotsum_s = smem_u32(hs);
+        next += walk_hotsum_bytes(dv);
+    }
+    return next;
 }
 
 __device__ __forceinline__ walk_class load_walk_class(const walk_tables& wt, uint32_t cls) {
@@ -443,7 +457,7 @@ template <bool EMIT>
 __global__ void __launch_bounds__(256, 4) vroom_thread_walk_kernel(const vroom_walk_params P) {
     extern __shared__ __align__(16) uint8_t smem[];
     walk_tables wt;
-    walk_setup(P.dv, P.sums, smem, wt);
+    walk_setup<EMIT>(P.dv, P.sums, smem, wt);
     __syncthreads();
     const uint64_t t = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (t >= P.n_ids) return;
@@ -456,14 +470,39 @@ __global__ void __launch_bounds__(256, 4) vroom_thread_walk_kernel(const vroom_w
         slot = P.bases[4 * c + 2];
     }
     const uint64_t in_base = reinterpret_cast<uint64_t>(P.in);
-    const uint64_t in_hi4 = (in_base + P.in_bytes + 3) & ~uint64_t(3);
-    // the 8 bytes at file offset q (zeros behind the end of the buffer), any alignment
+    // The 32 bytes under the cursor live in registers (two aligned 16-byte loads); a codeword is served from them and
+    // a new 16-byte piece is fetched only when the cursor leaves the window: every lane reads its own stretch of
+    // the file, so loads per codeword are what bounds this kernel (each one is a sector of its own).
+    const uint64_t in_hi16 = (in_base + P.in_bytes + 15) & ~uint64_t(15);
+    uint4 wlo = make_uint4(0, 0, 0, 0), whi = make_uint4(0, 0, 0, 0);
+    uint64_t wbase = ~uint64_t(0) - 64;  // absolute address of wlo (16-byte aligned)
+    auto ld16 = [&](uint64_t a) -> uint4 {
+        return a < in_hi16 ? __ldg(reinterpret_cast<const uint4*>(a)) : make_uint4(0, 0, 0, 0);
+    };
+    // the 8 bytes at file offset q (whatever follows the file reads as the bytes of its last 16-byte piece, then
+    // zeros; positions are checked against in_bytes by the caller), any alignment
     auto load8 = [&](uint64_t q) -> uint64_t {
-        const uint64_t a = in_base + q, a4 = a & ~uint64_t(3);
-        const uint32_t sh = uint32_t(a & 3) * 8u;
-        const uint32_t w0 = a4 < in_hi4 ? __ldg(reinterpret_cast<const uint32_t*>(a4)) : 0u;
-        const uint32_t w1 = a4 + 4 < in_hi4 ? __ldg(reinterpret_cast<const uint32_t*>(a4 + 4)) : 0u;
-        const uint32_t w2 = a4 + 8 < in_hi4 ? __ldg(reinterpret_cast<const uint32_t*>(a4 + 8)) : 0u;
+        const uint64_t a = in_base + q;
+        if (a - wbase >= 24u) {  // also true for a < wbase (wraps)
+            if (a - wbase < 40u) {  // the usual step: slide by one piece
+                wlo = whi;
+                wbase += 16;
+                whi = ld16(wbase + 16);
+            } else {
+                wbase = a & ~uint64_t(15);
+                wlo = ld16(wbase);
+                whi = ld16(wbase + 16);
+            }
+        }
+        const uint32_t idx = uint32_t(a - wbase);  // 0..23
+        const bool up = idx >= 16u;
+        const uint32_t a0 = up ? whi.x : wlo.x, a1 = up ? whi.y : wlo.y, a2 = up ? whi.z : wlo.z, a3 = up ? whi.w : wlo.w;
+        const uint32_t a4 = up ? 0u : whi.x, a5 = up ? 0u : whi.y;
+        const uint32_t j = (idx >> 2) & 3u;
+        const uint32_t w0 = j == 0u ? a0 : j == 1u ? a1 : j == 2u ? a2 : a3;
+        const uint32_t w1 = j == 0u ? a1 : j == 1u ? a2 : j == 2u ? a3 : a4;
+        const uint32_t w2 = j == 0u ? a2 : j == 1u ? a3 : j == 2u ? a4 : a5;
+        const uint32_t sh = (idx & 3u) * 8u;
         return (uint64_t(__funnelshift_r(w1, w2, sh)) << 32) | __funnelshift_r(w0, w1, sh);
     };
     // ---- unit packer (unit_packer's rules; the strip words of the open unit live in local memory) ----------
@@ -519,7 +558,7 @@ __global__ void __launch_bounds__(256, 4) vroom_thread_walk_kernel(const vroom_w
     uint32_t acc = 0;                    // sum(v + 1) of the list so far
     bool first_block = false;
     // current stream
-    uint32_t sel = 0, sb = 2, last_row = 0, hotlen_s = 0, group_s = 0, detail_s = 0, row_base = 0, lut_g = 0;
+    uint32_t sel = 0, sb = 2, last_row = 0, hotlen_s = 0, group_s = 0, detail_s = 0, row_base = 0, lut_g = 0, hotsum_s = 0;
     // open strip
     uint64_t s_pos = 0, s_out = 0;
     uint32_t s_acc = 0, s_ints = 0, cw = 0;
@@ -584,6 +623,7 @@ __global__ void __launch_bounds__(256, 4) vroom_thread_walk_kernel(const vroom_w
             detail_s = wc.detail_s;
             row_base = wc.row_base;
             lut_g = wc.lut_g_off;
+            hotsum_s = wt.hotsum_s + (narrow ? sel - dint::kSelectors : sel) * wt.hot_rows * 4u;
             last_row = (narrow ? min(wc.rows, 256u) : wc.rows) - 1u;
             sb = narrow ? 1u : 2u;
             list_rem -= size;
@@ -600,7 +640,7 @@ __global__ void __launch_bounds__(256, 4) vroom_thread_walk_kernel(const vroom_w
         // ---- one codeword ----------------------------------------------------------------------------------------
         const uint64_t bits = load8(pos);
         const uint32_t sym = uint32_t(bits) & (sb == 1u ? 0xFFu : 0xFFFFu);
-        uint32_t len = 1, sv, step = sb;
+        uint32_t len = 1, sv = 0, step = sb;
         if (sym < 2u) {
             uint32_t pay = uint32_t(bits >> (8u * sb));
             if (sym == 0u) pay &= 0xFFFFu;
@@ -623,7 +663,8 @@ __global__ void __launch_bounds__(256, 4) vroom_thread_walk_kernel(const vroom_w
                 }
             }
             len = 1u << code;
-            sv = __ldg(wt.sums + row_base + sym);
+            // the docID prefix is only stored by the emit pass; hot rows have their sums in shared memory
+            if (EMIT) sv = sym < wt.hot_rows ? lds_u32(hotsum_s + (sym << 2)) : __ldg(wt.sums + row_base + sym);
             s_run = s_run || sym < dint::kReserved;
         }
         pos += step;
