@@ -305,14 +305,16 @@ struct bit_reader {
 };
 
 // pre-order walk of read_interpolative (:124-146) with an explicit stack; emit(idx, val)
-// `stack`: this thread's 10 x uint4 of shared memory (depth <= 8 for n <= 255)
+// `stack`: this thread's column of a level-major shared-memory stack (entry k at stack[k * stride]; depth <= 8 for
+// n <= 255), so that the lanes of a warp, which push and pop in lock step, hit consecutive 16-byte slots
 template <typename Emit>
-__device__ void read_interpolative(bit_reader& br, uint32_t n, uint32_t low0, uint32_t high0, uint4* stack, Emit&& emit) {
+__device__ void read_interpolative(bit_reader& br, uint32_t n, uint32_t low0, uint32_t high0, uint4* stack, uint32_t stride,
+                                   Emit&& emit) {
     int sp = 1;
     stack[0] = make_uint4(0u, n, low0, high0);
     while (sp) {
         --sp;
-        const uint4 e = stack[sp];
+        const uint4 e = stack[sp * stride];
         uint32_t off = e.x, cnt = e.y, lo = e.z, hi = e.w;
         for (;;) {
             uint32_t h = cnt / 2;
@@ -321,7 +323,7 @@ __device__ void read_interpolative(bit_reader& br, uint32_t n, uint32_t low0, ui
             if (cnt == 1) break;
             uint32_t rn = cnt - h - 1;
             if (rn) {  // right half later
-                stack[sp] = make_uint4(off + h + 1, rn, val, hi);
+                stack[sp * stride] = make_uint4(off + h + 1, rn, val, hi);
                 ++sp;
             }
             if (!h) break;
@@ -341,70 +343,109 @@ __device__ __forceinline__ uint32_t vbyte_at(const uint8_t* base, uint64_t nbyte
     return v;
 }
 
+// One thread per partial block. A WARP takes kTailChunk consecutive entries of the block table (neighbouring lists:
+// their bytes and their outputs are neighbours too, which keeps the accesses of a warp inside a few KB), sorts the
+// partial blocks among them by size in shared memory (warp-local counting sort, no CTA barrier), and its lanes take
+// them in that order: the 32 lanes then decode tails of (nearly) the same length, whose interpolative trees have the
+// same shape, so the warp runs in lock step instead of waiting for its longest tail (tails hold 1..255 postings).
+// The freqs prefix sums of a tail stay in the thread's local memory until their adjacent differences are taken
+// (lanes in lock step touch the same element index: one 128-byte line per access), so nothing is read back from
+// global memory.
 constexpr int kTailThreads = 128;
+constexpr int kTailChunk = 256;
+struct tail_warp_smem {
+    unsigned int bins[257];
+    uint8_t order[kTailChunk];
+    uint8_t sizes[kTailChunk];
+};
 __global__ void __launch_bounds__(kTailThreads)
 index_tails_kernel(const uint8_t* __restrict__ lists, uint64_t lists_bytes, const dint_block* __restrict__ blocks,
                    uint64_t n_blocks, uint32_t block_size, uint32_t* __restrict__ docids, uint32_t* __restrict__ freqs) {
     __shared__ uint4 stacks[kTailThreads * 10];
-    uint4* stack = stacks + threadIdx.x * 10;
+    __shared__ tail_warp_smem wsm[kTailThreads / 32];
+    uint4* stack = stacks + threadIdx.x;  // level-major: entry k at stack[k * kTailThreads]
+    tail_warp_smem& W = wsm[threadIdx.x >> 5];
     const unsigned lane = threadIdx.x & 31u;
-    const uint64_t step = uint64_t(gridDim.x) * blockDim.x;
-    // warp-uniform trip count: the adjacent-difference pass at the end of a trip is done by the whole warp
-    for (uint64_t i0 = uint64_t(blockIdx.x) * blockDim.x + (threadIdx.x & ~31u); i0 < n_blocks; i0 += step) {
-        const uint64_t i = i0 + lane;
-        dint_block b;
-        b.size = block_size;  // lanes past the end / full blocks: nothing to do
-        if (i < n_blocks) b = blocks[i];
-        const bool tail = i < n_blocks && b.size < block_size;
-        const uint32_t n = tail ? b.size : 0u;
-        if (tail) {
-            uint64_t p = b.in_off;
+    uint32_t P[256];  // freqs prefix sums of the tail in hand (local memory)
+    const uint64_t n_chunks = (n_blocks + kTailChunk - 1) / kTailChunk;
+    const uint64_t n_warps = (uint64_t(gridDim.x) * blockDim.x) >> 5;
+    for (uint64_t c = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; c < n_chunks; c += n_warps) {
+        const uint64_t base = c * kTailChunk;
+        const uint32_t cn = uint32_t(min(uint64_t(kTailChunk), n_blocks - base));
+        // ---- counting sort of the chunk's partial blocks by size (descending) -------------------------------------
+        __syncwarp();
+        for (uint32_t t = lane; t < 257u; t += 32u) W.bins[t] = 0;
+        __syncwarp();
+        for (uint32_t t = lane; t < cn; t += 32u) {
+            uint32_t n = blocks[base + t].size;
+            if (n >= block_size || n > 255u) n = 0;  // full blocks are DINT coded (strips / tiles)
+            W.sizes[t] = uint8_t(n);
+            if (n) atomicAdd(&W.bins[255u - n], 1u);
+        }
+        __syncwarp();
+        {
+            unsigned int v[8], sum = 0;
+            for (int q = 0; q < 8; ++q) {
+                v[q] = W.bins[lane * 8 + q];
+                sum += v[q];
+            }
+            const unsigned int incl = warp_inclusive_scan(sum);
+            unsigned int acc = incl - sum;
+            __syncwarp();
+            for (int q = 0; q < 8; ++q) {
+                W.bins[lane * 8 + q] = acc;
+                acc += v[q];
+            }
+            if (lane == 31) W.bins[256] = incl;
+        }
+        __syncwarp();
+        const uint32_t n_tails = W.bins[256];
+        for (uint32_t t = lane; t < cn; t += 32u) {
+            const uint32_t n = W.sizes[t];
+            if (n) W.order[atomicAdd(&W.bins[255u - n], 1u)] = uint8_t(t);
+        }
+        __syncwarp();
+        // ---- decode ------------------------------------------------------------------------------------------------
+        for (uint32_t k = lane; k < n_tails; k += 32u) {
+            const uint64_t i = base + W.order[k];
+            const uint4 b0 = __ldg(reinterpret_cast<const uint4*>(blocks + i));
+            const uint4 b1 = __ldg(reinterpret_cast<const uint4*>(blocks + i) + 1);
+            const uint32_t n = b1.x, cur_base = b1.y, block_max = b1.z;
+            uint64_t p = (uint64_t(b0.y) << 32) | b0.x;
+            const uint64_t out_off = (uint64_t(b0.w) << 32) | b0.z;
             // docs: prefix sums P_i of the first n-1 values in [0, S], P_{n-1} = S
             // (block_codecs.hpp:139-146); docid_i = cur_base + P_i + i (dict_posting_list.hpp:304-307,122)
-            const uint32_t S = b.block_max - b.cur_base - (n - 1u);
-            uint32_t* dd = docids ? docids + b.out_off : nullptr;
-            if (dd) dd[n - 1] = b.block_max;
+            const uint32_t S = block_max - cur_base - (n - 1u);
+            uint32_t* dd = docids ? docids + out_off : nullptr;
+            if (dd) dd[n - 1] = block_max;
             if (n > 1) {
                 bit_reader br;
                 br.init(lists, lists_bytes, p);
-                const uint32_t cb = b.cur_base;
-                read_interpolative(br, n - 1, 0, S, stack, [&](uint32_t idx, uint32_t val) {
-                    if (dd) dd[idx] = cb + val + idx;
+                read_interpolative(br, n - 1, 0, S, stack, kTailThreads, [&](uint32_t idx, uint32_t val) {
+                    if (dd) dd[idx] = cur_base + val + idx;
                 });
                 p += (br.pos + 7) / 8;
             }
-            if (freqs) {
-                // freqs: sum_of_values == -1 -> leading vbyte (block_codecs.hpp:134-136); prefix sums first
-                uint32_t* ff = freqs + b.out_off;
-                const uint32_t Sf = vbyte_at(lists, lists_bytes, p);
-                ff[n - 1] = Sf;
-                if (n > 1) {
-                    bit_reader br;
-                    br.init(lists, lists_bytes, p);
-                    read_interpolative(br, n - 1, 0, Sf, stack, [&](uint32_t idx, uint32_t val) { ff[idx] = val; });
-                }
+            if (!freqs) continue;
+            // freqs: sum_of_values == -1 -> leading vbyte (block_codecs.hpp:134-136); prefix sums first
+            uint32_t* ff = freqs + out_off;
+            const uint32_t Sf = vbyte_at(lists, lists_bytes, p);
+            if (n == 1) {
+                ff[0] = Sf + 1u;  // freq = v + 1 (dict_posting_list.hpp:168)
+                continue;
             }
-        }
-        if (!freqs) continue;
-        // adjacent differences, freq = v + 1 (block_codecs.hpp:147-149, dict_posting_list.hpp:168): the warp
-        // walks the 32 tails of this trip together, 32 values at a time from the back, instead of every
-        // thread running a serial read-modify-write loop over global memory
-        __syncwarp();
-        const uint32_t have = __ballot_sync(FULL, n > 0u);
-        for (uint32_t m = have; m; m &= m - 1u) {
-            const int k = __ffs(m) - 1;
-            const uint32_t kn = __shfl_sync(FULL, n, k);
-            uint32_t* ff = freqs + __shfl_sync(FULL, b.out_off, k);
-            for (int32_t c = int32_t((kn - 1u) / 32u); c >= 0; --c) {
-                const uint32_t j = uint32_t(c) * 32u + lane;
-                uint32_t v = 0, w = 0;
-                if (j < kn) {
-                    v = ff[j];
-                    w = j ? ff[j - 1] : 0u;
-                }
-                __syncwarp();
-                if (j < kn) ff[j] = v - w + 1u;
-                __syncwarp();
+            {
+                bit_reader br;
+                br.init(lists, lists_bytes, p);
+                read_interpolative(br, n - 1, 0, Sf, stack, kTailThreads, [&](uint32_t idx, uint32_t val) { P[idx] = val; });
+            }
+            // adjacent differences (block_codecs.hpp:147-149), freq = v + 1
+            P[n - 1] = Sf;
+            uint32_t prev = 0;
+            for (uint32_t j = 0; j < n; ++j) {
+                const uint32_t v = P[j];
+                ff[j] = v - prev + 1u;
+                prev = v;
             }
         }
     }
@@ -866,8 +907,10 @@ static int launch_index_tails(int device, const uint8_t* d_lists, size_t lists_b
     device_info di;
     int rc = get_device_info(device, &di);
     if (rc) return rc;
-    uint64_t want = (n_blocks + kTailThreads - 1) / kTailThreads;
-    int tgrid = int(std::max<uint64_t>(1, std::min<uint64_t>(want, uint64_t(di.sms) * 16)));
+    if (!n_blocks) return DINT_OK;
+    const uint64_t n_chunks = (n_blocks + kTailChunk - 1) / kTailChunk;  // one warp per chunk
+    const uint64_t want = (n_chunks + kTailThreads / 32 - 1) / (kTailThreads / 32);
+    int tgrid = int(std::max<uint64_t>(1, std::min<uint64_t>(want, uint64_t(di.sms) * 8)));
     index_tails_kernel<<<tgrid, kTailThreads, 0, st>>>(d_lists, lists_bytes, d_blocks, n_blocks, block_size, d_docids, d_freqs);
     ++g_launches;
     CUDA_TRY(cudaGetLastError());
@@ -891,7 +934,7 @@ int dint_decode_index(const dint_dict* docs_dict, const dint_dict* freqs_dict, c
     }
     if (docs_dict->device != freqs_dict->device || docs_dict->kind != freqs_dict->kind) return DINT_E_ARG;
     if (n_blocks == 0) return DINT_OK;
-    if (!d_lists || !d_blocks || (!d_docids && !d_freqs)) return DINT_E_ARG;
+    if (!d_lists || !d_blocks || (!d_docids && !d_freqs) || (reinterpret_cast<uintptr_t>(d_blocks) & 15)) return DINT_E_ARG;
     if (!block_size) block_size = dint::kDefaultBlock;
     if (!index_block_size_ok(block_size)) return DINT_E_ARG;
     device_guard g(docs_dict->device);
@@ -933,7 +976,7 @@ int dint_decode_index_planned(const dint_dict* docs_dict, const dint_dict* freqs
                               uint32_t* d_freqs, void* stream) {
     if (!docs_dict || !freqs_dict || !docs_plan || !freqs_plan) return DINT_E_ARG;
     if (n_blocks == 0) return DINT_OK;
-    if (!d_lists || !d_blocks || (!d_docids && !d_freqs)) return DINT_E_ARG;
+    if (!d_lists || !d_blocks || (!d_docids && !d_freqs) || (reinterpret_cast<uintptr_t>(d_blocks) & 15)) return DINT_E_ARG;
     if (!block_size) block_size = dint::kDefaultBlock;
     if (!index_block_size_ok(block_size)) return DINT_E_ARG;
     int rc;
