@@ -46,7 +46,7 @@ SYMBOLS = [
     "dint_device_plan_num_sync_found", "dint_device_plan_retries", "dint_device_plan_discover_ms", "dint_device_plan_phase_ms",
     "dint_device_plan_units", "dint_device_plan_list_offsets", "dint_device_plan_list_byte_offsets",
     "dint_decode_index_planned", "dint_vroom_ctx_create_discover", "dint_vroom_ctx_num_lists",
-    "dint_vroom_ctx_num_ints", "dint_vroom_ctx_device_plan", "dint_vroom_ctx_results",
+    "dint_vroom_ctx_num_ints", "dint_vroom_ctx_device_plan", "dint_vroom_ctx_results", "dint_and_queries",
 ]
 
 
@@ -140,6 +140,7 @@ def lib():
         L.dint_vroom_ctx_device_plan.argtypes = [vp]
         L.dint_vroom_ctx_device_plan.restype = vp
         L.dint_vroom_ctx_results.argtypes = [vp, vp, vp, vp]
+        L.dint_and_queries.argtypes = [vp, vp, sz, vp, vp, sz, vp, vp]
         _lib = L
     return _lib
 
@@ -421,6 +422,12 @@ def decode_index_planned(docs_dict, freqs_dict, d_lists_ptr, lists_bytes, docs_p
     check(lib().dint_decode_index_planned(docs_dict.handle, freqs_dict.handle, d_lists_ptr, lists_bytes, docs_plan.handle,
                                           freqs_plan.handle, d_blocks_ptr, n_blocks, block_size, d_docids_ptr, d_freqs_ptr,
                                           stream))
+
+
+def and_queries(d_docids_ptr, d_list_offsets_ptr, n_lists, d_query_offsets_ptr, d_query_terms_ptr, n_queries, d_counts_ptr, stream=0):
+    """ds2i::and_query over decoded docID lists in HBM: counts[q] = documents holding every term of query q"""
+    check(lib().dint_and_queries(d_docids_ptr, d_list_offsets_ptr, n_lists, d_query_offsets_ptr, d_query_terms_ptr, n_queries,
+                                 d_counts_ptr, stream))
 
 
 def checksum_lists(d_values_ptr, d_list_offsets_ptr, n_lists, d_sums_ptr, stream=0):

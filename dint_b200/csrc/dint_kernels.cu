@@ -515,6 +515,90 @@ checksum_kernel(const uint32_t* __restrict__ values, const uint64_t* __restrict_
     }
 }
 
+// ---- batched AND-intersection over decoded docID lists (ds2i::and_query, include/ds2i/queries.hpp:34-86) --------
+// One warp per query. Lane k holds term k's list (start, length); duplicates are dropped like
+// remove_duplicate_terms does (:29-32). The reference walks the shortest list and calls next_geq on the others in
+// order of increasing length (:48-72); here 32 docIDs of the shortest list are tested at once, each lane looking its
+// candidate up in the other lists (shortest first, so most candidates die early) by binary search — the lists are
+// sorted arrays in HBM once decoded. counts[q] = documents that hold every term; a term id >= n_lists makes it 0.
+constexpr uint32_t kMaxQueryTerms = 32;
+__global__ void __launch_bounds__(128)
+and_queries_kernel(const uint32_t* __restrict__ docids, const uint64_t* __restrict__ offs, uint64_t n_lists,
+                   const uint64_t* __restrict__ qoff, const uint32_t* __restrict__ qterms, uint64_t n_queries,
+                   unsigned long long* __restrict__ counts) {
+    const unsigned lane = lane_id();
+    const uint64_t gwarp = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = (uint64_t(gridDim.x) * blockDim.x) >> 5;
+    for (uint64_t q = gwarp; q < n_queries; q += nwarps) {
+        const uint64_t t0 = qoff[q], t1 = qoff[q + 1];
+        const uint32_t nt = uint32_t(min(t1 - t0, uint64_t(kMaxQueryTerms)));
+        if (t1 - t0 > kMaxQueryTerms || nt == 0u) {  // more terms than lanes: not supported (flagged), empty query: 0
+            if (lane == 0) counts[q] = nt ? ~0ull : 0ull;
+            continue;
+        }
+        const uint32_t term = lane < nt ? qterms[t0 + lane] : 0xFFFFFFFFu;
+        // drop duplicates (keep the first occurrence)
+        bool keep = lane < nt;
+        for (uint32_t k = 0; k + 1 < nt; ++k) {
+            const uint32_t other = __shfl_sync(FULL, term, int(k));
+            if (lane > k && other == term) keep = false;
+        }
+        const bool bad = __ballot_sync(FULL, keep && term >= n_lists) != 0u;
+        if (bad) {
+            if (lane == 0) counts[q] = 0;
+            continue;
+        }
+        uint64_t start = 0;
+        uint32_t len = 0xFFFFFFFFu;
+        if (keep) {
+            start = offs[term];
+            len = uint32_t(min(offs[term + 1] - start, uint64_t(0xFFFFFFFEu)));
+        }
+        // order the kept lists by increasing length: rank of every lane's list (ties by lane)
+        uint32_t rank = 0;
+        for (uint32_t k = 0; k < nt; ++k) {
+            const uint32_t ol = __shfl_sync(FULL, len, int(k));
+            if (ol < len || (ol == len && k < lane)) ++rank;
+        }
+        const uint32_t n_kept = __popc(__ballot_sync(FULL, keep));
+        // lane r now takes over the list of rank r
+        uint64_t s_start = 0;
+        uint32_t s_len = 0;
+        for (uint32_t k = 0; k < nt; ++k) {
+            const uint32_t kr = __shfl_sync(FULL, keep ? rank : 0xFFFFFFFFu, int(k));
+            const uint64_t ks = shfl64(start, int(k));
+            const uint32_t kl = __shfl_sync(FULL, len, int(k));
+            if (kr == lane) {
+                s_start = ks;
+                s_len = kl;
+            }
+        }
+        const uint64_t a_start = shfl64(s_start, 0);
+        const uint32_t a_len = __shfl_sync(FULL, s_len, 0);
+        unsigned long long total = 0;
+        for (uint32_t c0 = 0; c0 < a_len; c0 += 32u) {
+            const bool has = c0 + lane < a_len;
+            const uint32_t cand = has ? docids[a_start + c0 + lane] : 0u;
+            bool alive = has;
+            for (uint32_t j = 1; j < n_kept && __any_sync(FULL, alive); ++j) {
+                const uint64_t bs = shfl64(s_start, int(j));
+                const uint32_t bl = __shfl_sync(FULL, s_len, int(j));
+                if (alive) {  // lower bound of cand in list j
+                    uint32_t lo = 0, hi = bl;
+                    while (lo < hi) {
+                        const uint32_t mid = (lo + hi) >> 1;
+                        if (docids[bs + mid] < cand) lo = mid + 1;
+                        else hi = mid;
+                    }
+                    alive = lo < bl && docids[bs + lo] == cand;
+                }
+            }
+            total += __popc(__ballot_sync(FULL, alive));
+        }
+        if (lane == 0) counts[q] = total;
+    }
+}
+
 // ---- single-list walk for the host-buffer convenience call ----------------------------------
 __global__ void __launch_bounds__(32)
 decode_list_kernel(dint_dict_view dv, uint32_t lut_bytes, int multi, const uint8_t* __restrict__ in, uint64_t in_bytes,
@@ -1013,6 +1097,30 @@ int dint_checksum_lists(const uint32_t* d_values, const uint64_t* d_list_offsets
     int grid = di.sms * 8;
     checksum_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         d_values, d_list_offsets, n_lists, reinterpret_cast<unsigned long long*>(d_sums));
+    ++g_launches;
+    CUDA_TRY(cudaGetLastError());
+    return DINT_OK;
+}
+
+int dint_and_queries(const uint32_t* d_docids, const uint64_t* d_list_offsets, size_t n_lists, const uint64_t* d_query_offsets,
+                     const uint32_t* d_query_terms, size_t n_queries, uint64_t* d_counts, void* stream) {
+    if (n_queries == 0) return DINT_OK;
+    if (!d_docids || !d_list_offsets || !d_query_offsets || !d_query_terms || !d_counts) return DINT_E_ARG;
+    cudaPointerAttributes pa;
+    CUDA_TRY(cudaPointerGetAttributes(&pa, d_docids));
+    if (pa.type != cudaMemoryTypeDevice && pa.type != cudaMemoryTypeManaged) {
+        dint::set_error("dint_and_queries: d_docids is not device memory (no CPU fallback)");
+        return DINT_E_NODEVICE;
+    }
+    device_guard g(pa.device);
+    device_info di;
+    int rc = get_device_info(pa.device, &di);
+    if (rc) return rc;
+    const uint64_t want = (n_queries + 3) / 4;  // 4 warps per CTA, one query per warp
+    const int grid = int(std::max<uint64_t>(1, std::min<uint64_t>(want, uint64_t(di.sms) * 16)));
+    and_queries_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        d_docids, d_list_offsets, n_lists, d_query_offsets, d_query_terms, n_queries,
+        reinterpret_cast<unsigned long long*>(d_counts));
     ++g_launches;
     CUDA_TRY(cudaGetLastError());
     return DINT_OK;

@@ -290,6 +290,16 @@ int dint_decode_index_planned(const dint_dict* docs_dict, const dint_dict* freqs
 int dint_checksum_lists(const uint32_t* d_values, const uint64_t* d_list_offsets, size_t n_lists, uint64_t* d_sums,
                         void* stream);
 
+/* ---- a consumer on the device: batched AND queries over the decoded docIDs ------------------ */
+/* ds2i::and_query<false> (include/ds2i/queries.hpp:34-86; caller: src/queries.cpp:15-61) for a batch of queries over
+ * docID lists that are already decoded in HBM (DINT_MODE_DOCIDS output of any decode call above + its list
+ * offsets): counts[q] = number of documents that contain every term of query q. Queries in CSR form:
+ * d_query_terms[d_query_offsets[q] .. d_query_offsets[q + 1]) are term ids (= list indices; duplicates are dropped
+ * like remove_duplicate_terms does; at most 32 terms per query, else counts[q] = UINT64_MAX; a term id >= n_lists
+ * gives 0). One warp per query: 32 docIDs of the shortest list are looked up in the other lists at a time. */
+int dint_and_queries(const uint32_t* d_docids, const uint64_t* d_list_offsets, size_t n_lists, const uint64_t* d_query_offsets,
+                     const uint32_t* d_query_terms, size_t n_queries, uint64_t* d_counts, void* stream);
+
 /* ---- host-buffer convenience: one Decoder::decode(dict, in, out, universe, n) call ------ */
 /* in/out are HOST pointers; copies in, decodes on the device, copies out; *consumed is
  * the reference's returned pointer minus `in`. out receives exactly n integers (RAW). */

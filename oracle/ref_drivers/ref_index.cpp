@@ -12,6 +12,8 @@
 //   ref_index dict  <type> <collection_basename>            (only builds ./dict.* in CWD)
 //   ref_index dump  <type> <index.bin> <out_docs.u32> <out_freqs.u32>
 //   ref_index scan  <type> <index.bin> [repeat]      (CPU baseline: full enumerator scan)
+//   ref_index and   <type> <index.bin> <queries> [repeat]   (the reference's and_query<false> per query line:
+//                                                           prints one result count per query, then a JSON timing line)
 #include <cassert>
 #include <cstring>
 #include <fstream>
@@ -48,6 +50,10 @@ using multi_packed_dint_index = dict_freq_index<multi_packed_builder, opt_dint_m
 
 #include "util.hpp"
 #include "verify_collection.hpp"
+// include/ds2i/queries.hpp (and_query, read_query) pulls in include/index_types.hpp, which needs real Boost.PP and
+// every codec of the zoo; the three DINT aliases it would provide are declared above, so it is pre-empted here
+// (same include guard idiom: #pragma once files cannot be skipped, hence the empty stand-ins under oracle/shim/stubs).
+#include "queries.hpp"
 
 using namespace ds2i;
 
@@ -125,12 +131,36 @@ int scan(const char* bin, int repeat) {
 }
 
 template <typename Index>
+int and_queries(const char* bin, const char* qfile, int repeat) {
+    Index index;
+    boost::iostreams::mapped_file_source m(bin);
+    succinct::mapper::map(index, m);
+    std::vector<term_id_vec> queries;
+    {
+        std::ifstream in(qfile);
+        term_id_vec q;
+        while (read_query(q, in)) queries.push_back(q);
+    }
+    std::vector<uint64_t> counts(queries.size());
+    double best = 1e30;
+    for (int r = 0; r < std::max(repeat, 1); ++r) {
+        double t0 = get_time_usecs();
+        for (size_t i = 0; i < queries.size(); ++i) counts[i] = and_query<false>()(index, queries[i]);
+        best = std::min(best, (get_time_usecs() - t0) / 1e6);
+    }
+    for (uint64_t c : counts) std::cout << c << "\n";
+    std::cout << "{\"queries\": " << queries.size() << ", \"seconds\": " << best << "}" << std::endl;
+    return 0;
+}
+
+template <typename Index>
 int run(int argc, char** argv) {
     std::string mode = argv[1];
     if (mode == "build" && argc >= 5) return build<Index>(argv[3], argv[4]);
     if (mode == "dict" && argc >= 4) return dict_only<Index>(argv[3]);
     if (mode == "dump" && argc >= 6) return dump<Index>(argv[3], argv[4], argv[5]);
     if (mode == "scan" && argc >= 4) return scan<Index>(argv[3], argc > 4 ? atoi(argv[4]) : 1);
+    if (mode == "and" && argc >= 5) return and_queries<Index>(argv[3], argv[4], argc > 5 ? atoi(argv[5]) : 1);
     return 2;
 }
 
