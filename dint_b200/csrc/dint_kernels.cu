@@ -360,18 +360,20 @@ struct tail_warp_smem {
 };
 __global__ void __launch_bounds__(kTailThreads)
 index_tails_kernel(const uint8_t* __restrict__ lists, uint64_t lists_bytes, const dint_block* __restrict__ blocks,
-                   uint64_t n_blocks, uint32_t block_size, uint32_t* __restrict__ docids, uint32_t* __restrict__ freqs) {
+                   uint64_t n_blocks, uint32_t block_size, uint32_t chunk, uint32_t* __restrict__ docids,
+                   uint32_t* __restrict__ freqs) {
     __shared__ uint4 stacks[kTailThreads * 10];
     __shared__ tail_warp_smem wsm[kTailThreads / 32];
     uint4* stack = stacks + threadIdx.x;  // level-major: entry k at stack[k * kTailThreads]
     tail_warp_smem& W = wsm[threadIdx.x >> 5];
     const unsigned lane = threadIdx.x & 31u;
     uint32_t P[256];  // freqs prefix sums of the tail in hand (local memory)
-    const uint64_t n_chunks = (n_blocks + kTailChunk - 1) / kTailChunk;
+    // chunk (<= kTailChunk, a multiple of 32): small tables are cut finer so that every SM gets work
+    const uint64_t n_chunks = (n_blocks + chunk - 1) / chunk;
     const uint64_t n_warps = (uint64_t(gridDim.x) * blockDim.x) >> 5;
     for (uint64_t c = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; c < n_chunks; c += n_warps) {
-        const uint64_t base = c * kTailChunk;
-        const uint32_t cn = uint32_t(min(uint64_t(kTailChunk), n_blocks - base));
+        const uint64_t base = c * chunk;
+        const uint32_t cn = uint32_t(min(uint64_t(chunk), n_blocks - base));
         // ---- counting sort of the chunk's partial blocks by size (descending) -------------------------------------
         __syncwarp();
         for (uint32_t t = lane; t < 257u; t += 32u) W.bins[t] = 0;
@@ -516,24 +518,25 @@ checksum_kernel(const uint32_t* __restrict__ values, const uint64_t* __restrict_
 }
 
 // ---- batched AND-intersection over decoded docID lists (ds2i::and_query, include/ds2i/queries.hpp:34-86) --------
-// One warp per query. Lane k holds term k's list (start, length); duplicates are dropped like
-// remove_duplicate_terms does (:29-32). The reference walks the shortest list and calls next_geq on the others in
-// order of increasing length (:48-72); here 32 docIDs of the shortest list are tested at once, each lane looking its
-// candidate up in the other lists (shortest first, so most candidates die early) by binary search — the lists are
-// sorted arrays in HBM once decoded. counts[q] = documents that hold every term; a term id >= n_lists makes it 0.
+// One CTA per query, its warps sharing the candidates. Lane k holds term k's list (start, length); duplicates are
+// dropped like remove_duplicate_terms does (:29-32). The reference walks the shortest list and calls next_geq on the
+// others in order of increasing length (:48-72); here every warp tests 32 docIDs of the shortest list at once, each
+// lane looking its candidate up in the other lists (shortest first, so most candidates die early) by binary search —
+// the lists are sorted arrays in HBM once decoded. counts[q] = documents that hold every term (partial counts of the
+// warps are added with atomics; the caller zeroes counts); a term id >= n_lists makes it 0.
 constexpr uint32_t kMaxQueryTerms = 32;
-__global__ void __launch_bounds__(128)
+constexpr uint32_t kAndWarps = 8;  // warps (one CTA) per query: they share the candidates of the shortest list
+__global__ void __launch_bounds__(kAndWarps * 32)
 and_queries_kernel(const uint32_t* __restrict__ docids, const uint64_t* __restrict__ offs, uint64_t n_lists,
                    const uint64_t* __restrict__ qoff, const uint32_t* __restrict__ qterms, uint64_t n_queries,
                    unsigned long long* __restrict__ counts) {
     const unsigned lane = lane_id();
-    const uint64_t gwarp = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-    const uint64_t nwarps = (uint64_t(gridDim.x) * blockDim.x) >> 5;
-    for (uint64_t q = gwarp; q < n_queries; q += nwarps) {
+    const uint32_t warp = threadIdx.x >> 5;
+    for (uint64_t q = blockIdx.x; q < n_queries; q += gridDim.x) {  // counts[] is zeroed by the caller
         const uint64_t t0 = qoff[q], t1 = qoff[q + 1];
         const uint32_t nt = uint32_t(min(t1 - t0, uint64_t(kMaxQueryTerms)));
         if (t1 - t0 > kMaxQueryTerms || nt == 0u) {  // more terms than lanes: not supported (flagged), empty query: 0
-            if (lane == 0) counts[q] = nt ? ~0ull : 0ull;
+            if (lane == 0 && warp == 0) counts[q] = nt ? ~0ull : 0ull;
             continue;
         }
         const uint32_t term = lane < nt ? qterms[t0 + lane] : 0xFFFFFFFFu;
@@ -544,10 +547,7 @@ and_queries_kernel(const uint32_t* __restrict__ docids, const uint64_t* __restri
             if (lane > k && other == term) keep = false;
         }
         const bool bad = __ballot_sync(FULL, keep && term >= n_lists) != 0u;
-        if (bad) {
-            if (lane == 0) counts[q] = 0;
-            continue;
-        }
+        if (bad) continue;  // counts[q] stays 0
         uint64_t start = 0;
         uint32_t len = 0xFFFFFFFFu;
         if (keep) {
@@ -576,7 +576,7 @@ and_queries_kernel(const uint32_t* __restrict__ docids, const uint64_t* __restri
         const uint64_t a_start = shfl64(s_start, 0);
         const uint32_t a_len = __shfl_sync(FULL, s_len, 0);
         unsigned long long total = 0;
-        for (uint32_t c0 = 0; c0 < a_len; c0 += 32u) {
+        for (uint32_t c0 = warp * 32u; c0 < a_len; c0 += kAndWarps * 32u) {
             const bool has = c0 + lane < a_len;
             const uint32_t cand = has ? docids[a_start + c0 + lane] : 0u;
             bool alive = has;
@@ -595,7 +595,7 @@ and_queries_kernel(const uint32_t* __restrict__ docids, const uint64_t* __restri
             }
             total += __popc(__ballot_sync(FULL, alive));
         }
-        if (lane == 0) counts[q] = total;
+        if (lane == 0 && total) atomicAdd(&counts[q], total);
     }
 }
 
@@ -992,10 +992,14 @@ static int launch_index_tails(int device, const uint8_t* d_lists, size_t lists_b
     int rc = get_device_info(device, &di);
     if (rc) return rc;
     if (!n_blocks) return DINT_OK;
-    const uint64_t n_chunks = (n_blocks + kTailChunk - 1) / kTailChunk;  // one warp per chunk
+    // one warp per chunk of the table; enough chunks to fill the GPU (32 resident warps per SM) before they grow
+    const uint64_t warps = uint64_t(di.sms) * 32;
+    uint32_t chunk = uint32_t(std::min<uint64_t>(kTailChunk, std::max<uint64_t>(32, (n_blocks / warps) & ~uint64_t(31))));
+    const uint64_t n_chunks = (n_blocks + chunk - 1) / chunk;
     const uint64_t want = (n_chunks + kTailThreads / 32 - 1) / (kTailThreads / 32);
     int tgrid = int(std::max<uint64_t>(1, std::min<uint64_t>(want, uint64_t(di.sms) * 8)));
-    index_tails_kernel<<<tgrid, kTailThreads, 0, st>>>(d_lists, lists_bytes, d_blocks, n_blocks, block_size, d_docids, d_freqs);
+    index_tails_kernel<<<tgrid, kTailThreads, 0, st>>>(d_lists, lists_bytes, d_blocks, n_blocks, block_size, chunk, d_docids,
+                                                      d_freqs);
     ++g_launches;
     CUDA_TRY(cudaGetLastError());
     return DINT_OK;
@@ -1116,9 +1120,10 @@ int dint_and_queries(const uint32_t* d_docids, const uint64_t* d_list_offsets, s
     device_info di;
     int rc = get_device_info(pa.device, &di);
     if (rc) return rc;
-    const uint64_t want = (n_queries + 3) / 4;  // 4 warps per CTA, one query per warp
-    const int grid = int(std::max<uint64_t>(1, std::min<uint64_t>(want, uint64_t(di.sms) * 16)));
-    and_queries_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+    // one CTA of kAndWarps warps per query; the warps add their partial counts with atomics
+    CUDA_TRY(cudaMemsetAsync(d_counts, 0, n_queries * sizeof(uint64_t), static_cast<cudaStream_t>(stream)));
+    const int grid = int(std::max<uint64_t>(1, std::min<uint64_t>(n_queries, uint64_t(di.sms) * 8)));
+    and_queries_kernel<<<grid, kAndWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(
         d_docids, d_list_offsets, n_lists, d_query_offsets, d_query_terms, n_queries,
         reinterpret_cast<unsigned long long*>(d_counts));
     ++g_launches;

@@ -296,7 +296,7 @@ int dint_checksum_lists(const uint32_t* d_values, const uint64_t* d_list_offsets
  * offsets): counts[q] = number of documents that contain every term of query q. Queries in CSR form:
  * d_query_terms[d_query_offsets[q] .. d_query_offsets[q + 1]) are term ids (= list indices; duplicates are dropped
  * like remove_duplicate_terms does; at most 32 terms per query, else counts[q] = UINT64_MAX; a term id >= n_lists
- * gives 0). One warp per query: 32 docIDs of the shortest list are looked up in the other lists at a time. */
+ * gives 0). One CTA per query: each warp looks 32 docIDs of the shortest list up in the other lists at a time. */
 int dint_and_queries(const uint32_t* d_docids, const uint64_t* d_list_offsets, size_t n_lists, const uint64_t* d_query_offsets,
                      const uint32_t* d_query_terms, size_t n_queries, uint64_t* d_counts, void* stream);
 
