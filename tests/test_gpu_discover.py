@@ -185,3 +185,55 @@ def test_index_discover_subset_of_blocks(golden):
     want_d = np.concatenate([full_d[s:s + k] for s, k in zip(src, n)])
     want_f = np.concatenate([full_f[s:s + k] for s, k in zip(src, n)])
     assert np.array_equal(_np(dd), want_d) and np.array_equal(_np(ff), want_f)
+
+
+def test_full_size_multi_dictionary_every_engine(oracle):
+    """a multi_packed dictionary at its maximum size (6 classes x 65536 + 7 entries: a 192 KB 4-bit length table)
+    must decode through every engine: the tile decoder shrinks its CTA until table + rings fit in shared memory
+    (it used to refuse), the strip decoder and the device-side discovery use the group tables"""
+    from test_gpu_parity import _synthetic_packed_dictionary, _decode_lists
+    type_ = "multi_packed_dint"
+    dict_bytes = _synthetic_packed_dictionary(6, 65543, 7)
+    di = sb.DictImage(capi.KIND_OF_TYPE[type_], dict_bytes)
+    rng = np.random.default_rng(8)
+    lists = []
+    for li in range(40):
+        vals = []
+        n = int(rng.choice([3, 60, 300, 1500]))
+        cls = int(rng.integers(0, 6))
+        ents = [t for t in di.classes[cls][7:65536] if t is not None]
+        while len(vals) < n:
+            if rng.random() < 0.8:
+                vals.extend(ents[int(rng.integers(0, len(ents)))])
+            else:
+                vals.extend(rng.integers(0, 1 << 20, 2).tolist())
+        lists.append(vals[:n])
+    want = np.concatenate([np.asarray(v, dtype=np.uint32) for v in lists])
+    sels = [0, 1, 2, 3, 4, 5, 7, 9]
+    ho = oracle.dict_parse(KINDS[type_], dict_bytes)
+    for engine in ("strips", "units"):
+        out, data, vf = _decode_lists(type_, dict_bytes, lists, engine=engine, selectors=sels)
+        o, _ = oracle.vroom_decode_file(ho, data, len(want), len(lists))
+        assert np.array_equal(o, want)
+        assert np.array_equal(out, want), engine
+    vd = driver.VroomFile(type_, data, dict_bytes, plan="device", sync_stride=2048)
+    assert np.array_equal(_np(vd.decode(mode=capi.MODE_RAW)), want)
+    # the literal Decoder::decode drop-in (one list, host buffers) with the same dictionary: its scratch is reused
+    d = capi.Dictionary(2, dict_bytes, device=0)
+    host_plan = capi.VroomPlan(d, data)
+    lbo = host_plan.list_byte_offsets.astype(np.int64)
+    for li in (0, 5, 39):
+        hdr = len(sb.vbyte(len(lists[li]))) + len(sb.vbyte(sum(lists[li]) & 0xFFFFFFFF))
+        vals, used = capi.decode_list_host(d, data[lbo[li] + hdr:], len(lists[li]))
+        assert np.array_equal(vals, np.asarray(lists[li], dtype=np.uint32)) and used == lbo[li + 1] - lbo[li] - hdr
+    oracle.dict_free(ho)
+
+
+def test_index_block_size_out_of_range_is_rejected(golden):
+    idx = driver.IndexFile("single_packed_dint", golden.bytes(golden.index_name("single_packed_dint")))
+    p = idx.plan
+    out = torch.zeros(idx.n_postings, dtype=torch.int32, device="cuda")
+    with pytest.raises(capi.DintError) as e:
+        capi.decode_index(idx.docs_dict, idx.freqs_dict, idx.d_bin.data_ptr() + p.lists_off, p.lists_len,
+                          idx.d_blocks.data_ptr(), int(p.n_blocks), 2048, out.data_ptr(), None)
+    assert e.value.code == -1

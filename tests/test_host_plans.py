@@ -114,6 +114,60 @@ def test_malformed_inputs_are_rejected(golden):
         capi.IndexPlan(0, idx)  # wrong dictionary kind for this file
 
 
+def _multi_dict_parts(dict_bytes):
+    """header words + the three arrays of a multi_packed dictionary file (multi_dictionary.hpp:70-91)"""
+    w = np.frombuffer(dict_bytes, dtype="<u4").copy()
+    ns, no, nt = int(w[1]), int(w[2]), int(w[3])
+    return w, 4, 4 + ns, 4 + ns + no, nt
+
+
+def test_malformed_dictionaries_are_rejected(golden):
+    """what a dictionary must satisfy for the device tables to mean what the reference's copy() does:
+    monotone class starts, classes of at most 65536 + 7 entries, exception rows of length 1, entry lengths
+    in {1, 2, 4, 8, 16} (the device stores log2(length)) — anything else is DINT_E_FORMAT, not a wrong decode"""
+    good = golden.bytes(golden.dict_name("multi_packed_dint", "docs"))
+    capi.Dictionary(2, good)  # the fixture itself is fine
+    w, so, oo, to, nt = _multi_dict_parts(good)
+    bad = w.copy()
+    bad[so + 1], bad[so + 2] = w[so + 2], w[so + 1]  # class starts swapped
+    with pytest.raises(capi.DintError) as e:
+        capi.Dictionary(2, bad.tobytes())
+    assert e.value.code == -2
+    first_entry = int(w[so]) + 7  # first non-reserved row of class 0
+    bad = w.copy()
+    bad[oo + first_entry] = (2 << 24) | (int(w[oo + first_entry]) & 0xFFFFFF)  # length 3
+    with pytest.raises(capi.DintError) as e:
+        capi.Dictionary(2, bad.tobytes())
+    assert e.value.code == -2
+    bad = w.copy()
+    bad[oo + int(w[so])] = (1 << 24)  # the 16-bit exception row claims length 2
+    with pytest.raises(capi.DintError) as e:
+        capi.Dictionary(2, bad.tobytes())
+    assert e.value.code == -2
+    bad = w.copy()
+    bad[oo + int(w[so]) + 2] = 0x0F000000  # run codeword 2 must be 256 zeros
+    with pytest.raises(capi.DintError):
+        capi.Dictionary(2, bad.tobytes())
+    # single_packed: the same length rule
+    sp = np.frombuffer(golden.bytes(golden.dict_name("single_packed_dint", "docs")), dtype="<u4").copy()
+    sp[3 + 100] = (4 << 24) | (int(sp[3 + 100]) & 0xFFFFFF)  # length 5
+    with pytest.raises(capi.DintError) as e:
+        capi.Dictionary(1, sp.tobytes())
+    assert e.value.code == -2
+
+
+def test_corrupt_index_header_is_an_error_not_a_crash(golden):
+    """an absurd list count in the header must come back as an error code (no allocation sized by it, no exception
+    through the C boundary)"""
+    idx = bytearray(golden.bytes(golden.index_name("single_packed_dint")))
+    for n in (2 ** 62, 2 ** 40, len(idx) * 9):
+        bad = bytearray(idx)
+        bad[13:21] = int(n).to_bytes(8, "little")  # m_size, behind the 8-byte flags and 5 global parameters
+        with pytest.raises(capi.DintError) as e:
+            capi.IndexPlan(1, bytes(bad))
+        assert e.value.code in (-2, -4)
+
+
 def test_empty_vroom_file(golden):
     d = capi.Dictionary(1, golden.bytes(golden.dict_name("single_packed_dint", "docs")))
     plan = capi.VroomPlan(d, b"")

@@ -71,3 +71,29 @@ def test_sharded_decode_reduces_to_whole_file(golden, oracle, world, type_, part
     vals, ln = oracle.vroom_decode_file(ho, bin_, golden.n_postings, golden.n_lists)
     want = int(g.checksum_lists(vals, ln.astype(np.int64)).sum(dtype=np.uint64)) & 0x7FFFFFFFFFFFFFFF
     assert count == golden.n_postings and checksum == want
+
+
+def test_virtual_cuts_of_a_replicated_collection():
+    """bench.py cuts R back-to-back copies of the sample into term ranges of equal postings without materialising
+    R x lists entries: the cuts must be those of shard.split_by_postings on the materialised lengths"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    rng = np.random.default_rng(5)
+    lengths = np.maximum(1, (3000 / rng.zipf(1.2, 500)).astype(np.int64))
+    lo = np.concatenate([[0], np.cumsum(lengths)])
+    n_ints, n_lists = int(lo[-1]), len(lengths)
+    for R, world in ((8, 1), (8, 2), (8, 8), (7, 3), (5, 4), (640, 8)):
+        cuts = bench.virtual_cuts(lo, n_ints, R, world)
+        assert cuts[0] == (0, 0) and cuts[-1] == (R, 0) and len(cuts) == world + 1
+        flat = [q * n_lists + j for q, j in cuts]
+        assert all(b >= a for a, b in zip(flat, flat[1:]))
+        per = [(q1 * n_ints + lo[j1]) - (q0 * n_ints + lo[j0]) for (q0, j0), (q1, j1) in zip(cuts, cuts[1:])]
+        assert sum(per) == R * n_ints
+        assert max(per) - R * n_ints / world <= lengths.max()  # off by at most one list
+        if R <= 8:
+            b = shard.split_by_postings(np.tile(lengths, R), world)
+            assert [int(x) for x in b] == flat
+        if R % world == 0:  # whole replicas per rank: exactly equal shards
+            assert len(set(per)) == 1 and all(j == 0 for _, j in cuts)
