@@ -206,55 +206,47 @@ int dint_vroom_discover(const dint_dict* d, const uint8_t* d_in, size_t in_bytes
         uint32_t status;
         bool by_warp, counted;
     };
-    // runs one pass over chains[ids]: device arrays are indexed by the position in ids
-    auto run_pass = [&](std::vector<chain>& chains, const std::vector<uint32_t>& ids, bool emit, const std::vector<uint64_t>* bases) -> int {
-        const uint64_t n = ids.size();
+    // ---- one pass over chains[ids]: device arrays are indexed by the position k in ids (slot 2k / 8k) ----------------
+    struct pass_bufs {
+        dev_buf d_se, d_cnt, d_order, d_bases;
+        uint64_t n = 0, n_short = 0, n_long = 0;
+    };
+    auto prepare = [&](const std::vector<chain>& chains, const std::vector<uint32_t>& ids, pass_bufs& pb) -> int {
+        const uint64_t n = pb.n = ids.size();
+        pb.n_short = pb.n_long = 0;
         if (!n) return DINT_OK;
-        std::vector<uint64_t> se(2 * n + 2), cnt(4 * n, 0);
+        std::vector<uint64_t> se(2 * n + 2);
         std::vector<uint32_t> order(n);
-        uint64_t n_short = 0, n_long = 0;
         // walk_params wants chain c = [chain_start[c], chain_start[c + 1]): give every chain its own pair
         for (uint64_t k = 0; k < n; ++k) {
             se[2 * k] = chains[ids[k]].start;
             se[2 * k + 1] = chains[ids[k]].end;
         }
         for (uint64_t k = 0; k < n; ++k)
-            if (!chains[ids[k]].by_warp) order[n_short++] = uint32_t(2 * k);
+            if (!chains[ids[k]].by_warp) order[pb.n_short++] = uint32_t(2 * k);
         for (uint64_t k = 0; k < n; ++k)
-            if (chains[ids[k]].by_warp) order[n_short + n_long++] = uint32_t(2 * k);
-        dev_buf d_se, d_cnt, d_order, d_bases;
-        CUDA_TRY(cudaMalloc(&d_se.p, se.size() * 8));
-        CUDA_TRY(cudaMalloc(&d_cnt.p, 8 * n * 8));  // indexed by 2k: [2k][4]
-        CUDA_TRY(cudaMalloc(&d_order.p, n * 4));
-        CUDA_TRY(cudaMemcpyAsync(d_se.p, se.data(), se.size() * 8, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(d_order.p, order.data(), n * 4, cudaMemcpyHostToDevice, st));
-        std::vector<uint64_t> wide;
-        if (emit) {  // counts of the count pass (checked by the emit pass) + bases, both at index 2k
-            wide.assign(8 * n, 0);
-            for (uint64_t k = 0; k < n; ++k) {
-                const chain& c = chains[ids[k]];
-                wide[8 * k] = c.lists;
-                wide[8 * k + 1] = c.ints;
-                wide[8 * k + 2] = c.units;
-            }
-            CUDA_TRY(cudaMemcpyAsync(d_cnt.p, wide.data(), 8 * n * 8, cudaMemcpyHostToDevice, st));
-            std::vector<uint64_t> b(8 * n, 0);
-            for (uint64_t k = 0; k < n; ++k)
-                for (int j = 0; j < 3; ++j) b[8 * k + j] = (*bases)[4 * ids[k] + j];
-            CUDA_TRY(cudaMalloc(&d_bases.p, 8 * n * 8));
-            CUDA_TRY(cudaMemcpyAsync(d_bases.p, b.data(), 8 * n * 8, cudaMemcpyHostToDevice, st));
-            CUDA_TRY(cudaStreamSynchronize(st));
-            P.bases = d_bases.as<uint64_t>();
-        }
-        P.chain_start = d_se.as<uint64_t>();
-        P.n_chains = 2 * n;
-        P.counts = d_cnt.as<uint64_t>();
+            if (chains[ids[k]].by_warp) order[pb.n_short + pb.n_long++] = uint32_t(2 * k);
+        CUDA_TRY(cudaMalloc(&pb.d_se.p, se.size() * 8));
+        CUDA_TRY(cudaMalloc(&pb.d_cnt.p, 8 * n * 8));
+        CUDA_TRY(cudaMalloc(&pb.d_bases.p, 8 * n * 8));
+        CUDA_TRY(cudaMalloc(&pb.d_order.p, n * 4));
+        CUDA_TRY(cudaMemcpyAsync(pb.d_se.p, se.data(), se.size() * 8, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(pb.d_order.p, order.data(), n * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaStreamSynchronize(st));  // se / order go out of scope
+        return DINT_OK;
+    };
+    auto launch = [&](pass_bufs& pb, bool emit) -> int {
+        if (!pb.n) return DINT_OK;
+        P.chain_start = pb.d_se.as<uint64_t>();
+        P.n_chains = 2 * pb.n;
+        P.counts = pb.d_cnt.as<uint64_t>();
+        P.bases = pb.d_bases.as<uint64_t>();
         CUDA_TRY(cudaMemsetAsync(d_status.p, 0, 16, st));
-        if (n_short) {
-            P.chain_ids = d_order.as<uint32_t>();
-            P.n_ids = n_short;
+        if (pb.n_short) {
+            P.chain_ids = pb.d_order.as<uint32_t>();
+            P.n_ids = pb.n_short;
             const size_t smem = walk_smem(d, 0) + (emit ? walk_hotsum_bytes(d->view()) : 0);
-            const int grid = int((n_short + 255) / 256);
+            const int grid = int((pb.n_short + 255) / 256);
             if (emit) {
                 CUDA_TRY(cudaFuncSetAttribute(vroom_thread_walk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
                 vroom_thread_walk_kernel<true><<<grid, 256, smem, st>>>(P);
@@ -265,39 +257,91 @@ int dint_vroom_discover(const dint_dict* d, const uint8_t* d_in, size_t in_bytes
             ++g_launches;
             CUDA_TRY(cudaGetLastError());
         }
-        if (n_long) {
-            P.chain_ids = d_order.as<uint32_t>() + n_short;
-            P.n_ids = n_long;
+        if (pb.n_long) {
+            P.chain_ids = pb.d_order.as<uint32_t>() + pb.n_short;
+            P.n_ids = pb.n_long;
             int grid = 0, rc2;
             size_t smem = 0;
             if (emit) {
-                rc2 = walk_grid(vroom_walk_kernel<true>, d, kWalkWarps, n_long, &grid, &smem);
+                rc2 = walk_grid(vroom_walk_kernel<true>, d, kWalkWarps, pb.n_long, &grid, &smem);
                 if (rc2) return rc2;
                 vroom_walk_kernel<true><<<grid, kWalkWarps * 32, smem, st>>>(P);
             } else {
-                rc2 = walk_grid(vroom_walk_kernel<false>, d, kWalkWarps, n_long, &grid, &smem);
+                rc2 = walk_grid(vroom_walk_kernel<false>, d, kWalkWarps, pb.n_long, &grid, &smem);
                 if (rc2) return rc2;
                 vroom_walk_kernel<false><<<grid, kWalkWarps * 32, smem, st>>>(P);
             }
             ++g_launches;
             CUDA_TRY(cudaGetLastError());
         }
-        if (!emit) {
-            std::vector<uint64_t> h(8 * n);
-            CUDA_TRY(cudaMemcpyAsync(h.data(), d_cnt.p, 8 * n * 8, cudaMemcpyDeviceToHost, st));
-            CUDA_TRY(cudaStreamSynchronize(st));
+        return DINT_OK;
+    };
+    auto fetch = [&](pass_bufs& pb, std::vector<chain>& chains, const std::vector<uint32_t>& ids) -> int {
+        const uint64_t n = pb.n;
+        if (!n) return DINT_OK;
+        std::vector<uint64_t> h(8 * n);
+        CUDA_TRY(cudaMemcpyAsync(h.data(), pb.d_cnt.p, 8 * n * 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        for (uint64_t k = 0; k < n; ++k) {
+            chain& c = chains[ids[k]];
+            c.lists = h[8 * k];
+            c.ints = h[8 * k + 1];
+            c.units = h[8 * k + 2];
+            c.status = uint32_t(h[8 * k + 3] & 0xFF);
+            c.reached = h[8 * k + 3] >> 8;
+            c.counted = true;
+        }
+        return DINT_OK;
+    };
+    // count pass of a repair round / emit pass with host-computed bases (the slow path)
+    auto run_pass = [&](std::vector<chain>& chains, const std::vector<uint32_t>& ids, bool emit, const std::vector<uint64_t>* bases) -> int {
+        pass_bufs pb;
+        int rc2 = prepare(chains, ids, pb);
+        if (rc2 || !pb.n) return rc2;
+        const uint64_t n = pb.n;
+        if (emit) {  // counts of the count pass (checked by the emit pass) + bases, both at slot 8k
+            std::vector<uint64_t> wide(8 * n, 0), b(8 * n, 0);
             for (uint64_t k = 0; k < n; ++k) {
-                chain& c = chains[ids[k]];
-                c.lists = h[8 * k];
-                c.ints = h[8 * k + 1];
-                c.units = h[8 * k + 2];
-                c.status = uint32_t(h[8 * k + 3] & 0xFF);
-                c.reached = h[8 * k + 3] >> 8;
-                c.counted = true;
+                const chain& c = chains[ids[k]];
+                wide[8 * k] = c.lists;
+                wide[8 * k + 1] = c.ints;
+                wide[8 * k + 2] = c.units;
+                for (int j = 0; j < 3; ++j) b[8 * k + j] = (*bases)[4 * ids[k] + j];
             }
-        } else {
+            CUDA_TRY(cudaMemcpyAsync(pb.d_cnt.p, wide.data(), 8 * n * 8, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaMemcpyAsync(pb.d_bases.p, b.data(), 8 * n * 8, cudaMemcpyHostToDevice, st));
             CUDA_TRY(cudaStreamSynchronize(st));
         }
+        rc2 = launch(pb, emit);
+        if (rc2) return rc2;
+        if (!emit) return fetch(pb, chains, ids);
+        CUDA_TRY(cudaStreamSynchronize(st));
+        return DINT_OK;
+    };
+    auto finish = [&](uint64_t lists, uint64_t ints) -> int {
+        const uint64_t tail[2] = {ints, uint64_t(in_bytes)};
+        CUDA_TRY(cudaMemcpyAsync(plan->d_list_offsets + lists, &tail[0], 8, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(plan->d_list_byte_offsets + lists, &tail[1], 8, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaEventRecord(ev1, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        CUDA_TRY(cudaEventElapsedTime(&plan->discover_ms, ev0, ev1));
+        CUDA_TRY(cudaEventElapsedTime(&plan->phase_ms[0], ev0, evs));
+        CUDA_TRY(cudaEventElapsedTime(&plan->phase_ms[1], evs, evc));
+        CUDA_TRY(cudaEventElapsedTime(&plan->phase_ms[2], evc, ev1));
+        return DINT_OK;
+    };
+    auto allocate_outputs = [&](uint64_t lists, uint64_t ints, uint64_t units, uint64_t n_chains) -> int {
+        plan->n_lists = lists;
+        plan->n_ints = ints;
+        plan->n_units = units;
+        plan->n_chains = n_chains;
+        CUDA_TRY(cudaMalloc(&plan->d_units, (units + 1) * sizeof(dint_strip_unit)));
+        CUDA_TRY(cudaMalloc(&plan->d_list_offsets, (lists + 1) * 8));
+        CUDA_TRY(cudaMalloc(&plan->d_list_byte_offsets, (lists + 1) * 8));
+        P.units = plan->d_units;
+        P.units_cap = units;
+        P.list_offsets = plan->d_list_offsets;
+        P.list_byte_offsets = plan->d_list_byte_offsets;
         return DINT_OK;
     };
 
@@ -317,9 +361,65 @@ int dint_vroom_discover(const dint_dict* d, const uint8_t* d_in, size_t in_bytes
         std::vector<uint32_t> todo(chains.size());
         for (size_t i = 0; i < chains.size(); ++i) todo[i] = uint32_t(i);
         std::vector<uint32_t> linked;  // the chains of the file, in order
-        for (uint32_t round = 0;; ++round) {
-            rc = run_pass(chains, todo, false, nullptr);
+        // ---- fast path: everything stays on the device ------------------------------------------------------------------
+        // count pass -> chain_scan_kernel (every chain landed on its successor? + decoupled look-back scan of the chain
+        // totals into chain bases) -> the host reads back four numbers, sizes the tables -> emit pass
+        bool first_counted = false;
+        if (!chains.empty()) {
+            pass_bufs pb;
+            rc = prepare(chains, todo, pb);
             if (rc) return rc;
+            rc = launch(pb, false);
+            if (rc) return rc;
+            const uint64_t n = pb.n, tiles = (n + 255) / 256;
+            dev_buf d_scan;  // tile_agg [tiles][4] | tile_inc [tiles][4] | totals [4] | flags [tiles] | counter
+            const size_t scan_bytes = (8 * tiles + 4) * 8 + (tiles + 4) * 4;
+            CUDA_TRY(cudaMalloc(&d_scan.p, scan_bytes));
+            CUDA_TRY(cudaMemsetAsync(d_scan.p, 0, scan_bytes, st));
+            chain_scan_params S;
+            S.n = n;
+            S.se = pb.d_se.as<uint64_t>();
+            S.cnt = pb.d_cnt.as<uint64_t>();
+            S.bases = pb.d_bases.as<uint64_t>();
+            S.tile_agg = d_scan.as<unsigned long long>();
+            S.tile_inc = S.tile_agg + 4 * tiles;
+            S.totals = S.tile_inc + 4 * tiles;
+            S.tile_flag = reinterpret_cast<unsigned int*>(S.totals + 4);
+            S.tile_counter = S.tile_flag + tiles;
+            chain_scan_kernel<<<int(tiles), 256, 0, st>>>(S);
+            ++g_launches;
+            CUDA_TRY(cudaGetLastError());
+            uint64_t totals[4] = {0, 0, 0, 0};
+            CUDA_TRY(cudaMemcpyAsync(totals, S.totals, 32, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            if (totals[3] == 0) {
+                CUDA_TRY(cudaEventRecord(evc, st));
+                rc = allocate_outputs(totals[0], totals[1], totals[2], n);
+                if (rc) return rc;
+                rc = launch(pb, true);
+                if (rc) return rc;
+                uint32_t h_status = 0;
+                CUDA_TRY(cudaMemcpyAsync(&h_status, d_status.p, 4, cudaMemcpyDeviceToHost, st));
+                CUDA_TRY(cudaStreamSynchronize(st));
+                if (h_status != WALK_OK) {
+                    dint::set_error("vroom .bin: the emit pass of the device walk disagrees with the count pass");
+                    return DINT_E_FORMAT;
+                }
+                rc = finish(totals[0], totals[1]);
+                if (rc) return rc;
+                *out = plan.release();
+                return DINT_OK;
+            }
+            // some chain did not land on its successor (or is malformed): repair on the host, from these counts
+            rc = fetch(pb, chains, todo);
+            if (rc) return rc;
+            first_counted = true;
+        }
+        for (uint32_t round = 0;; ++round) {
+            if (!(round == 0 && first_counted)) {
+                rc = run_pass(chains, todo, false, nullptr);
+                if (rc) return rc;
+            }
             todo.clear();
             // index of the chain that starts at a given byte: candidates are sorted by start, repairs are appended
             std::vector<std::pair<uint64_t, uint32_t>> by_start(chains.size());
@@ -394,18 +494,9 @@ int dint_vroom_discover(const dint_dict* d, const uint8_t* d_in, size_t in_bytes
             ints += c.ints;
             units += c.units;
         }
-        plan->n_lists = lists;
-        plan->n_ints = ints;
-        plan->n_units = units;
-        plan->n_chains = linked.size();
-        CUDA_TRY(cudaMalloc(&plan->d_units, (units + 1) * sizeof(dint_strip_unit)));
-        CUDA_TRY(cudaMalloc(&plan->d_list_offsets, (lists + 1) * 8));
-        CUDA_TRY(cudaMalloc(&plan->d_list_byte_offsets, (lists + 1) * 8));
+        rc = allocate_outputs(lists, ints, units, linked.size());
+        if (rc) return rc;
         if (!linked.empty()) {
-            P.units = plan->d_units;
-            P.units_cap = units;
-            P.list_offsets = plan->d_list_offsets;
-            P.list_byte_offsets = plan->d_list_byte_offsets;
             rc = run_pass(chains, linked, true, &bases);
             if (rc) return rc;
             uint32_t h_status = 0;
@@ -415,15 +506,8 @@ int dint_vroom_discover(const dint_dict* d, const uint8_t* d_in, size_t in_bytes
                 return DINT_E_FORMAT;
             }
         }
-        const uint64_t tail[2] = {ints, uint64_t(in_bytes)};
-        CUDA_TRY(cudaMemcpyAsync(plan->d_list_offsets + lists, &tail[0], 8, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(plan->d_list_byte_offsets + lists, &tail[1], 8, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaEventRecord(ev1, st));
-        CUDA_TRY(cudaStreamSynchronize(st));
-        CUDA_TRY(cudaEventElapsedTime(&plan->discover_ms, ev0, ev1));
-        CUDA_TRY(cudaEventElapsedTime(&plan->phase_ms[0], ev0, evs));
-        CUDA_TRY(cudaEventElapsedTime(&plan->phase_ms[1], evs, evc));
-        CUDA_TRY(cudaEventElapsedTime(&plan->phase_ms[2], evc, ev1));
+        rc = finish(lists, ints);
+        if (rc) return rc;
     } catch (const std::bad_alloc&) {
         return DINT_E_NOMEM;
     }

@@ -701,6 +701,105 @@ __global__ void __launch_bounds__(256, 4) vroom_thread_walk_kernel(const vroom_w
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// chain totals -> chain bases: single-pass exclusive scan with decoupled look-back
+// ---------------------------------------------------------------------------------------------------------
+// After the count pass every chain knows how many lists, integers and strip units it holds; the emit pass needs
+// the sums over all chains in front of it. One CTA per tile of 256 chains: local scan, publish the tile's
+// aggregate, look back over the preceding tiles' descriptors (aggregate or inclusive prefix, whichever is there)
+// instead of waiting for a global barrier. The same kernel checks that every chain ended exactly on the next
+// chain's start (if one did not, the host repairs the chain table and this fast path is not taken).
+struct chain_scan_params {
+    uint64_t n;                       // chains, in file order; chain k occupies slots [8k, 8k + 4) of cnt / bases
+    const uint64_t* se;               // [2k] start, [2k + 1] end of chain k
+    const uint64_t* cnt;              // count pass: lists, ints, units, status | reached << 8
+    uint64_t* bases;                  // out: first list, first int, first unit of chain k
+    unsigned long long* tile_agg;     // [tiles][4] aggregate of a tile (3 values)
+    unsigned long long* tile_inc;     // [tiles][4] inclusive prefix up to and including a tile
+    unsigned int* tile_flag;          // [tiles] 0: nothing yet, 1: aggregate published, 2: inclusive prefix published
+    unsigned int* tile_counter;       // hands out tile ids in launch order (forward progress of the look-back)
+    unsigned long long* totals;       // out: lists, ints, units, (!= 0: some chain did not land on its successor)
+};
+
+__global__ void __launch_bounds__(256) chain_scan_kernel(const chain_scan_params P) {
+    __shared__ unsigned int s_tile;
+    __shared__ unsigned long long s_warp[8][3], s_prefix[3];
+    const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_tile = atomicAdd(P.tile_counter, 1u);
+    __syncthreads();
+    const uint64_t tile = s_tile, k = tile * 256 + threadIdx.x;
+    const bool valid = k < P.n;
+    unsigned long long v[3] = {0, 0, 0};
+    bool bad = false;
+    if (valid) {
+        v[0] = P.cnt[8 * k];
+        v[1] = P.cnt[8 * k + 1];
+        v[2] = P.cnt[8 * k + 2];
+        const uint64_t st = P.cnt[8 * k + 3];
+        bad = (st & 0xFF) != WALK_OK || (st >> 8) != P.se[2 * k + 1];
+    }
+    if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(P.totals + 3, 1ull);
+    // CTA-wide exclusive scan of the three counters
+    unsigned long long incl[3];
+    for (int j = 0; j < 3; ++j) {
+        unsigned long long x = v[j];
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long y = shfl64(x, lane >= unsigned(o) ? int(lane) - o : int(lane));
+            if (lane >= unsigned(o)) x += y;
+        }
+        incl[j] = x;
+        if (lane == 31) s_warp[warp][j] = x;
+    }
+    __syncthreads();
+    unsigned long long excl[3], agg[3];
+    for (int j = 0; j < 3; ++j) {
+        unsigned long long before = 0, total = 0;
+        for (unsigned w = 0; w < 8; ++w) {
+            const unsigned long long t = s_warp[w][j];
+            if (w < warp) before += t;
+            total += t;
+        }
+        excl[j] = before + incl[j] - v[j];
+        agg[j] = total;
+    }
+    // ---- decoupled look-back (thread 0) ----------------------------------------------------------------------
+    if (threadIdx.x == 0) {
+        volatile unsigned long long* vagg = P.tile_agg;
+        volatile unsigned long long* vinc = P.tile_inc;
+        volatile unsigned int* vflag = P.tile_flag;
+        unsigned long long prefix[3] = {0, 0, 0};
+        if (tile == 0) {
+            for (int j = 0; j < 3; ++j) vinc[j] = agg[j];
+            __threadfence();
+            vflag[0] = 2u;
+        } else {
+            for (int j = 0; j < 3; ++j) vagg[4 * tile + j] = agg[j];
+            __threadfence();
+            vflag[tile] = 1u;
+            for (uint64_t t = tile; t-- > 0;) {
+                unsigned int f;
+                while ((f = vflag[t]) == 0u) {
+                }
+                __threadfence();
+                if (f == 2u) {
+                    for (int j = 0; j < 3; ++j) prefix[j] += vinc[4 * t + j];
+                    break;
+                }
+                for (int j = 0; j < 3; ++j) prefix[j] += vagg[4 * t + j];
+            }
+            for (int j = 0; j < 3; ++j) vinc[4 * tile + j] = prefix[j] + agg[j];
+            __threadfence();
+            vflag[tile] = 2u;
+        }
+        for (int j = 0; j < 3; ++j) s_prefix[j] = prefix[j];
+        if ((tile + 1) * 256 >= P.n)
+            for (int j = 0; j < 3; ++j) P.totals[j] = prefix[j] + agg[j];
+    }
+    __syncthreads();
+    if (valid)
+        for (int j = 0; j < 3; ++j) P.bases[8 * k + j] = s_prefix[j] + excl[j];
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // speculative sync points of a vroom .bin: one thread per candidate byte position
 // ---------------------------------------------------------------------------------------------------------
 struct find_sync_params {
