@@ -804,29 +804,19 @@ def run_e2e(torch, dist, capi, dev, w, args, streams, world):
         torch.cuda.synchronize(dev)
         if world > 1:
             dist.barrier()
-        # the two files of the collection are loaded by two host threads on two streams (the discovery's passes
-        # are latency bound and leave most of the GPU idle, so they overlap well)
-        from concurrent.futures import ThreadPoolExecutor
-        disc = [0.0, 0.0]
-
-        def load_one(k):
-            h_bin, h_sums, mode, part = cold[k]
-            torch.cuda.set_device(dev)
-            s = lanes[k].cuda_stream
-            for r in range(R // Kc):
-                dec = capi.VroomHostDecoder.discover(streams[part].dict, h_bin.data_ptr(), h_bin.numel(),
-                                                     block_size=w["block_size"], stream=s)
-                disc[k] += dec.device_plan.discover_ms
-                dec.decode_resident(mode=mode, stream=s)
-                dec.results(h_sums_ptr=h_sums.data_ptr(), stream=s)
-                dec.sync(s)
-                dec.close()
-
-        pool = ThreadPoolExecutor(max_workers=2)
+        # one file after the other on one stream (loading the two files from two host threads was measured and is slower:
+        # the cudaMalloc / cudaFree calls of one discovery synchronise the device under the other's kernels)
         t0 = time.perf_counter()
-        for f in [pool.submit(load_one, k) for k in range(len(cold))]:
-            f.result()
-        disc_ms = max(disc)
+        disc_ms = 0.0
+        for r in range(R // Kc):
+            for h_bin, h_sums, mode, part in cold:
+                dec = capi.VroomHostDecoder.discover(streams[part].dict, h_bin.data_ptr(), h_bin.numel(),
+                                                     block_size=w["block_size"], stream=st.cuda_stream)
+                disc_ms += dec.device_plan.discover_ms
+                dec.decode_resident(mode=mode, stream=st.cuda_stream)
+                dec.results(h_sums_ptr=h_sums.data_ptr(), stream=st.cuda_stream)
+                dec.sync(st.cuda_stream)
+                dec.close()
         wall = time.perf_counter() - t0
         for h_bin, h_sums, mode, part in cold:  # every replica's checksums are the sample's
             v = h_sums.view(Kc, streams[part].sample_lists)
@@ -840,8 +830,8 @@ def run_e2e(torch, dist, capi, dev, w, args, streams, world):
                            "discovery_ms_rank0": disc_ms, "files_per_stream_and_rank": R // Kc,
                            "timer": "host wall clock around synchronised calls (max over ranks)",
                            "call": ("per file: dint_vroom_ctx_create_discover (cudaMalloc + H2D + sync search + count + emit) -> "
-                                    "dint_vroom_decode_resident -> dint_vroom_ctx_results (checksums, D2H) -> destroy; the docs "
-                                    "and the freqs file are loaded by two host threads on two streams; nothing reused between files")}
+                                    "dint_vroom_decode_resident -> dint_vroom_ctx_results (checksums, D2H) -> destroy; no overlap, "
+                                    "nothing reused between files")}
     return out
 
 
