@@ -3,7 +3,7 @@
 // libdint_b200.so. Plain C++; nothing here touches CUDA directly.
 //
 //   dint_b200_decode <type> <encoded_data_filename> --dict <dictionary_filename>
-//                    [--repeat N] [--device D] [--mode raw|docids|freqs] [--sums <file>]
+//                    [--repeat N] [--device D] [--mode raw|docids|freqs] [--sums <file>] [--host-plan]
 //
 // Same positional arguments, the same failure behaviour (std::runtime_error for a missing
 // dictionary / unreadable file, "ERROR: unknown type" for an unknown codec) and the same JSON
@@ -60,12 +60,14 @@ int main(int argc, char** argv) {
     const char* dictionary_filename = nullptr;
     const char* sums_filename = nullptr;
     int repeat = 10, device = 0, mode = DINT_MODE_RAW;
+    bool host_plan = false;
     for (int i = 3; i < argc; ++i) {
         std::string a = argv[i];
         if (a == "--dict" && i + 1 < argc) dictionary_filename = argv[++i];
         else if (a == "--repeat" && i + 1 < argc) repeat = std::max(1, atoi(argv[++i]));
         else if (a == "--device" && i + 1 < argc) device = atoi(argv[++i]);
         else if (a == "--sums" && i + 1 < argc) sums_filename = argv[++i];
+        else if (a == "--host-plan") host_plan = true;
         else if (a == "--mode" && i + 1 < argc) {
             std::string m = argv[++i];
             mode = m == "docids" ? DINT_MODE_DOCIDS : m == "freqs" ? DINT_MODE_FREQS : DINT_MODE_RAW;
@@ -86,13 +88,22 @@ int main(int argc, char** argv) {
 
     dint_dict* dict = nullptr;
     check(dint_dict_create(kind, dict_bytes.data(), dict_bytes.size(), device, &dict), "dint_dict_create");
+    // load time: file -> HBM, and the GPU finds every list / block / strip start in it (no host walk of the codewords;
+    // --host-plan: the serial host walk dint_vroom_plan_create instead)
     double t0 = now();
     dint_vroom_plan* plan = nullptr;
-    check(dint_vroom_plan_create(dict, bin.data(), bin.size(), 0, 0, &plan), "dint_vroom_plan_create");
-    double t_plan = now() - t0;
-    const uint64_t n_lists = dint_vroom_plan_num_lists(plan), n_ints = dint_vroom_plan_num_ints(plan);
     dint_vroom_ctx* ctx = nullptr;
-    check(dint_vroom_ctx_create(dict, plan, 0, &ctx), "dint_vroom_ctx_create");
+    double discover_ms = 0;
+    if (host_plan) {
+        check(dint_vroom_plan_create(dict, bin.data(), bin.size(), 0, 0, &plan), "dint_vroom_plan_create");
+        check(dint_vroom_ctx_create(dict, plan, 0, &ctx), "dint_vroom_ctx_create");
+    } else {
+        check(dint_vroom_ctx_create_discover(dict, bin.data(), bin.size(), 0, nullptr, 0, 0, nullptr, &ctx),
+              "dint_vroom_ctx_create_discover");
+        discover_ms = dint_device_plan_discover_ms(dint_vroom_ctx_device_plan(ctx));
+    }
+    double t_plan = now() - t0;
+    const uint64_t n_lists = dint_vroom_ctx_num_lists(ctx), n_ints = dint_vroom_ctx_num_ints(ctx);
 
     std::vector<uint64_t> sums(n_lists ? n_lists : 1);
     // pass 0: file -> HBM, decode, per-list checksums back (the end-to-end call)
@@ -125,7 +136,8 @@ int main(int argc, char** argv) {
     std::cout << "\"ns_x_int\": \"" << ns_x_int << "\", ";
     std::cout << "\"ints_x_sec\": \"" << ints_x_sec << "\", ";
     std::cout << "\"device\": " << device << ", \"repeat\": " << repeat << ", \"mode\": " << mode
-              << ", \"plan_sec\": " << t_plan << ", \"first_pass_with_h2d_sec\": " << t_first
+              << ", \"plan_sec\": " << t_plan << ", \"plan\": \"" << (host_plan ? "host walk" : "device discovery")
+              << "\", \"discover_device_ms\": " << discover_ms << ", \"first_pass_with_h2d_sec\": " << t_first
               << ", \"kernel_launches\": " << dint_kernel_launches() << ", \"checksum\": \"" << checksum << "\"";
     std::cout << "}" << std::endl;
 

@@ -441,6 +441,11 @@ def test_cpp_host_driver(golden, tmp_path, type_):
     st = json.loads(out.strip().splitlines()[-1])
     assert int(st["num_sequences"]) == golden.n_lists and int(st["num_integers"]) == golden.n_postings
     assert st["type"] == type_ and int(st["ints_x_sec"]) > 0 and st["kernel_launches"] >= 4
+    assert st["plan"] == "device discovery" and st["discover_device_ms"] > 0  # no host walk of the codewords
+    out2 = subprocess.run([_build.DRIVER, type_, binp, "--dict", dictp, "--mode", "docids", "--repeat", "1", "--host-plan"],
+                          check=True, capture_output=True, text=True).stdout
+    st2 = json.loads(out2.strip().splitlines()[-1])
+    assert st2["plan"] == "host walk" and st2["checksum"] == st["checksum"] and st2["num_sequences"] == st["num_sequences"]
     vf = driver.VroomFile(type_, golden.bytes(golden.vroom_name(type_, "docs")), golden.bytes(golden.dict_name(type_, "docs")))
     docs = _np(vf.decode(mode=capi.MODE_DOCIDS))
     assert g.sha(docs.tobytes()) == golden.sha["docids_sha256"]
