@@ -343,6 +343,32 @@ __device__ __forceinline__ uint32_t vbyte_at(const uint8_t* base, uint64_t nbyte
     return v;
 }
 
+// Writes the n values of a decoded tail (this thread's local array) to dst: scalar stores up to the first 16-byte
+// boundary, then 16-byte stores. The interpolative walk produces the values in tree order; storing each one where it
+// belongs as it appears meant eight separate 4-byte stores per 32-byte sector, spread over time — L2 then fetches
+// every sector it is about to partially overwrite (measured: 2 x the output bytes written + as many read).
+// DIFF: the values are prefix sums, store their adjacent differences + 1 (the freqs of a tail).
+template <bool DIFF>
+__device__ __forceinline__ void write_tail(uint32_t* __restrict__ dst, const uint32_t* P, uint32_t n) {
+    uint32_t prev = 0, j = 0;
+    auto val = [&](uint32_t k) {
+        const uint32_t v = P[k];
+        const uint32_t r = DIFF ? v - prev + 1u : v;
+        prev = v;
+        return r;
+    };
+    for (; j < n && (reinterpret_cast<uintptr_t>(dst + j) & 15u); ++j) dst[j] = val(j);
+    for (; j + 4u <= n; j += 4u) {
+        uint4 q;
+        q.x = val(j);
+        q.y = val(j + 1u);
+        q.z = val(j + 2u);
+        q.w = val(j + 3u);
+        *reinterpret_cast<uint4*>(dst + j) = q;
+    }
+    for (; j < n; ++j) dst[j] = val(j);
+}
+
 // One thread per partial block. A WARP takes kTailChunk consecutive entries of the block table (neighbouring lists:
 // their bytes and their outputs are neighbours too, which keeps the accesses of a warp inside a few KB), sorts the
 // partial blocks among them by size in shared memory (warp-local counting sort, no CTA barrier), and its lanes take
@@ -367,7 +393,7 @@ index_tails_kernel(const uint8_t* __restrict__ lists, uint64_t lists_bytes, cons
     uint4* stack = stacks + threadIdx.x;  // level-major: entry k at stack[k * kTailThreads]
     tail_warp_smem& W = wsm[threadIdx.x >> 5];
     const unsigned lane = threadIdx.x & 31u;
-    uint32_t P[256];  // freqs prefix sums of the tail in hand (local memory)
+    uint32_t P[256];  // the values of the tail in hand, in list order (local memory)
     // chunk (<= kTailChunk, a multiple of 32): small tables are cut finer so that every SM gets work
     const uint64_t n_chunks = (n_blocks + chunk - 1) / chunk;
     const uint64_t n_warps = (uint64_t(gridDim.x) * blockDim.x) >> 5;
@@ -419,14 +445,17 @@ index_tails_kernel(const uint8_t* __restrict__ lists, uint64_t lists_bytes, cons
             // (block_codecs.hpp:139-146); docid_i = cur_base + P_i + i (dict_posting_list.hpp:304-307,122)
             const uint32_t S = block_max - cur_base - (n - 1u);
             uint32_t* dd = docids ? docids + out_off : nullptr;
-            if (dd) dd[n - 1] = block_max;
             if (n > 1) {
                 bit_reader br;
                 br.init(lists, lists_bytes, p);
                 read_interpolative(br, n - 1, 0, S, stack, kTailThreads, [&](uint32_t idx, uint32_t val) {
-                    if (dd) dd[idx] = cur_base + val + idx;
+                    P[idx] = cur_base + val + idx;
                 });
                 p += (br.pos + 7) / 8;
+            }
+            if (dd) {
+                P[n - 1] = block_max;
+                write_tail<false>(dd, P, n);
             }
             if (!freqs) continue;
             // freqs: sum_of_values == -1 -> leading vbyte (block_codecs.hpp:134-136); prefix sums first
@@ -443,12 +472,7 @@ index_tails_kernel(const uint8_t* __restrict__ lists, uint64_t lists_bytes, cons
             }
             // adjacent differences (block_codecs.hpp:147-149), freq = v + 1
             P[n - 1] = Sf;
-            uint32_t prev = 0;
-            for (uint32_t j = 0; j < n; ++j) {
-                const uint32_t v = P[j];
-                ff[j] = v - prev + 1u;
-                prev = v;
-            }
+            write_tail<true>(ff, P, n);
         }
     }
 }
