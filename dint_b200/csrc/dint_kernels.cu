@@ -310,26 +310,32 @@ struct bit_reader {
 template <typename Emit>
 __device__ void read_interpolative(bit_reader& br, uint32_t n, uint32_t low0, uint32_t high0, uint4* stack, uint32_t stride,
                                    Emit&& emit) {
-    int sp = 1;
-    stack[0] = make_uint4(0u, n, low0, high0);
-    while (sp) {
-        --sp;
-        const uint4 e = stack[sp * stride];
-        uint32_t off = e.x, cnt = e.y, lo = e.z, hi = e.w;
-        for (;;) {
-            uint32_t h = cnt / 2;
-            uint32_t val = lo + br.read_int(hi - lo + 1u);
-            emit(off + h, val);
-            if (cnt == 1) break;
-            uint32_t rn = cnt - h - 1;
-            if (rn) {  // right half later
-                stack[sp * stride] = make_uint4(off + h + 1, rn, val, hi);
-                ++sp;
-            }
-            if (!h) break;
-            cnt = h;  // left half now
-            hi = val;
+    // ONE node per trip, whatever the shape of the tree: lanes that decode tails of similar length then stay in the
+    // same instructions (a walk down the left spine inside a pop loop made every lane wait for the longest spine)
+    int sp = 0;
+    bool have = n != 0u;
+    uint32_t off = 0, cnt = n, lo = low0, hi = high0;
+    for (;;) {
+        if (!have) {
+            if (sp == 0) break;
+            --sp;
+            const uint4 e = stack[sp * stride];
+            off = e.x;
+            cnt = e.y;
+            lo = e.z;
+            hi = e.w;
         }
+        const uint32_t h = cnt / 2;
+        const uint32_t val = lo + br.read_int(hi - lo + 1u);
+        emit(off + h, val);
+        const uint32_t rn = cnt - h - 1;
+        if (rn) {  // right half later
+            stack[sp * stride] = make_uint4(off + h + 1, rn, val, hi);
+            ++sp;
+        }
+        have = h != 0u;  // left half now
+        cnt = h;
+        hi = val;
     }
 }
 
