@@ -31,6 +31,7 @@ namespace {
 using namespace dintk;
 
 constexpr int kWarpsPerCta = 16;
+constexpr int kDefaultFreqsVariant = 7;  // strip decoder variant of frequency streams (7: bulk-copy flush)
 constexpr int kThreads = kWarpsPerCta * 32;
 constexpr uint32_t kImplicitUnit = 8;  // segments per work unit when the caller passes no unit table
 
@@ -937,7 +938,7 @@ static int strip_launch_setup(dint_dict* d) {
     d->strip_smem = fixed + size_t(d->strip_warps) * per_warp;
     d->strip_sms = di.sms;
     const char* v = std::getenv("DINT_B200_STRIP_VARIANT");
-    d->strip_variant = v && *v ? int(std::strtoul(v, nullptr, 10)) & 3 : -1;
+    d->strip_variant = v && *v ? int(std::strtoul(v, nullptr, 10)) & 7 : -1;
     // opt every instance in to the device's maximum once per device
     static std::mutex mu;
     static bool done[64] = {false};
@@ -952,6 +953,7 @@ static int strip_launch_setup(dint_dict* d) {
         OPT_IN(OUT_RAW)
         OPT_IN(OUT_DOCIDS)
         OPT_IN(OUT_FREQS)
+        CUDA_TRY(cudaFuncSetAttribute(decode_strips_kernel<OUT_FREQS, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
 #undef OPT_IN
         done[d->device] = true;
     }
@@ -990,7 +992,15 @@ int dint_decode_strips(const dint_dict* d, const uint8_t* d_in, size_t in_bytes,
     const size_t smem = d->strip_smem;
     const int grid = int(std::max<uint64_t>(1, std::min<uint64_t>((n_units + warps - 1) / warps, uint64_t(d->strip_sms))));
     // kernel variant (see decode_strips_kernel): d-gap streams 0, frequency streams 3; DINT_B200_STRIP_VARIANT overrides
-    const int variant = d->strip_variant >= 0 ? d->strip_variant : (mode == DINT_MODE_FREQS ? 3 : 0);
+    // (variant 7 = 3 + bulk-copy flush: frequency streams into a 16-byte aligned output)
+    int variant = d->strip_variant >= 0 ? d->strip_variant : (mode == DINT_MODE_FREQS ? kDefaultFreqsVariant : 0);
+    if (variant > 3 && (mode != DINT_MODE_FREQS || variant != 7 || (reinterpret_cast<uintptr_t>(d_out) & 15))) variant &= 3;
+    if (variant == 7) {
+        decode_strips_kernel<OUT_FREQS, 7><<<grid, warps * 32, smem, st>>>(P);
+        ++g_launches;
+        CUDA_TRY(cudaGetLastError());
+        return DINT_OK;
+    }
 #define LAUNCH_STRIPS_V(M, V) decode_strips_kernel<M, V><<<grid, warps * 32, smem, st>>>(P);
 #define LAUNCH_STRIPS(M)                                                                   \
     if (variant == 0) { LAUNCH_STRIPS_V(M, 0) } else if (variant == 1) { LAUNCH_STRIPS_V(M, 1) } \

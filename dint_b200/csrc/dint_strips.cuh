@@ -166,6 +166,37 @@ __device__ __forceinline__ void flush_image(uint32_t image_s, uint32_t bits_s, u
     }
 }
 
+// FREQS, VARIANT bit 2: the image already holds the final values (every store of the decode loop adds the +1), so
+// the flush is a copy: the aligned middle of the unit's slice goes out with ONE bulk shared -> global copy issued by
+// lane 0 (cp.async.bulk: the copy engine reads the image, no LDS.128 / STG.128 per lane), the partial quads at its
+// two ends with scalar stores. The caller waits for the copy to have READ the image before the next unit writes it.
+__device__ __forceinline__ void flush_image_bulk(uint32_t image_s, uint32_t* __restrict__ out, uint64_t out_off, uint32_t n_ints,
+                                                 unsigned lane) {
+    const uint32_t a = uint32_t(out_off) & 3u;
+    const uint32_t total = a + n_ints;
+    uint32_t* g0 = out + (out_off - a);                 // image word w <-> g0[w]
+    const uint32_t first = a ? min(4u, total) : 0u;     // words [a, first): head quad, partial
+    const uint32_t last = max(first, total & ~3u);      // words [last, total): tail quad, partial
+    if (lane < 4u) {
+        if (lane >= a && lane < first) st_stream(g0 + lane, lds_u32(image_s + (lane << 2)));
+        const uint32_t w = last + lane;
+        if (w < total && w >= first) st_stream(g0 + w, lds_u32(image_s + (w << 2)));
+    }
+    // generic-proxy writes of every lane -> visible to the async proxy, then one lane issues the copy
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0u && last > first) {
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g0 + first), "r"(image_s + (first << 2)),
+                     "r"((last - first) << 2)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+}
+__device__ __forceinline__ void bulk_flush_wait_read(unsigned lane) {
+    if (lane == 0u) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    __syncwarp();
+}
+
 // predicated shared loads: the destination keeps its value when the predicate is false (no branch)
 __device__ __forceinline__ void lds_u8_if(uint32_t& v, uint32_t a, bool p) {
     asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q ld.shared.u8 %0, [%1];\n\t}" : "+r"(v) : "r"(a), "r"(uint32_t(p)));
@@ -219,6 +250,9 @@ constexpr uint32_t kStripClassBytes = 8u * uint32_t(sizeof(strip_class));
 template <int MODE, int VARIANT>
 __global__ void __launch_bounds__(768, 1) decode_strips_kernel(const strip_params P) {
     constexpr bool REUSE = (VARIANT & 1) != 0, RUNFLAG = (VARIANT & 2) != 0;
+    // bit 2 (FREQS with RUNFLAG only): +1 folded into the stores, bulk-copy flush (needs a 16-byte aligned output)
+    constexpr bool BULK = (VARIANT & 4) != 0 && MODE == OUT_FREQS && RUNFLAG;
+    constexpr uint32_t kFill = BULK ? 1u : 0u;  // what a run codeword's integers read as in the image
     extern __shared__ __align__(16) uint8_t smem[];
     const unsigned lane = lane_id();
     const uint32_t warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
@@ -335,9 +369,10 @@ __global__ void __launch_bounds__(768, 1) decode_strips_kernel(const strip_param
                 start_word_s = bits_s + ((pos >> 5) << 2);
                 asm volatile("atom.shared.or.b32 _, [%0], %1;" ::"r"(start_word_s), "r"(1u << (pos & 31u)) : "memory");
             }
+            if (BULK) bulk_flush_wait_read(lane);  // the previous unit's copy has read the image
             if (RUNFLAG && H.has_runs())  // run codewords store nothing: they rely on a cleared image
                 for (uint32_t q = 4u * lane; q < a + n_ints; q += 128u)
-                    asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(image_s + (q << 2)), "r"(0u) : "memory");
+                    asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(image_s + (q << 2)), "r"(kFill) : "memory");
             cp_async_wait_all();
             __syncwarp();
 
@@ -349,21 +384,30 @@ __global__ void __launch_bounds__(768, 1) decode_strips_kernel(const strip_param
             // {image address | log2(length) << 24, dictionary row} and done for up to 64 codewords at a
             // time, so that one round trip to L2 serves all of them.
             uint32_t qn = 0;
+            auto plus = [](uint4 v) {  // BULK: the image holds final freqs (v + 1)
+                if (BULK) {
+                    v.x += 1u;
+                    v.y += 1u;
+                    v.z += 1u;
+                    v.w += 1u;
+                }
+                return v;
+            };
             auto drain = [&]() {
                 __syncwarp();
                 for (uint32_t k = lane; k < qn; k += 32u) {
                     uint32_t ex, ey;
                     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(ex), "=r"(ey) : "r"(queue_s + 8u * k));
                     const uint4* rp = reinterpret_cast<const uint4*>(dv.rows + size_t(ey) * dint::kEntry);
-                    const uint4 r = __ldg(rp);
+                    const uint4 r = plus(__ldg(rp));
                     const uint32_t oo = ex & 0xFFFFFFu, cc = ex >> 24;
                     sts_u32(oo, r.x);
                     sts_tail3_log2(oo, cc, r.y, r.z, r.w);
                     if (cc > 2u) {
-                        sts_4(oo + 16u, __ldg(rp + 1));
+                        sts_4(oo + 16u, plus(__ldg(rp + 1)));
                         if (cc > 3u) {
-                            sts_4(oo + 32u, __ldg(rp + 2));
-                            sts_4(oo + 48u, __ldg(rp + 3));
+                            sts_4(oo + 32u, plus(__ldg(rp + 2)));
+                            sts_4(oo + 48u, plus(__ldg(rp + 3)));
                         }
                     }
                 }
@@ -387,14 +431,15 @@ __global__ void __launch_bounds__(768, 1) decode_strips_kernel(const strip_param
             auto put = [&](uint32_t oo, uint32_t sym, bool on, bool dichot, uint32_t code, uint4 r, uint32_t pay) {
                 const uint32_t words = dichot ? code : 0u;
                 if (sym < 2u) r.x = pay;
+                r = plus(r);
                 if (on && (sym < 2u || dichot)) sts_u32(oo, r.x);
                 sts_tail3_log2(oo, words, r.y, r.z, r.w);
                 if (words > 2u) {
-                    sts_4(oo + 16u, lds_v4(hot0_s + hot1_delta + (sym << 4)));
+                    sts_4(oo + 16u, plus(lds_v4(hot0_s + hot1_delta + (sym << 4))));
                     if (words > 3u) {
                         const uint4* rp = reinterpret_cast<const uint4*>(dv.rows + size_t(c_row_base + sym) * dint::kEntry);
-                        sts_4(oo + 32u, __ldg(rp + 2));
-                        sts_4(oo + 48u, __ldg(rp + 3));
+                        sts_4(oo + 32u, plus(__ldg(rp + 2)));
+                        sts_4(oo + 48u, plus(__ldg(rp + 3)));
                     }
                 }
             };
@@ -453,7 +498,9 @@ __global__ void __launch_bounds__(768, 1) decode_strips_kernel(const strip_param
         if (n_valid) stage(N.in_off(), N.in_len());
 
         // ---- write the unit ------------------------------------------------------------------------------------
-        if (valid) {
+        if (valid && BULK) {
+            flush_image_bulk(image_s, P.out, out_off, n_ints, lane);
+        } else if (valid) {
             flush_image<MODE, !RUNFLAG>(image_s, bits_s, P.out, out_off, n_ints, doc_base, (starts & ~1u) != 0u, vec_ok, lane);
             if (MODE == OUT_DOCIDS && start_word_s) sts_u32(start_word_s, 0u);
             __syncwarp();
@@ -463,6 +510,10 @@ __global__ void __launch_bounds__(768, 1) decode_strips_kernel(const strip_param
         valid = n_valid;
     }
     cp_async_wait_all();
+    if (BULK) {  // the last copy must be complete before the CTA (and its shared memory) goes away
+        if (lane == 0u) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        __syncwarp();
+    }
 }
 
 }  // namespace dintk

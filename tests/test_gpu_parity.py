@@ -301,6 +301,22 @@ def test_strips_unaligned_output_and_input(golden, type_, shift):
     assert np.all(got[:shift] == 0xFFFFFFFF) and np.all(got[shift + vf.n_ints:] == 0xFFFFFFFF)
 
 
+@pytest.mark.parametrize("type_", ("single_packed_dint", "multi_packed_dint"))
+@pytest.mark.parametrize("shift", (0, 1, 2, 3))
+def test_strips_freqs_bulk_flush_and_its_fallback(golden, type_, shift):
+    """frequency streams leave the shared-memory image with one bulk copy per unit (cp.async.bulk) when the output is
+    16-byte aligned, and with the per-lane flush otherwise: both must give the collection's freqs, and nothing may be
+    written outside the output slice (partial quads at both ends of every unit)"""
+    bin_ = golden.bytes(golden.vroom_name(type_, "freqs"))
+    vf = driver.VroomFile(type_, bin_, golden.bytes(golden.dict_name(type_, "freqs")))
+    out = torch.full((vf.n_ints + 8,), -1, dtype=torch.int32, device="cuda")
+    capi.decode_strips(vf.dict, vf.d_in.data_ptr(), len(bin_), vf.d_strip_units.data_ptr(), int(vf.plan.n_strip_units),
+                       out.data_ptr() + 4 * shift, capi.MODE_FREQS, stream=torch.cuda.current_stream().cuda_stream)
+    got = _np(out)
+    assert g.sha(got[shift:shift + vf.n_ints].tobytes()) == golden.sha["freqs_sha256"]
+    assert np.all(got[:shift] == 0xFFFFFFFF) and np.all(got[shift + vf.n_ints:] == 0xFFFFFFFF)
+
+
 def test_strips_rejects_units_beyond_the_limits(golden, vroom_files):
     """a unit the decoder cannot hold (corrupt table: too many integers / bytes / strips, or input past the end)
     is skipped: its slice of the output stays untouched, every other unit decodes, nothing faults"""
