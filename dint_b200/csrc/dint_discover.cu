@@ -4,6 +4,9 @@
 // Replaces, for files that are already in HBM, the serial host walk of dint_vroom_plan_create: the only
 // host work left is O(chains) bookkeeping (a prefix sum over a few thousand chain totals).
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <ctime>
 #include <memory>
 #include <vector>
 
@@ -58,6 +61,21 @@ int walk_grid(K kernel, const dint_dict* d, int warps, uint64_t want_warps, int*
 }
 
 constexpr int kWalkWarps = 16;
+
+// DINT_B200_TRACE=1: host timestamps of the discovery's steps on stderr (diagnostics)
+struct tracer {
+    bool on;
+    double t0;
+    static double now() {
+        timespec ts;
+        clock_gettime(CLOCK_MONOTONIC, &ts);
+        return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+    }
+    tracer() : on(std::getenv("DINT_B200_TRACE") != nullptr), t0(now()) {}
+    void operator()(const char* what) {
+        if (on) std::fprintf(stderr, "[dint trace] %8.2f ms  %s\n", now() - t0, what);
+    }
+};
 
 }  // namespace
 
@@ -293,12 +311,15 @@ int dint_vroom_discover(const dint_dict* d, const uint8_t* d_in, size_t in_bytes
         }
         return DINT_OK;
     };
+    tracer trace0;
+    tracer* tr_ptr = &trace0;
     // count pass of a repair round / emit pass with host-computed bases (the slow path)
     auto run_pass = [&](std::vector<chain>& chains, const std::vector<uint32_t>& ids, bool emit, const std::vector<uint64_t>* bases) -> int {
         pass_bufs pb;
         int rc2 = prepare(chains, ids, pb);
         if (rc2 || !pb.n) return rc2;
         const uint64_t n = pb.n;
+        if (emit) tr_ptr->operator()("  emit: prepared");
         if (emit) {  // counts of the count pass (checked by the emit pass) + bases, both at slot 8k
             std::vector<uint64_t> wide(8 * n, 0), b(8 * n, 0);
             for (uint64_t k = 0; k < n; ++k) {
@@ -312,10 +333,13 @@ int dint_vroom_discover(const dint_dict* d, const uint8_t* d_in, size_t in_bytes
             CUDA_TRY(cudaMemcpyAsync(pb.d_bases.p, b.data(), 8 * n * 8, cudaMemcpyHostToDevice, st));
             CUDA_TRY(cudaStreamSynchronize(st));
         }
+        if (emit) tr_ptr->operator()("  emit: uploaded");
         rc2 = launch(pb, emit);
         if (rc2) return rc2;
         if (!emit) return fetch(pb, chains, ids);
+        tr_ptr->operator()("  emit: launched");
         CUDA_TRY(cudaStreamSynchronize(st));
+        tr_ptr->operator()("  emit: synced");
         return DINT_OK;
     };
     auto finish = [&](uint64_t lists, uint64_t ints) -> int {
@@ -345,6 +369,7 @@ int dint_vroom_discover(const dint_dict* d, const uint8_t* d_in, size_t in_bytes
         return DINT_OK;
     };
 
+    tracer tr;
     try {
         // ---- count pass + repair rounds ------------------------------------------------------------------------------
         // Every candidate start gets a chain that runs to the next candidate. A chain that starts at a true list start
@@ -411,9 +436,11 @@ int dint_vroom_discover(const dint_dict* d, const uint8_t* d_in, size_t in_bytes
                 return DINT_OK;
             }
             // some chain did not land on its successor (or is malformed): repair on the host, from these counts
+            tr("fast path refused");
             rc = fetch(pb, chains, todo);
             if (rc) return rc;
             first_counted = true;
+            tr("counts fetched");
         }
         for (uint32_t round = 0;; ++round) {
             if (!(round == 0 && first_counted)) {
@@ -480,6 +507,7 @@ int dint_vroom_discover(const dint_dict* d, const uint8_t* d_in, size_t in_bytes
             }
             ++plan->retries;
         }
+        tr("linked");
         CUDA_TRY(cudaEventRecord(evc, st));
         // ---- bases of every linked chain (host: one pass over the chain totals) ---------------------------------------
         std::vector<uint64_t> bases(chains.size() * 4 + 4, 0);
@@ -494,11 +522,14 @@ int dint_vroom_discover(const dint_dict* d, const uint8_t* d_in, size_t in_bytes
             ints += c.ints;
             units += c.units;
         }
+        tr("bases");
         rc = allocate_outputs(lists, ints, units, linked.size());
         if (rc) return rc;
+        tr("allocated");
         if (!linked.empty()) {
             rc = run_pass(chains, linked, true, &bases);
             if (rc) return rc;
+            tr("emit pass done");
             uint32_t h_status = 0;
             CUDA_TRY(cudaMemcpy(&h_status, d_status.p, 4, cudaMemcpyDeviceToHost));
             if (h_status != WALK_OK) {
