@@ -47,6 +47,9 @@ SYMBOLS = [
     "dint_device_plan_units", "dint_device_plan_list_offsets", "dint_device_plan_list_byte_offsets",
     "dint_decode_index_planned", "dint_vroom_ctx_create_discover", "dint_vroom_ctx_num_lists",
     "dint_vroom_ctx_num_ints", "dint_vroom_ctx_device_plan", "dint_vroom_ctx_results", "dint_and_queries",
+    "dint_index_device_plan_create", "dint_device_index_destroy", "dint_device_index_num_lists", "dint_device_index_num_docs",
+    "dint_device_index_num_postings", "dint_device_index_num_blocks", "dint_device_index_build_ms", "dint_device_index_blocks",
+    "dint_device_index_list_offsets", "dint_device_index_endpoints", "dint_device_index_layout",
 ]
 
 
@@ -141,6 +144,18 @@ def lib():
         L.dint_vroom_ctx_device_plan.restype = vp
         L.dint_vroom_ctx_results.argtypes = [vp, vp, vp, vp]
         L.dint_and_queries.argtypes = [vp, vp, sz, vp, vp, sz, vp, vp]
+        L.dint_index_device_plan_create.argtypes = [i32, vp, sz, vp, i32, u32, vp, C.POINTER(vp)]
+        L.dint_device_index_destroy.argtypes = [vp]
+        L.dint_device_index_destroy.restype = None
+        for f in ("num_lists", "num_docs", "num_postings", "num_blocks"):
+            getattr(L, "dint_device_index_" + f).argtypes = [vp]
+            getattr(L, "dint_device_index_" + f).restype = u64
+        L.dint_device_index_build_ms.argtypes = [vp]
+        L.dint_device_index_build_ms.restype = C.c_double
+        for f in ("blocks", "list_offsets", "endpoints"):
+            getattr(L, "dint_device_index_" + f).argtypes = [vp]
+            getattr(L, "dint_device_index_" + f).restype = vp
+        L.dint_device_index_layout.argtypes = [vp] + [C.POINTER(u64)] * 5
         _lib = L
     return _lib
 
@@ -389,6 +404,42 @@ class IndexPlan:
         self.lists_off, self.lists_len, self.docs_dict_off, self.freqs_dict_off, self.end_off = [x.value for x in v]
         self.block_size = block_size
         L.dint_index_plan_destroy(h)
+
+
+class DeviceIndexPlan:
+    """Block table of a frozen dict_freq_index built ON THE DEVICE (dint_index_device_plan_create): the host reads
+    only the fixed-size header of the file; endpoints, list offsets and blocks stay in HBM."""
+
+    def __init__(self, kind, data, d_bin_ptr, device=0, block_size=256, stream=0):
+        a = np.frombuffer(data, dtype=np.uint8)
+        h = C.c_void_p()
+        check(lib().dint_index_device_plan_create(kind, _np_ptr(a), len(a), d_bin_ptr, device, block_size, stream, C.byref(h)))
+        L = lib()
+        self.handle = h
+        self.kind = kind
+        self.block_size = block_size
+        self.n_lists = L.dint_device_index_num_lists(h)
+        self.num_docs = L.dint_device_index_num_docs(h)
+        self.n_postings = L.dint_device_index_num_postings(h)
+        self.n_blocks = L.dint_device_index_num_blocks(h)
+        self.build_ms = L.dint_device_index_build_ms(h)
+        self.blocks_ptr = L.dint_device_index_blocks(h)
+        self.list_offsets_ptr = L.dint_device_index_list_offsets(h)
+        self.endpoints_ptr = L.dint_device_index_endpoints(h)
+        v = [C.c_uint64(0) for _ in range(5)]
+        check(L.dint_device_index_layout(h, *[C.byref(x) for x in v]))
+        self.lists_off, self.lists_len, self.docs_dict_off, self.freqs_dict_off, self.end_off = [x.value for x in v]
+
+    def close(self):
+        if getattr(self, "handle", None):
+            lib().dint_device_index_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def decode_segments(dictionary, d_in_ptr, in_bytes, d_segs_ptr, n_segs, d_out_ptr, mode, stream=0, block_size=256):

@@ -12,6 +12,7 @@
 
 #include "dint_cuda_util.hpp"
 #include "dint_discover.cuh"
+#include "dint_index_blocks.cuh"
 
 using namespace dintk;
 
@@ -655,6 +656,174 @@ int dint_index_discover(const dint_dict* docs_dict, const dint_dict* freqs_dict,
     }
     *docs_plan = plans[0].release();
     *freqs_plan = plans[1].release();
+    return DINT_OK;
+}
+
+
+// ---- block table of a frozen index, built on the device -------------------------------------------------------
+void dint_device_index_destroy(dint_device_index* p) {
+    if (!p) return;
+    {
+        device_guard g(p->device);
+        cudaFree(p->d_endpoints);
+        cudaFree(p->d_list_offsets);
+        cudaFree(p->d_blocks);
+    }
+    delete p;
+}
+uint64_t dint_device_index_num_lists(const dint_device_index* p) { return p ? p->h.n_lists : 0; }
+uint64_t dint_device_index_num_docs(const dint_device_index* p) { return p ? p->h.num_docs : 0; }
+uint64_t dint_device_index_num_postings(const dint_device_index* p) { return p ? p->n_postings : 0; }
+uint64_t dint_device_index_num_blocks(const dint_device_index* p) { return p ? p->n_blocks : 0; }
+double dint_device_index_build_ms(const dint_device_index* p) { return p ? double(p->build_ms) : 0.0; }
+const dint_block* dint_device_index_blocks(const dint_device_index* p) { return p ? p->d_blocks : nullptr; }
+const uint64_t* dint_device_index_list_offsets(const dint_device_index* p) { return p ? p->d_list_offsets : nullptr; }
+const uint64_t* dint_device_index_endpoints(const dint_device_index* p) { return p ? p->d_endpoints : nullptr; }
+int dint_device_index_layout(const dint_device_index* p, uint64_t* lists_off, uint64_t* lists_len, uint64_t* docs_dict_off,
+                             uint64_t* freqs_dict_off, uint64_t* end_off) {
+    if (!p) return DINT_E_ARG;
+    if (lists_off) *lists_off = p->h.lists_off;
+    if (lists_len) *lists_len = p->h.lists_len;
+    if (docs_dict_off) *docs_dict_off = p->h.docs_dict_off;
+    if (freqs_dict_off) *freqs_dict_off = p->h.freqs_dict_off;
+    if (end_off) *end_off = p->h.end_off;
+    return DINT_OK;
+}
+
+int dint_index_device_plan_create(int kind, const void* h_bin, size_t len, const uint8_t* d_bin, int device, uint32_t block_size,
+                                  void* stream, dint_device_index** out) {
+    if (!h_bin || !d_bin || !out) return DINT_E_ARG;
+    if (!block_size) block_size = dint::kDefaultBlock;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        dint::set_error("no CUDA device: dint_b200 has no CPU fallback");
+        return DINT_E_NODEVICE;
+    }
+    std::unique_ptr<dint_device_index, void (*)(dint_device_index*)> ix(new (std::nothrow) dint_device_index, dint_device_index_destroy);
+    if (!ix) return DINT_E_NOMEM;
+    ix->device = device;
+    ix->kind = kind;
+    int rc = dint::index_header_parse(kind, static_cast<const uint8_t*>(h_bin), len, &ix->h);  // O(1) host work
+    if (rc) return rc;
+    const dint_index_header& H = ix->h;
+    device_guard g(device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    device_info di;
+    rc = get_device_info(device, &di);
+    if (rc) return rc;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    CUDA_TRY(cudaEventCreate(&ev0));
+    CUDA_TRY(cudaEventCreate(&ev1));
+    struct ev_guard {
+        cudaEvent_t a, b;
+        ~ev_guard() {
+            cudaEventDestroy(a);
+            cudaEventDestroy(b);
+        }
+    } evg{ev0, ev1};
+    CUDA_TRY(cudaEventRecord(ev0, st));
+    const uint64_t n = H.n_lists;
+    CUDA_TRY(cudaMalloc(&ix->d_endpoints, (n + 1) * 8));
+    CUDA_TRY(cudaMalloc(&ix->d_list_offsets, (n + 1) * 8));
+    dev_buf d_status;
+    CUDA_TRY(cudaMalloc(&d_status.p, 16));
+    CUDA_TRY(cudaMemsetAsync(d_status.p, 0, 16, st));
+    const uint64_t lists_len = H.lists_len;
+    CUDA_TRY(cudaMemcpyAsync(ix->d_endpoints + n, &lists_len, 8, cudaMemcpyHostToDevice, st));
+    if (n) {
+        // ---- Elias-Fano endpoints --------------------------------------------------------------------------------
+        ef_params E;
+        E.words = d_bin + H.ef_words_off;
+        E.n = n;
+        E.hb_off = H.hb_off;
+        E.hb_len = H.hb_len;
+        E.lb_off = H.lb_off;
+        E.l = uint32_t(H.l);
+        E.n_hwords = (H.hb_len + 63) / 64;
+        dev_buf d_popc, d_rank;
+        CUDA_TRY(cudaMalloc(&d_popc.p, E.n_hwords * 4));
+        CUDA_TRY(cudaMalloc(&d_rank.p, (E.n_hwords + 1) * 8));
+        E.popc = d_popc.as<uint32_t>();
+        E.rank = d_rank.as<uint64_t>();
+        E.endpoints = ix->d_endpoints;
+        const int grid = int(std::max<uint64_t>(1, std::min<uint64_t>((E.n_hwords + 255) / 256, uint64_t(di.sms) * 8)));
+        ef_popc_kernel<<<grid, 256, 0, st>>>(E);
+        scan_u32_kernel<<<1, 1024, 0, st>>>(E.popc, d_rank.as<uint64_t>(), E.n_hwords);
+        ef_emit_kernel<<<grid, 256, 0, st>>>(E);
+        g_launches += 3;
+        CUDA_TRY(cudaGetLastError());
+        uint64_t ones = 0;
+        CUDA_TRY(cudaMemcpyAsync(&ones, d_rank.as<uint64_t>() + E.n_hwords, 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if (ones < n) {
+            dint::set_error("index .bin: Elias-Fano: fewer endpoints than lists");
+            return DINT_E_FORMAT;
+        }
+        // ---- list headers -> postings and blocks per list -> their prefix sums ---------------------------------------
+        dev_buf d_n, d_nb, d_bbase;
+        CUDA_TRY(cudaMalloc(&d_n.p, n * 4));
+        CUDA_TRY(cudaMalloc(&d_nb.p, n * 4));
+        CUDA_TRY(cudaMalloc(&d_bbase.p, (n + 1) * 8));
+        index_lists_params L;
+        L.lists = d_bin + H.lists_off;
+        L.lists_len = H.lists_len;
+        L.n = n;
+        L.block_size = block_size;
+        L.endpoints = ix->d_endpoints;
+        L.list_n = d_n.as<uint32_t>();
+        L.list_blocks = d_nb.as<uint32_t>();
+        L.status = d_status.as<uint32_t>();
+        const int lgrid = int(std::max<uint64_t>(1, std::min<uint64_t>((n + 255) / 256, uint64_t(di.sms) * 8)));
+        index_lists_kernel<<<lgrid, 256, 0, st>>>(L);
+        scan_u32_kernel<<<1, 1024, 0, st>>>(L.list_n, ix->d_list_offsets, n);
+        scan_u32_kernel<<<1, 1024, 0, st>>>(L.list_blocks, d_bbase.as<uint64_t>(), n);
+        g_launches += 3;
+        CUDA_TRY(cudaGetLastError());
+        uint64_t totals[2] = {0, 0};
+        uint32_t h_status = 0;
+        CUDA_TRY(cudaMemcpyAsync(&totals[0], ix->d_list_offsets + n, 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(&totals[1], d_bbase.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(&h_status, d_status.p, 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if (h_status) {
+            dint::set_error("index .bin: bad list header or endpoint (device walk)");
+            return DINT_E_FORMAT;
+        }
+        ix->n_postings = totals[0];
+        ix->n_blocks = totals[1];
+        // ---- the block table ----------------------------------------------------------------------------------------
+        CUDA_TRY(cudaMalloc(&ix->d_blocks, (ix->n_blocks + 1) * sizeof(dint_block)));
+        index_blocks_params B;
+        B.lists = L.lists;
+        B.lists_len = H.lists_len;
+        B.n = n;
+        B.block_size = block_size;
+        B.endpoints = ix->d_endpoints;
+        B.list_n = L.list_n;
+        B.list_offsets = ix->d_list_offsets;
+        B.block_base = d_bbase.as<uint64_t>();
+        B.blocks = ix->d_blocks;
+        B.status = d_status.as<uint32_t>();
+        const uint64_t groups = (n + 31) / 32;
+        const int bgrid = int(std::max<uint64_t>(1, std::min<uint64_t>((groups + 7) / 8, uint64_t(di.sms) * 8)));
+        index_blocks_kernel<<<bgrid, 256, 0, st>>>(B);
+        ++g_launches;
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(&h_status, d_status.p, 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if (h_status) {
+            dint::set_error("index .bin: block endpoint out of range (device walk)");
+            return DINT_E_FORMAT;
+        }
+    } else {
+        const uint64_t zero = 0;
+        CUDA_TRY(cudaMemcpyAsync(ix->d_list_offsets, &zero, 8, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMalloc(&ix->d_blocks, sizeof(dint_block)));
+    }
+    CUDA_TRY(cudaEventRecord(ev1, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaEventElapsedTime(&ix->build_ms, ev0, ev1));
+    *out = ix.release();
     return DINT_OK;
 }
 

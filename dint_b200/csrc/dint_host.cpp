@@ -220,6 +220,71 @@ static int validate(dint_dict* d) {
     return DINT_OK;
 }
 
+// extent of `nvec` mappable_vector<uint32_t> images (u64 count + payload each, mapper.hpp:128-146): sizes only
+static bool mapped_extent(int kind, const uint8_t* p, size_t len, size_t* used) {
+    const int nvec = kind == DINT_DICT_RECT ? 1 : kind == DINT_DICT_PACKED ? 2 : 3;
+    size_t off = 0;
+    for (int v = 0; v < nvec; ++v) {
+        if (off + 8 > len) return false;
+        const uint64_t cnt = rd64(p + off);
+        off += 8;
+        if (cnt > (len - off) / 4) return false;
+        off += size_t(cnt) * 4;
+    }
+    *used = off;
+    return true;
+}
+
+// The header walk of dint_index_plan_create without touching anything that grows with the collection:
+// u64 freeze flags | global_parameters 5 x u8 | u64 m_size | u64 m_num_docs | bit_vector { u64 bits, u64 words, words }
+// | u64 m_lists.size | m_lists | docs dictionary | freqs dictionary (dict_freq_index.hpp:209-214, mapper.hpp:100-156)
+int index_header_parse(int kind, const uint8_t* bin, size_t len, dint_index_header* h) {
+    auto bad = [&](const char* m) {
+        set_error(std::string("index .bin: ") + m);
+        return DINT_E_FORMAT;
+    };
+    if (kind < 0 || kind > 2) return DINT_E_ARG;
+    size_t off = 8;
+    if (len < off + 5 + 32) return bad("truncated header");
+    const uint32_t log_s0 = bin[off], log_s1 = bin[off + 1];
+    off += 5;
+    h->n_lists = rd64(bin + off);
+    h->num_docs = rd64(bin + off + 8);
+    h->ef_bits = rd64(bin + off + 16);
+    h->ef_words = rd64(bin + off + 24);
+    off += 32;
+    if (h->ef_words > (len - off) / 8 || h->ef_bits > h->ef_words * 64) return bad("endpoints bit vector out of range");
+    h->ef_words_off = off;
+    off += size_t(h->ef_words) * 8;
+    if (off + 8 > len) return bad("truncated m_lists");
+    h->lists_len = rd64(bin + off);
+    off += 8;
+    h->lists_off = off;
+    if (h->lists_len > len - off) return bad("m_lists out of range");
+    off += size_t(h->lists_len);
+    h->docs_dict_off = off;
+    size_t used = 0;
+    if (!mapped_extent(kind, bin + off, len - off, &used)) return bad("docs dictionary");
+    off += used;
+    h->freqs_dict_off = off;
+    if (!mapped_extent(kind, bin + off, len - off, &used)) return bad("freqs dictionary");
+    off += used;
+    h->end_off = off;
+    if (off != len) return bad("trailing bytes");
+    const uint64_t n = h->n_lists, universe = h->lists_len;
+    if (n > universe || n > h->ef_bits) return bad("list count out of range");
+    if (n) {  // compact_elias_fano.hpp:14-61
+        h->l = universe > n ? msb64(universe / n) : 0;
+        h->hb_len = n + (universe >> h->l) + 2;
+        const uint64_t ptr_size = h->hb_len > 1 ? msb64(h->hb_len - 1) + 1 : 0;
+        const uint64_t p0 = (h->hb_len - n) >> log_s0, p1 = n >> log_s1;
+        h->hb_off = (p0 + p1) * ptr_size;
+        h->lb_off = h->hb_off + h->hb_len;
+        if (h->lb_off + n * h->l != h->ef_bits) return bad("Elias-Fano geometry mismatch");
+    }
+    return DINT_OK;
+}
+
 }  // namespace dint
 
 using namespace dint;

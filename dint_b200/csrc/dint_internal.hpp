@@ -156,6 +156,29 @@ struct dint_device_plan {
     uint64_t n_sync_found = 0;                // sync points the speculative search contributed
 };
 
+// Fixed-size header of a frozen dict_freq_index .bin: everything the host reads of the file when the block table is
+// built on the device (dint_index_device_plan_create)
+struct dint_index_header {
+    uint64_t n_lists = 0, num_docs = 0;
+    uint64_t ef_words_off = 0, ef_bits = 0, ef_words = 0;  // byte offset of the bit vector's words, its bits / words
+    uint64_t l = 0, hb_off = 0, hb_len = 0, lb_off = 0;    // Elias-Fano geometry (bit offsets inside the vector)
+    uint64_t lists_off = 0, lists_len = 0, docs_dict_off = 0, freqs_dict_off = 0, end_off = 0;
+};
+namespace dint {
+int index_header_parse(int kind, const uint8_t* bin, size_t len, dint_index_header* h);  // dint_host.cpp
+}
+
+// Block table + list offsets + endpoints of a frozen index, built on the device (dint_discover.cu)
+struct dint_device_index {
+    int device = -1, kind = 0;
+    dint_index_header h;
+    uint64_t n_postings = 0, n_blocks = 0;
+    uint64_t* d_endpoints = nullptr;     // n_lists + 1 byte offsets in m_lists
+    uint64_t* d_list_offsets = nullptr;  // n_lists + 1 postings
+    dint_block* d_blocks = nullptr;      // n_blocks
+    float build_ms = 0.f;                // device timeline (CUDA events)
+};
+
 // implemented in dint_kernels.cu
 int dint_dict_upload(dint_dict* d);
 void dint_dict_release_device(dint_dict* d);

@@ -151,13 +151,29 @@ class ShardedVroomFile(VroomFile):
 class IndexFile:
     """A frozen dict_freq_index .bin resident on one GPU (dictionaries are read from the file)."""
 
-    def __init__(self, type_, bin_bytes, device=0, block_size=256):
+    def __init__(self, type_, bin_bytes, device=0, block_size=256, plan="host"):
+        """plan="host": header, Elias-Fano endpoints and block tables expanded on the host (dint_index_plan_create);
+        plan="device": the host reads the fixed-size header only, the GPU builds the block table from the bytes in HBM
+        (dint_index_device_plan_create)"""
         if type_ not in capi.KIND_OF_TYPE:
             raise ValueError(f"unknown type '{type_}'")
         self.type = type_
         self.dev = _require_cuda(device)
         kind = capi.KIND_OF_TYPE[type_]
         self.block_size = block_size
+        self.docs_plan = self.freqs_plan = None
+        if plan == "device":
+            self.d_bin = _to_device_bytes(bin_bytes, self.dev)
+            with torch.cuda.device(self.dev):
+                st = torch.cuda.current_stream(self.dev).cuda_stream
+                self.plan = capi.DeviceIndexPlan(kind, bin_bytes, self.d_bin.data_ptr(), device=device, block_size=block_size, stream=st)
+            p = self.plan
+            self.docs_dict = capi.Dictionary(kind, bin_bytes[p.docs_dict_off:p.freqs_dict_off], device=device, mapped=True)
+            self.freqs_dict = capi.Dictionary(kind, bin_bytes[p.freqs_dict_off:p.end_off], device=device, mapped=True)
+            self.n_postings, self.n_lists = int(p.n_postings), int(p.n_lists)
+            self.d_blocks = device_view(p.blocks_ptr, int(p.n_blocks) * 32, "|u1", self.dev)
+            self.d_list_offsets = device_view(p.list_offsets_ptr, self.n_lists + 1, "<i8", self.dev)
+            return
         self.plan = capi.IndexPlan(kind, bin_bytes, block_size=block_size)
         p = self.plan
         self.docs_dict = capi.Dictionary(kind, bin_bytes[p.docs_dict_off:p.freqs_dict_off], device=device, mapped=True)

@@ -53,7 +53,7 @@
 extern "C" {
 #endif
 
-#define DINT_B200_ABI_VERSION 5 /* 5: device-side discovery (dint_vroom_discover, dint_index_discover, dint_device_plan_*) */
+#define DINT_B200_ABI_VERSION 6 /* 5: device-side discovery (dint_vroom_discover, dint_index_discover, dint_device_plan_*); 6: dint_index_device_plan_create, dint_and_queries */
 
 /* dictionary kinds == the reference's three dictionary types */
 enum {
@@ -146,6 +146,7 @@ typedef struct dint_vroom_plan dint_vroom_plan;
 typedef struct dint_index_plan dint_index_plan;
 typedef struct dint_vroom_ctx dint_vroom_ctx;
 typedef struct dint_device_plan dint_device_plan;
+typedef struct dint_device_index dint_device_index;
 
 const char* dint_last_error(void);
 int dint_abi_version(void);
@@ -235,6 +236,25 @@ int dint_vroom_discover(const dint_dict* d, const uint8_t* d_in, size_t in_bytes
 int dint_index_discover(const dint_dict* docs_dict, const dint_dict* freqs_dict, const uint8_t* d_lists, size_t lists_bytes,
                         const dint_block* d_blocks, size_t n_blocks, uint32_t block_size, void* stream,
                         dint_device_plan** docs_plan, dint_device_plan** freqs_plan);
+/* Device-side twin of dint_index_plan_create for an index file that is already in HBM (d_bin: DEVICE pointer to the
+ * whole .bin image on `device`; h_bin: the same bytes on the host, of which ONLY the fixed-size header and the size
+ * fields of the embedded vectors are read — nothing that grows with the collection). The GPU expands the
+ * Elias-Fano list endpoints (compact_elias_fano.hpp:14-61), parses every list header (dict_posting_list.hpp:90-107)
+ * and writes the dint_block table + list offsets; they stay in HBM (accessors below return DEVICE pointers).
+ * Synchronises `stream`. */
+int dint_index_device_plan_create(int kind, const void* h_bin, size_t len, const uint8_t* d_bin, int device, uint32_t block_size,
+                                  void* stream, dint_device_index** out);
+void dint_device_index_destroy(dint_device_index* p);
+uint64_t dint_device_index_num_lists(const dint_device_index* p);
+uint64_t dint_device_index_num_docs(const dint_device_index* p);
+uint64_t dint_device_index_num_postings(const dint_device_index* p);
+uint64_t dint_device_index_num_blocks(const dint_device_index* p);
+double dint_device_index_build_ms(const dint_device_index* p);               /* device timeline, CUDA events */
+const dint_block* dint_device_index_blocks(const dint_device_index* p);      /* DEVICE, num_blocks entries */
+const uint64_t* dint_device_index_list_offsets(const dint_device_index* p);  /* DEVICE, num_lists + 1 */
+const uint64_t* dint_device_index_endpoints(const dint_device_index* p);     /* DEVICE, num_lists + 1 byte offsets in m_lists */
+int dint_device_index_layout(const dint_device_index* p, uint64_t* lists_off, uint64_t* lists_len, uint64_t* docs_dict_off,
+                             uint64_t* freqs_dict_off, uint64_t* end_off);
 void dint_device_plan_destroy(dint_device_plan* p);
 uint64_t dint_device_plan_num_lists(const dint_device_plan* p);
 uint64_t dint_device_plan_num_ints(const dint_device_plan* p);

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), f"{n} declared in include/dint_b200.h but not exported"
     assert sorted(capi.SYMBOLS) == names
-    assert L.dint_abi_version() == 5
+    assert L.dint_abi_version() == 6
 
 
 def test_struct_layouts_match_header():

@@ -237,3 +237,46 @@ def test_index_block_size_out_of_range_is_rejected(golden):
         capi.decode_index(idx.docs_dict, idx.freqs_dict, idx.d_bin.data_ptr() + p.lists_off, p.lists_len,
                           idx.d_blocks.data_ptr(), int(p.n_blocks), 2048, out.data_ptr(), None)
     assert e.value.code == -1
+
+
+@pytest.mark.parametrize("type_", g.TYPES)
+def test_index_block_table_built_on_the_device(golden, type_):
+    """dint_index_device_plan_create: Elias-Fano endpoints, list offsets and the block table found by the GPU are
+    exactly the host pre-pass's, and the scan through them gives the reference enumerator's output"""
+    data = golden.bytes(golden.index_name(type_))
+    host = capi.IndexPlan(capi.KIND_OF_TYPE[type_], data)
+    idx = driver.IndexFile(type_, data, plan="device")
+    p = idx.plan
+    assert (p.n_lists, p.n_postings, p.n_blocks, p.num_docs) == (host.n_lists, host.n_postings, host.n_blocks, host.num_docs)
+    assert (p.lists_off, p.lists_len, p.docs_dict_off, p.freqs_dict_off, p.end_off) == \
+        (host.lists_off, host.lists_len, host.docs_dict_off, host.freqs_dict_off, host.end_off)
+    ep = driver.device_view(p.endpoints_ptr, p.n_lists + 1, "<i8", idx.dev).cpu().numpy().astype(np.uint64)
+    assert np.array_equal(ep, host.endpoints)
+    assert np.array_equal(idx.d_list_offsets.cpu().numpy().astype(np.uint64), host.list_offsets)
+    blocks = idx.d_blocks.cpu().numpy().view(capi.BLOCK_DTYPE)
+    assert np.array_equal(blocks, host.blocks)
+    for engine in ("strips", "tiles"):
+        d, f = idx.scan(engine=engine)
+        assert g.sha(_np(d).tobytes()) == golden.sha["docids_sha256"], engine
+        assert g.sha(_np(f).tobytes()) == golden.sha["freqs_sha256"], engine
+
+
+def test_index_device_plan_block128_and_corrupt_files(golden, golden128):
+    data = golden128.bytes(golden128.index_name("single_packed_dint"))
+    idx = driver.IndexFile("single_packed_dint", data, block_size=128, plan="device")
+    d, f = idx.scan(engine="strips")
+    assert g.sha(_np(d).tobytes()) == golden128.sha["docids_sha256"] and g.sha(_np(f).tobytes()) == golden128.sha["freqs_sha256"]
+    good = golden.bytes(golden.index_name("single_packed_dint"))
+    d_bin = torch.frombuffer(bytearray(good), dtype=torch.uint8).cuda()
+    for bad in (good[:len(good) - 8], good[:40]):
+        with pytest.raises(capi.DintError):
+            capi.DeviceIndexPlan(1, bad, d_bin.data_ptr())
+    # a corrupt list header inside m_lists is found by the device walk
+    host = capi.IndexPlan(1, good)
+    broken = bytearray(good)
+    pos = host.lists_off + int(host.endpoints[5])
+    broken[pos:pos + 5] = b"\x00\x00\x00\x00\x00"  # vbyte without a terminator
+    d_broken = torch.frombuffer(bytearray(broken), dtype=torch.uint8).cuda()
+    with pytest.raises(capi.DintError) as e:
+        capi.DeviceIndexPlan(1, bytes(broken), d_broken.data_ptr())
+    assert e.value.code == -2
