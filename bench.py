@@ -866,24 +866,23 @@ def run_gpu_index(args):
     st = torch.cuda.current_stream(dev)
     kind = KINDS[args.type]
     data = w["index"]
-    # host: header + Elias-Fano endpoints + per-list block tables of ONE replica (no codeword is touched: the
-    # file's own endpoints say where every block starts)
-    t0 = time.perf_counter()
-    plan = capi.IndexPlan(kind, data, block_size=w["block_size"])
-    host_plan_ms = (time.perf_counter() - t0) * 1e3
+    # ONE replica's file goes to the GPU as it is; the host reads its fixed-size header, the GPU expands the
+    # Elias-Fano endpoints, parses the list headers and writes the block table (dint_index_device_plan_create)
+    d_file = torch.frombuffer(bytearray(data), dtype=torch.uint8).to(dev)
+    plan = capi.DeviceIndexPlan(kind, data, d_file.data_ptr(), device=dev.index, block_size=w["block_size"], stream=st.cuda_stream)
+    table_ms = plan.build_ms
     docs_dict = capi.Dictionary(kind, data[plan.docs_dict_off:plan.freqs_dict_off], device=dev.index, mapped=True)
     freqs_dict = capi.Dictionary(kind, data[plan.freqs_dict_off:plan.end_off], device=dev.index, mapped=True)
-    lists = torch.frombuffer(bytearray(data[plan.lists_off:plan.lists_off + plan.lists_len]), dtype=torch.uint8).to(dev)
-    d_lists = lists.repeat(R)
+    d_lists = d_file[plan.lists_off:plan.lists_off + plan.lists_len].repeat(R)
     n_blocks, n_post = int(plan.n_blocks), int(plan.n_postings)
-    blk = torch.from_numpy(plan.blocks.view(np.int64).reshape(-1, 4).copy()).to(dev)
+    blk = driver.device_view(plan.blocks_ptr, n_blocks * 4, "<i8", dev).view(-1, 4)
     shift = torch.zeros(R, 1, 4, dtype=torch.int64, device=dev)
     rr = torch.arange(R, dtype=torch.int64, device=dev)
     shift[:, 0, 0] = rr * int(plan.lists_len)
     shift[:, 0, 1] = rr * n_post
-    d_blocks = (blk[None, :, :] + shift).reshape(-1, 4).contiguous()
-    del blk, shift
-    full = int((plan.blocks["size"] == w["block_size"]).sum())
+    d_blocks = (blk[None, :, :] + shift).reshape(-1, 4).contiguous()  # every replica is a file of its own
+    full = int(((blk[:, 2] & 0xFFFFFFFF) == w["block_size"]).sum().item())
+    del shift
     # device: codeword boundaries of every full block of every replica
     dp, fp = capi.DevicePlan.discover_index(docs_dict, freqs_dict, d_lists.data_ptr(), d_lists.numel(), d_blocks.data_ptr(),
                                             R * n_blocks, w["block_size"], stream=st.cuda_stream)
@@ -908,7 +907,7 @@ def run_gpu_index(args):
         first = t[:n_post].cpu().numpy().view(np.uint32)
         last = t[(R - 1) * n_post:].cpu().numpy().view(np.uint32)
         ok = ok and hashlib.sha256(first.tobytes()).hexdigest() == w["sha"][key] and np.array_equal(first, last)
-    lo = torch.from_numpy(plan.list_offsets.astype(np.int64)).to(dev)
+    lo = driver.device_view(plan.list_offsets_ptr, int(plan.n_lists) + 1, "<i8", dev)
     d_lo = torch.cat([(lo[:-1][None, :] + (rr * n_post)[:, None]).reshape(-1), torch.tensor([R * n_post], dtype=torch.int64, device=dev)])
     n_lists = int(plan.n_lists)
     local_sum = 0
@@ -970,9 +969,10 @@ def run_gpu_index(args):
                      "frac": algo / (step_ms * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_launch": algo, "avg_launch_ms": step_ms,
                      "traffic": None, "bytes_per_int": algo / (2 * R * n_post)},
         "clocks": clocks, "gpu_launches": int(launches), "checksum": ((int(red[1].item()) << 32) + int(red[2].item())) & MASK63,
-        "prepass": {"what": ("dint_index_discover: block starts from the file's own endpoints, codeword boundaries of the full "
-                             "blocks found on the device; host = header/Elias-Fano/block-table bookkeeping of one replica"),
-                    "device_ms": dp.discover_ms + fp.discover_ms, "host_bookkeeping_ms": host_plan_ms,
+        "prepass": {"what": ("dint_index_device_plan_create (Elias-Fano endpoints, list headers, block table of one replica's file, "
+                             "on the device; the host reads the fixed-size header) + dint_index_discover (codeword boundaries of "
+                             "the full blocks of every replica, on the device)"),
+                    "device_ms": dp.discover_ms + fp.discover_ms, "block_table_device_ms": table_ms,
                     "G_ints_per_s": 2 * R * n_post / max(dp.discover_ms + fp.discover_ms, 1e-9) / 1e6,
                     "strip_table_bytes_per_int": 160.0 * (dp.n_units + fp.n_units) / (2 * R * n_post), "host_walk": "none"},
     }
