@@ -869,8 +869,12 @@ def run_gpu_index(args):
     # ONE replica's file goes to the GPU as it is; the host reads its fixed-size header, the GPU expands the
     # Elias-Fano endpoints, parses the list headers and writes the block table (dint_index_device_plan_create)
     d_file = torch.frombuffer(bytearray(data), dtype=torch.uint8).to(dev)
-    plan = capi.DeviceIndexPlan(kind, data, d_file.data_ptr(), device=dev.index, block_size=w["block_size"], stream=st.cuda_stream)
-    table_ms = plan.build_ms
+    table_ms_all = []
+    for attempt in range(3):  # the first call also pays for loading the kernels; all attempts are listed
+        plan = None
+        plan = capi.DeviceIndexPlan(kind, data, d_file.data_ptr(), device=dev.index, block_size=w["block_size"], stream=st.cuda_stream)
+        table_ms_all.append(plan.build_ms)
+    table_ms = min(table_ms_all)
     docs_dict = capi.Dictionary(kind, data[plan.docs_dict_off:plan.freqs_dict_off], device=dev.index, mapped=True)
     freqs_dict = capi.Dictionary(kind, data[plan.freqs_dict_off:plan.end_off], device=dev.index, mapped=True)
     d_lists = d_file[plan.lists_off:plan.lists_off + plan.lists_len].repeat(R)
@@ -972,7 +976,7 @@ def run_gpu_index(args):
         "prepass": {"what": ("dint_index_device_plan_create (Elias-Fano endpoints, list headers, block table of one replica's file, "
                              "on the device; the host reads the fixed-size header) + dint_index_discover (codeword boundaries of "
                              "the full blocks of every replica, on the device)"),
-                    "device_ms": dp.discover_ms + fp.discover_ms, "block_table_device_ms": table_ms,
+                    "device_ms": dp.discover_ms + fp.discover_ms, "block_table_device_ms": table_ms, "block_table_device_ms_every_attempt": table_ms_all,
                     "G_ints_per_s": 2 * R * n_post / max(dp.discover_ms + fp.discover_ms, 1e-9) / 1e6,
                     "strip_table_bytes_per_int": 160.0 * (dp.n_units + fp.n_units) / (2 * R * n_post), "host_walk": "none"},
     }
