@@ -53,6 +53,21 @@ def test_no_silent_cpu_fallback(golden):
     from dint_b200 import driver
     with pytest.raises(capi.DintError):
         driver.VroomFile("single_packed_dint", b"", data)
+    # the round-2 entry points refuse as well: device-side discovery, cold host ctx, device index plan, AND queries
+    L = capi.lib()
+    h = C.c_void_p()
+    buf = np.zeros(64, dtype=np.uint8)
+    assert L.dint_vroom_discover(d.handle, buf.ctypes.data, 64, 256, None, 0, 0, None, C.byref(h)) == capi.E_NODEVICE
+    assert L.dint_vroom_ctx_create_discover(d.handle, buf.ctypes.data, 64, 256, None, 0, 0, None, C.byref(h)) == capi.E_NODEVICE
+    h2 = C.c_void_p()
+    assert L.dint_index_discover(d.handle, d.handle, buf.ctypes.data, 64, buf.ctypes.data, 1, 256, None, C.byref(h), C.byref(h2)) \
+        == capi.E_NODEVICE
+    idx = golden.bytes(golden.index_name("single_packed_dint"))
+    a = np.frombuffer(idx, dtype=np.uint8)
+    assert L.dint_index_device_plan_create(1, a.ctypes.data, len(a), a.ctypes.data, 0, 256, None, C.byref(h)) == capi.E_NODEVICE
+    rc = L.dint_and_queries(buf.ctypes.data, buf.ctypes.data, 1, buf.ctypes.data, buf.ctypes.data, 1, buf.ctypes.data, None)
+    assert rc in (capi.E_NODEVICE, -3)  # no device to ask about the pointer: a CUDA error, never a CPU answer
+    assert not buf.any()
 
 
 def test_product_does_not_reference_the_oracle():
