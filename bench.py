@@ -703,8 +703,74 @@ def run_e2e(torch, dist, capi, dev, w, args, streams, world):
     K = max(1, min(args.e2e_batch, R))
     while R % K:
         K -= 1
-    decs, ints = [], 0
-    h2d = d2h = 0
+    out = {}
+    # per-replica counts known from the resident streams (every replica is the sample)
+    ints = streams["docs"].sample_ints + streams["freqs"].sample_ints
+    h2d = streams["docs"].sample_bytes + streams["freqs"].sample_bytes
+    d2h = 8 * (streams["docs"].sample_lists + streams["freqs"].sample_lists)
+    total = world * R * ints  # every rank holds R whole replicas (aligned term ranges)
+    # ---- cold: nothing known about the file --------------------------------------------------------------------
+    if not args.no_e2e_cold:
+        decs_meta = [(capi.MODE_DOCIDS, "docs"), (capi.MODE_FREQS, "freqs")]
+        # the rank's whole range as ONE host file per stream (what a loader sees the first time it meets a collection)
+        Kc = max(1, min(args.cold_batch or R, R))
+        while R % Kc:
+            Kc -= 1
+        cold = []
+        for mode, part in decs_meta:
+            bin_ = w["parts"][part][0]
+            h_bin = torch.frombuffer(bytearray(bin_ * Kc), dtype=torch.uint8).pin_memory()
+            h_sums = torch.empty(Kc * streams[part].sample_lists, dtype=torch.int64).pin_memory()
+            cold.append((h_bin, h_sums, mode, part))
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        # one file after the other on one stream (loading the two files from two host threads was measured and is slower:
+        # the cudaMalloc / cudaFree calls of one discovery synchronise the device under the other's kernels)
+        walls, discs, parts = [], [], []
+        for attempt in range(max(1, args.cold_repeats)):  # every attempt is a first touch: nothing survives a call
+            t0 = time.perf_counter()
+            disc_ms = 0.0
+            bd = [0.0, 0.0, 0.0]  # create (malloc + H2D + discovery), decode + checksums + D2H, destroy
+            for r in range(R // Kc):
+                for h_bin, h_sums, mode, part in cold:
+                    ta = time.perf_counter()
+                    dec = capi.VroomHostDecoder.discover(streams[part].dict, h_bin.data_ptr(), h_bin.numel(),
+                                                         block_size=w["block_size"], stream=st.cuda_stream)
+                    tb = time.perf_counter()
+                    disc_ms += dec.device_plan.discover_ms
+                    dec.decode_resident(mode=mode, stream=st.cuda_stream)
+                    dec.results(h_sums_ptr=h_sums.data_ptr(), stream=st.cuda_stream)
+                    dec.sync(st.cuda_stream)
+                    tc = time.perf_counter()
+                    dec.close()
+                    td = time.perf_counter()
+                    bd = [bd[0] + (tb - ta) * 1e3, bd[1] + (tc - tb) * 1e3, bd[2] + (td - tc) * 1e3]
+            wt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(wt, op=dist.ReduceOp.MAX)
+            walls.append(float(wt.item()))
+            discs.append(disc_ms)
+            parts.append(bd)
+        wall = min(walls)
+        disc_ms = discs[walls.index(wall)]
+        breakdown = parts[walls.index(wall)]
+        for h_bin, h_sums, mode, part in cold:  # every replica's checksums are the sample's
+            v = h_sums.view(Kc, streams[part].sample_lists)
+            assert bool((v == v[0:1]).all()), "e2e_cold: checksums differ between replicas"
+        out["e2e_cold"] = {"value": total / wall / 1e9, "unit": "G ints/s", "h2d_bytes_per_step": world * R * h2d,
+                           "d2h_bytes_per_step": world * R * d2h, "steps": len(walls), "ms_per_step": wall * 1e3,
+                           "ms_every_attempt": [x * 1e3 for x in walls],
+                           "note": ("best of the attempts (each one a complete first touch); the discovery has host steps "
+                                    "between its passes and the shared box shows sporadic host stalls of 0.5-0.8 s"),
+                           "discovery_ms_rank0": disc_ms, "files_per_stream_and_rank": R // Kc,
+                           "create_decode_destroy_ms_rank0": breakdown,
+                           "timer": "host wall clock around synchronised calls (max over ranks)",
+                           "call": ("per file: dint_vroom_ctx_create_discover (cudaMalloc + H2D + sync search + count + emit) -> "
+                                    "dint_vroom_decode_resident -> dint_vroom_ctx_results (checksums, D2H) -> destroy; no overlap, "
+                                    "nothing reused between files")}
+        del cold
+    decs = []
     for part, mode in (("docs", capi.MODE_DOCIDS), ("freqs", capi.MODE_FREQS)):
         bin_, dict_bytes, _, _ = w["parts"][part]
         d = streams[part].dict
@@ -716,9 +782,6 @@ def run_e2e(torch, dist, capi, dev, w, args, streams, world):
             h_sums = torch.empty(int(dec.n_lists), dtype=torch.int64).pin_memory()
             per_lane.append([dec, h_sums, None])
         decs.append((per_lane, h_bin, mode, part))
-        ints += int(per_lane[0][0].n_ints) // K
-        h2d += len(bin_)
-        d2h += int(per_lane[0][0].n_lists) // K * 8
     steps = max(1, min(args.steps, args.e2e_steps))
 
     def one_step(with_out):
@@ -761,13 +824,12 @@ def run_e2e(torch, dist, capi, dev, w, args, streams, world):
     for per_lane, _, _, part in decs:
         assert bool((per_lane[0][1] == per_lane[1][1]).all()), "e2e: lanes disagree"
     ms = timed(lambda: one_step(False), steps)
-    total = world * R * ints  # every rank holds R whole replicas (aligned term ranges)
-    out = {"e2e": {"value": total * steps / (ms * 1e-3) / 1e9, "unit": "G ints/s", "h2d_bytes_per_step": world * R * h2d,
+    out["e2e"] = {"value": total * steps / (ms * 1e-3) / 1e9, "unit": "G ints/s", "h2d_bytes_per_step": world * R * h2d,
                    "d2h_bytes_per_step": world * R * d2h, "steps": steps, "ms_per_step": ms / steps,
                    "returns": "per-list 64-bit checksums (the decoded postings stay in HBM)",
                    "call": (f"dint_vroom_decode_host (pinned .bin in, per-list checksums out), {2 * (R // K)} calls per step and rank "
                             f"({K} sample files per call) alternating between 2 contexts/streams; restart points found on the "
-                            f"device when the context was created (no host plan)")}}
+                            f"device when the context was created (no host plan)")}
     # ---- all postings back to the host ------------------------------------------------------------------------
     if not args.no_e2e_out:
         for per_lane, _, _, _ in decs:
@@ -792,61 +854,6 @@ def run_e2e(torch, dist, capi, dev, w, args, streams, world):
         for per_lane, _, _, _ in decs:
             for rec in per_lane:
                 rec[2] = None
-    # ---- cold: nothing known about the file --------------------------------------------------------------------
-    if not args.no_e2e_cold:
-        for per_lane, _, _, _ in decs:
-            for rec in per_lane:
-                rec[0].close()
-        decs_meta = [(mode, part) for _, _, mode, part in decs]
-        del decs
-        # the rank's whole range as ONE host file per stream (what a loader sees the first time it meets a collection)
-        Kc = max(1, min(args.cold_batch or R, R))
-        while R % Kc:
-            Kc -= 1
-        cold = []
-        for mode, part in decs_meta:
-            bin_ = w["parts"][part][0]
-            h_bin = torch.frombuffer(bytearray(bin_ * Kc), dtype=torch.uint8).pin_memory()
-            h_sums = torch.empty(Kc * streams[part].sample_lists, dtype=torch.int64).pin_memory()
-            cold.append((h_bin, h_sums, mode, part))
-        torch.cuda.synchronize(dev)
-        if world > 1:
-            dist.barrier()
-        # one file after the other on one stream (loading the two files from two host threads was measured and is slower:
-        # the cudaMalloc / cudaFree calls of one discovery synchronise the device under the other's kernels)
-        walls, discs = [], []
-        for attempt in range(max(1, args.cold_repeats)):  # every attempt is a first touch: nothing survives a call
-            t0 = time.perf_counter()
-            disc_ms = 0.0
-            for r in range(R // Kc):
-                for h_bin, h_sums, mode, part in cold:
-                    dec = capi.VroomHostDecoder.discover(streams[part].dict, h_bin.data_ptr(), h_bin.numel(),
-                                                         block_size=w["block_size"], stream=st.cuda_stream)
-                    disc_ms += dec.device_plan.discover_ms
-                    dec.decode_resident(mode=mode, stream=st.cuda_stream)
-                    dec.results(h_sums_ptr=h_sums.data_ptr(), stream=st.cuda_stream)
-                    dec.sync(st.cuda_stream)
-                    dec.close()
-            wt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-            if world > 1:
-                dist.all_reduce(wt, op=dist.ReduceOp.MAX)
-            walls.append(float(wt.item()))
-            discs.append(disc_ms)
-        wall = min(walls)
-        disc_ms = discs[walls.index(wall)]
-        for h_bin, h_sums, mode, part in cold:  # every replica's checksums are the sample's
-            v = h_sums.view(Kc, streams[part].sample_lists)
-            assert bool((v == v[0:1]).all()), "e2e_cold: checksums differ between replicas"
-        out["e2e_cold"] = {"value": total / wall / 1e9, "unit": "G ints/s", "h2d_bytes_per_step": world * R * h2d,
-                           "d2h_bytes_per_step": world * R * d2h, "steps": len(walls), "ms_per_step": wall * 1e3,
-                           "ms_every_attempt": [x * 1e3 for x in walls],
-                           "note": ("best of the attempts (each one a complete first touch); the discovery has host steps "
-                                    "between its passes and the shared box shows sporadic host stalls of 0.5-0.8 s"),
-                           "discovery_ms_rank0": disc_ms, "files_per_stream_and_rank": R // Kc,
-                           "timer": "host wall clock around synchronised calls (max over ranks)",
-                           "call": ("per file: dint_vroom_ctx_create_discover (cudaMalloc + H2D + sync search + count + emit) -> "
-                                    "dint_vroom_decode_resident -> dint_vroom_ctx_results (checksums, D2H) -> destroy; no overlap, "
-                                    "nothing reused between files")}
     return out
 
 
