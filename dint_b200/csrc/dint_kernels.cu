@@ -389,12 +389,14 @@ constexpr int kTailChunk = 256;
 struct tail_warp_smem {
     unsigned int bins[257];
     uint8_t order[kTailChunk];
-    uint8_t sizes[kTailChunk];
+    uint16_t sizes[kTailChunk];
 };
 __global__ void __launch_bounds__(kTailThreads)
 index_tails_kernel(const uint8_t* __restrict__ lists, uint64_t lists_bytes, const dint_block* __restrict__ blocks,
                    uint64_t n_blocks, uint32_t block_size, uint32_t chunk, uint32_t* __restrict__ docids,
                    uint32_t* __restrict__ freqs) {
+    // block_size: blocks of fewer postings are interpolative coded (dict_freq_index: the partial blocks; a
+    // block_freq_index<interpolative_block> is decoded by passing 257: every block of up to 256 postings)
     __shared__ uint4 stacks[kTailThreads * 10];
     __shared__ tail_warp_smem wsm[kTailThreads / 32];
     uint4* stack = stacks + threadIdx.x;  // level-major: entry k at stack[k * kTailThreads]
@@ -413,9 +415,9 @@ index_tails_kernel(const uint8_t* __restrict__ lists, uint64_t lists_bytes, cons
         __syncwarp();
         for (uint32_t t = lane; t < cn; t += 32u) {
             uint32_t n = blocks[base + t].size;
-            if (n >= block_size || n > 255u) n = 0;  // full blocks are DINT coded (strips / tiles)
-            W.sizes[t] = uint8_t(n);
-            if (n) atomicAdd(&W.bins[255u - n], 1u);
+            if (n >= block_size || n > 256u) n = 0;  // full blocks are DINT coded (strips / tiles)
+            W.sizes[t] = uint16_t(n);
+            if (n) atomicAdd(&W.bins[256u - n], 1u);
         }
         __syncwarp();
         {
@@ -437,7 +439,7 @@ index_tails_kernel(const uint8_t* __restrict__ lists, uint64_t lists_bytes, cons
         const uint32_t n_tails = W.bins[256];
         for (uint32_t t = lane; t < cn; t += 32u) {
             const uint32_t n = W.sizes[t];
-            if (n) W.order[atomicAdd(&W.bins[255u - n], 1u)] = uint8_t(t);
+            if (n) W.order[atomicAdd(&W.bins[256u - n], 1u)] = uint8_t(t);
         }
         __syncwarp();
         // ---- decode ------------------------------------------------------------------------------------------------
@@ -1122,6 +1124,24 @@ int dint_decode_index_planned(const dint_dict* docs_dict, const dint_dict* freqs
     // partial blocks: interpolative
     device_guard g(docs_dict->device);
     return launch_index_tails(docs_dict->device, d_lists, lists_bytes, d_blocks, n_blocks, block_size, d_docids, d_freqs,
+                              static_cast<cudaStream_t>(stream));
+}
+
+int dint_decode_index_interpolative(const uint8_t* d_lists, size_t lists_bytes, const dint_block* d_blocks, size_t n_blocks,
+                                    uint32_t block_size, uint32_t* d_docids, uint32_t* d_freqs, void* stream) {
+    if (n_blocks == 0) return DINT_OK;
+    if (!d_lists || !d_blocks || (!d_docids && !d_freqs) || (reinterpret_cast<uintptr_t>(d_blocks) & 15)) return DINT_E_ARG;
+    if (!block_size) block_size = dint::kDefaultBlock;
+    if (!index_block_size_ok(block_size)) return DINT_E_ARG;
+    cudaPointerAttributes pa;
+    CUDA_TRY(cudaPointerGetAttributes(&pa, d_lists));
+    if (pa.type != cudaMemoryTypeDevice && pa.type != cudaMemoryTypeManaged) {
+        dint::set_error("dint_decode_index_interpolative: d_lists is not device memory (no CPU fallback)");
+        return DINT_E_NODEVICE;
+    }
+    device_guard g(pa.device);
+    // every block is interpolative: the kernel's "partial block" threshold is put above the largest block
+    return launch_index_tails(pa.device, d_lists, lists_bytes, d_blocks, n_blocks, block_size + 1u, d_docids, d_freqs,
                               static_cast<cudaStream_t>(stream));
 }
 

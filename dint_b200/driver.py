@@ -17,6 +17,7 @@ import torch
 from . import capi, shard
 
 TYPES = ("single_rect_dint", "single_packed_dint", "multi_packed_dint")
+INDEX_TYPES = TYPES + ("block_interpolative",)  # frozen index files: + block_freq_index<interpolative_block>
 
 
 def _require_cuda(device):
@@ -168,16 +169,20 @@ class IndexFile:
                 st = torch.cuda.current_stream(self.dev).cuda_stream
                 self.plan = capi.DeviceIndexPlan(kind, bin_bytes, self.d_bin.data_ptr(), device=device, block_size=block_size, stream=st)
             p = self.plan
-            self.docs_dict = capi.Dictionary(kind, bin_bytes[p.docs_dict_off:p.freqs_dict_off], device=device, mapped=True)
-            self.freqs_dict = capi.Dictionary(kind, bin_bytes[p.freqs_dict_off:p.end_off], device=device, mapped=True)
+            self.docs_dict = self.freqs_dict = None
+            if kind != capi.INDEX_BLOCK_INTERPOLATIVE:
+                self.docs_dict = capi.Dictionary(kind, bin_bytes[p.docs_dict_off:p.freqs_dict_off], device=device, mapped=True)
+                self.freqs_dict = capi.Dictionary(kind, bin_bytes[p.freqs_dict_off:p.end_off], device=device, mapped=True)
             self.n_postings, self.n_lists = int(p.n_postings), int(p.n_lists)
             self.d_blocks = device_view(p.blocks_ptr, int(p.n_blocks) * 32, "|u1", self.dev)
             self.d_list_offsets = device_view(p.list_offsets_ptr, self.n_lists + 1, "<i8", self.dev)
             return
         self.plan = capi.IndexPlan(kind, bin_bytes, block_size=block_size)
         p = self.plan
-        self.docs_dict = capi.Dictionary(kind, bin_bytes[p.docs_dict_off:p.freqs_dict_off], device=device, mapped=True)
-        self.freqs_dict = capi.Dictionary(kind, bin_bytes[p.freqs_dict_off:p.end_off], device=device, mapped=True)
+        self.docs_dict = self.freqs_dict = None
+        if kind != capi.INDEX_BLOCK_INTERPOLATIVE:
+            self.docs_dict = capi.Dictionary(kind, bin_bytes[p.docs_dict_off:p.freqs_dict_off], device=device, mapped=True)
+            self.freqs_dict = capi.Dictionary(kind, bin_bytes[p.freqs_dict_off:p.end_off], device=device, mapped=True)
         self.d_bin = _to_device_bytes(bin_bytes, self.dev)
         self.d_blocks = _structured_to_device(p.blocks, self.dev)
         self.d_list_offsets = torch.from_numpy(p.list_offsets.astype(np.int64)).to(self.dev)
@@ -206,6 +211,11 @@ class IndexFile:
             freqs = torch.empty(self.n_postings, dtype=torch.int32, device=self.dev)
         st = (stream or torch.cuda.current_stream(self.dev)).cuda_stream
         p = self.plan
+        if self.docs_dict is None:  # block_freq_index<interpolative_block>: every block is interpolative coded
+            capi.decode_index_interpolative(self.d_bin.data_ptr() + p.lists_off, p.lists_len, self.d_blocks.data_ptr(),
+                                            int(p.n_blocks), self.block_size, docids.data_ptr() if want_docs else None,
+                                            freqs.data_ptr() if want_freqs else None, stream=st)
+            return docids, freqs
         if engine == "strips":
             dp, fp = self.discover(stream)
             capi.decode_index_planned(self.docs_dict, self.freqs_dict, self.d_bin.data_ptr() + p.lists_off, p.lists_len, dp, fp,

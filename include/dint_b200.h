@@ -53,13 +53,18 @@
 extern "C" {
 #endif
 
-#define DINT_B200_ABI_VERSION 6 /* 5: device-side discovery (dint_vroom_discover, dint_index_discover, dint_device_plan_*); 6: dint_index_device_plan_create, dint_and_queries */
+#define DINT_B200_ABI_VERSION 6 /* 5: device-side discovery (dint_vroom_discover, dint_index_discover, dint_device_plan_*); 6: dint_index_device_plan_create, dint_and_queries, dint_decode_index_interpolative */
 
 /* dictionary kinds == the reference's three dictionary types */
 enum {
     DINT_DICT_RECT = 0,   /* single_rect_dint   : rectangular_dictionary   */
     DINT_DICT_PACKED = 1, /* single_packed_dint : single_dictionary<pack>  */
-    DINT_DICT_MULTI = 2   /* multi_packed_dint  : multi_dictionary<pack>   */
+    DINT_DICT_MULTI = 2,  /* multi_packed_dint  : multi_dictionary<pack>   */
+    /* index files only (dint_index_plan_create / dint_index_device_plan_create): a frozen
+     * block_freq_index<interpolative_block> ("block_interpolative", include/index_types.hpp:41) — the container
+     * dict_freq_index mirrors (include/ds2i/block_freq_index.hpp, block_posting_list.hpp), no dictionaries, every
+     * block binary-interpolative coded; decoded by dint_decode_index_interpolative */
+    DINT_INDEX_BLOCK_INTERPOLATIVE = 3
 };
 
 /* output modes of dint_decode_segments */
@@ -305,6 +310,13 @@ int dint_decode_index_planned(const dint_dict* docs_dict, const dint_dict* freqs
                               size_t lists_bytes, const dint_device_plan* docs_plan, const dint_device_plan* freqs_plan,
                               const dint_block* d_blocks, size_t n_blocks, uint32_t block_size, uint32_t* d_docids,
                               uint32_t* d_freqs, void* stream);
+
+/* block_freq_index<interpolative_block> (the first of the other block codecs behind the same ABI):
+ * every block of the table — full ones included — is interpolative_block::decode'd
+ * (include/ds2i/block_codecs.hpp:104-150; block_posting_list.hpp: decode_docs_block / decode_freqs_block) into
+ * docid() / freq() values. d_blocks from a plan made with kind DINT_INDEX_BLOCK_INTERPOLATIVE. */
+int dint_decode_index_interpolative(const uint8_t* d_lists, size_t lists_bytes, const dint_block* d_blocks, size_t n_blocks,
+                                    uint32_t block_size, uint32_t* d_docids, uint32_t* d_freqs, void* stream);
 
 /* sums[i] = sum_{j in list i} (value_j + 1) * (j + 1)  mod 2^64 */
 int dint_checksum_lists(const uint32_t* d_values, const uint64_t* d_list_offsets, size_t n_lists, uint64_t* d_sums,

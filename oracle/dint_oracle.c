@@ -319,6 +319,10 @@ int oracle_index_parse(int kind, const uint8_t* bin, size_t len, oracle_index_in
     off += info->lists_len;
     if (off > len) return -1;
     info->docs_dict_off = off;
+    if (kind == ORACLE_BLOCK_INTERPOLATIVE) { /* block_freq_index.hpp:138-146: no dictionaries behind m_lists */
+        info->freqs_dict_off = info->end_off = off;
+        return off == len ? 0 : -2;
+    }
     size_t used = 0;
     oracle_dict* d = oracle_dict_parse_mapped(kind, bin + off, len - off, &used);
     if (!d) return -1;
@@ -376,8 +380,9 @@ long oracle_index_decode(int kind, const uint8_t* bin, size_t len, uint32_t bloc
     if (list_n && info.n_lists > list_cap) return -1;
     uint64_t* ep = (uint64_t*)malloc((info.n_lists + 1) * 8);
     if (oracle_index_endpoints(bin, &info, ep) != 0) { free(ep); return -1; }
-    oracle_dict* dd = oracle_dict_parse_mapped(kind, bin + info.docs_dict_off, len - info.docs_dict_off, NULL);
-    oracle_dict* fd = oracle_dict_parse_mapped(kind, bin + info.freqs_dict_off, len - info.freqs_dict_off, NULL);
+    const int dictless = kind == ORACLE_BLOCK_INTERPOLATIVE; /* interpolative_block::decode for every block */
+    oracle_dict* dd = dictless ? NULL : oracle_dict_parse_mapped(kind, bin + info.docs_dict_off, len - info.docs_dict_off, NULL);
+    oracle_dict* fd = dictless ? NULL : oracle_dict_parse_mapped(kind, bin + info.freqs_dict_off, len - info.freqs_dict_off, NULL);
     uint32_t* dbuf = (uint32_t*)malloc((size_t)(block_size + 512) * 4);
     uint32_t* fbuf = (uint32_t*)malloc((size_t)(block_size + 512) * 4);
     size_t pos = 0;
@@ -400,9 +405,14 @@ long oracle_index_decode(int kind, const uint8_t* bin, size_t len, uint32_t bloc
             uint32_t bmax = rd32(maxs + 4 * b);
             memset(dbuf, 0, (size_t)(block_size + 512) * 4);
             memset(fbuf, 0, (size_t)(block_size + 512) * 4);
-            const uint8_t* fdata =
-                block_data + oracle_block_decode(dd, block_data, dbuf, bmax - cur_base - (size - 1), size, block_size);
-            oracle_block_decode(fd, fdata, fbuf, 0xFFFFFFFFu, size, block_size);
+            const uint8_t* fdata;
+            if (dictless) { /* block_posting_list.hpp (decode_docs_block / decode_freqs_block) over block_codecs.hpp:130-150 */
+                fdata = block_data + oracle_interpolative_decode(block_data, dbuf, bmax - cur_base - (size - 1), size);
+                oracle_interpolative_decode(fdata, fbuf, 0xFFFFFFFFu, size);
+            } else {
+                fdata = block_data + oracle_block_decode(dd, block_data, dbuf, bmax - cur_base - (size - 1), size, block_size);
+                oracle_block_decode(fd, fdata, fbuf, 0xFFFFFFFFu, size, block_size);
+            }
             uint32_t doc = dbuf[0] + cur_base;
             for (uint32_t i = 0; i < size; ++i) {
                 if (i) doc += dbuf[i] + 1;
@@ -413,6 +423,7 @@ long oracle_index_decode(int kind, const uint8_t* bin, size_t len, uint32_t bloc
         }
     }
     free(dbuf); free(fbuf); free(ep);
-    oracle_dict_free(dd); oracle_dict_free(fd);
+    if (dd) oracle_dict_free(dd);
+    if (fd) oracle_dict_free(fd);
     return rc ? rc : (long)pos;
 }

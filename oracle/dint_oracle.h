@@ -18,7 +18,10 @@
 extern "C" {
 #endif
 
-enum { ORACLE_RECT = 0, ORACLE_PACKED = 1, ORACLE_MULTI = 2 };
+enum { ORACLE_RECT = 0, ORACLE_PACKED = 1, ORACLE_MULTI = 2,
+       /* index files only: block_freq_index<interpolative_block> (include/ds2i/block_freq_index.hpp, block_posting_list.hpp:
+        * the container dict_freq_index mirrors) — no dictionaries, every block binary-interpolative coded */
+       ORACLE_BLOCK_INTERPOLATIVE = 3 };
 
 typedef struct oracle_dict oracle_dict;
 

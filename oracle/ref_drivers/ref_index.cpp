@@ -32,6 +32,7 @@
 #include "dictionary_builders.hpp"
 #include "block_statistics.hpp"
 #include "dict_freq_index.hpp"
+#include "block_freq_index.hpp"
 
 namespace ds2i {
 using adjusted_collector_type = adjusted<constants::max_entry_size>;
@@ -46,6 +47,9 @@ using multi_packed_builder =
 using single_rect_dint_index = dict_freq_index<single_rectangular_builder, opt_dint_single_dict_block>;
 using single_packed_dint_index = dict_freq_index<single_packed_builder, opt_dint_single_dict_block>;
 using multi_packed_dint_index = dict_freq_index<multi_packed_builder, opt_dint_multi_dict_block>;
+// include/index_types.hpp:26: block_interpolative — the first of the other block codecs of block_freq_index
+// (SURVEY §8f rank 4); same container, no dictionaries, every block binary-interpolative coded
+using block_interpolative_index = block_freq_index<interpolative_block>;
 }  // namespace ds2i
 
 #include "util.hpp"
@@ -173,6 +177,7 @@ int main(int argc, char** argv) {
     if (t == "single_rect_dint") return run<single_rect_dint_index>(argc, argv);
     if (t == "single_packed_dint") return run<single_packed_dint_index>(argc, argv);
     if (t == "multi_packed_dint") return run<multi_packed_dint_index>(argc, argv);
+    if (t == "block_interpolative") return run<block_interpolative_index>(argc, argv);
     std::cerr << "unknown type " << t << std::endl;
     return 2;
 }

@@ -79,3 +79,14 @@ def test_rect_and_packed_dictionaries_entrywise_identical(oracle, golden):
             assert np.array_equal(ra[:min(na, 16)], rb[:min(na, 16)])
         oracle.dict_free(a)
         oracle.dict_free(b)
+
+
+def test_block_interpolative_index_decodes_to_the_collection(golden, oracle):
+    """block_freq_index<interpolative_block> of the test collection, built and verified by the reference
+    (oracle/make_block_codec_fixture.py): the C restatement must reproduce the collection from it"""
+    import hashlib
+    data = golden.bytes("index.block_interpolative.bin")
+    d, f, ln = oracle.index_decode(3, data, golden.n_postings + 16)
+    assert len(d) == golden.n_postings and len(ln) == golden.n_lists
+    assert hashlib.sha256(d.tobytes()).hexdigest() == golden.sha["docids_sha256"]
+    assert hashlib.sha256(f.tobytes()).hexdigest() == golden.sha["freqs_sha256"]
