@@ -12,10 +12,13 @@
  *                            include/dint/rectangular_dictionary.hpp:79-92, 206-213
  *                            include/dint/single_dictionary.hpp:88-107, 230-238
  *                            include/dint/multi_dictionary.hpp:93-121, 293-304
- *   dint_vroom_plan_*      the `while (begin != end) header::read ...` walk of a vroom .bin
+ *   dint_vroom_discover /  the `while (begin != end) header::read ...` walk of a vroom .bin, done by the GPU on the
+ *   dint_vroom_plan_*        bytes in HBM (discover) or by one host thread (plan): where every list, block and
+ *                            strip of <= 8 codewords starts
  *                            vroom_env/decode.cpp:139-150, vroom_env/codecs.hpp:110-124
- *   dint_index_plan_*      succinct::mapper::map(dict_freq_index) + Elias-Fano endpoints +
- *                          document_enumerator's per-list block table
+ *   dint_index_device_plan_* succinct::mapper::map(dict_freq_index) + Elias-Fano endpoints +
+ *   / dint_index_plan_*      document_enumerator's per-list block table, on the device / on the host;
+ *   dint_index_discover      + the codeword boundaries inside the full blocks (device)
  *                            include/dint/dict_freq_index.hpp:174-181, 209-214
  *                            include/ds2i/compact_elias_fano.hpp:14-61
  *                            include/dint/dict_posting_list.hpp:90-107
@@ -33,10 +36,15 @@
  *   dint_decode_list_host  one Decoder::decode(dict, in, out, universe, n) call, host buffers
  *   dint_vroom_ctx_* /     the whole decode_dint() loop of vroom_env/decode.cpp:139-150 on HOST
  *   dint_vroom_decode_host   buffers: H2D of the .bin, batch decode, D2H of the result
+ *   dint_decode_index_planned   dint_decode_index through the strip tables of dint_index_discover (fast path)
+ *   dint_decode_index_interpolative  the same scan of a block_freq_index<interpolative_block>
+ *                            include/ds2i/block_freq_index.hpp, block_posting_list.hpp, block_codecs.hpp:104-150
+ *   dint_and_queries       ds2i::and_query<false> for a batch of queries over the decoded docIDs
+ *                            include/ds2i/queries.hpp:34-86, src/queries.cpp:15-61
  *   dint_checksum_lists    (new) per-list 64-bit checksums used for large-scale parity
  *
  * Ownership: the caller owns every device buffer; nothing is allocated on the decode
- * path. Outputs are PACKED (list after list, no slack) — unlike the reference, which
+ * path (the *_create / *_discover calls are load-time: they allocate and synchronise). Outputs are PACKED (list after list, no slack) — unlike the reference, which
  * needs a pre-zeroed buffer with 16..256 ints of slack (dint_codecs.hpp:11,
  * dict_posting_list.hpp:104-105). Handles are immutable after creation and may be used
  * from any stream of the device they were created on.
