@@ -9,8 +9,8 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdint_b200.so")
 DRIVER = os.path.join(HERE, "dint_b200_decode")
 SOURCES = [os.path.join(CSRC, "dint_kernels.cu"), os.path.join(CSRC, "dint_discover.cu"), os.path.join(CSRC, "dint_host.cpp")]
-HEADERS = [os.path.join(CSRC, "dint_internal.hpp"), os.path.join(CSRC, "dint_decoder.cuh"), os.path.join(CSRC, "dint_strips.cuh"), os.path.join(CSRC, "dint_discover.cuh"), os.path.join(CSRC, "dint_cuda_util.hpp"),
-           os.path.join(ROOT, "include", "dint_b200.h")]
+HEADERS = [os.path.join(CSRC, h) for h in ("dint_internal.hpp", "dint_cuda_util.hpp", "dint_decoder.cuh", "dint_strips.cuh", "dint_discover.cuh",
+                                            "dint_index_blocks.cuh", "dint_block_codecs.cuh")] + [os.path.join(ROOT, "include", "dint_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall"]
 

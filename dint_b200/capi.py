@@ -13,11 +13,13 @@ from . import _build
 
 DICT_RECT, DICT_PACKED, DICT_MULTI = 0, 1, 2
 INDEX_BLOCK_INTERPOLATIVE = 3  # index files only: block_freq_index<interpolative_block>, no dictionaries
+INDEX_BLOCK_VBYTE = 4  # block_freq_index<vbyte_block>
+INDEX_BLOCK_U32 = 5  # block_freq_index<u32_block>
 MODE_RAW, MODE_DOCIDS, MODE_FREQS = 0, 1, 2
 E_NODEVICE = -5
 
 KIND_OF_TYPE = {"single_rect_dint": DICT_RECT, "single_packed_dint": DICT_PACKED, "multi_packed_dint": DICT_MULTI,
-                "block_interpolative": INDEX_BLOCK_INTERPOLATIVE}
+                "block_interpolative": INDEX_BLOCK_INTERPOLATIVE, "block_vbyte": INDEX_BLOCK_VBYTE, "block_u32": INDEX_BLOCK_U32}
 
 SEGMENT_DTYPE = np.dtype([("in_off", "<u8"), ("out_off", "<u8"), ("n", "<u4"), ("doc_base", "<u4"),
                           ("in_len", "<u4"), ("doc_sum", "<u4")])
@@ -52,7 +54,7 @@ SYMBOLS = [
     "dint_index_device_plan_create", "dint_device_index_destroy", "dint_device_index_num_lists", "dint_device_index_num_docs",
     "dint_device_index_num_postings", "dint_device_index_num_blocks", "dint_device_index_build_ms", "dint_device_index_blocks",
     "dint_device_index_list_offsets", "dint_device_index_endpoints", "dint_device_index_layout",
-    "dint_decode_index_interpolative",
+    "dint_decode_index_interpolative", "dint_decode_index_blocks",
 ]
 
 
@@ -160,6 +162,7 @@ def lib():
             getattr(L, "dint_device_index_" + f).restype = vp
         L.dint_device_index_layout.argtypes = [vp] + [C.POINTER(u64)] * 5
         L.dint_decode_index_interpolative.argtypes = [vp, sz, vp, sz, u32, vp, vp, vp]
+        L.dint_decode_index_blocks.argtypes = [i32, vp, sz, vp, sz, u32, vp, vp, vp]
         _lib = L
     return _lib
 
@@ -477,6 +480,12 @@ def decode_index_planned(docs_dict, freqs_dict, d_lists_ptr, lists_bytes, docs_p
     check(lib().dint_decode_index_planned(docs_dict.handle, freqs_dict.handle, d_lists_ptr, lists_bytes, docs_plan.handle,
                                           freqs_plan.handle, d_blocks_ptr, n_blocks, block_size, d_docids_ptr, d_freqs_ptr,
                                           stream))
+
+
+def decode_index_blocks(kind, d_lists_ptr, lists_bytes, d_blocks_ptr, n_blocks, block_size, d_docids_ptr, d_freqs_ptr, stream=0):
+    """block_freq_index<interpolative_block | vbyte_block | u32_block>: every block of the table by that codec"""
+    check(lib().dint_decode_index_blocks(kind, d_lists_ptr, lists_bytes, d_blocks_ptr, n_blocks, block_size, d_docids_ptr,
+                                         d_freqs_ptr, stream))
 
 
 def decode_index_interpolative(d_lists_ptr, lists_bytes, d_blocks_ptr, n_blocks, block_size, d_docids_ptr, d_freqs_ptr, stream=0):

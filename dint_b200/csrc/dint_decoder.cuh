@@ -136,6 +136,22 @@ __device__ __forceinline__ void sts_4(uint32_t a, uint4 v) {
         : "memory");
 }
 
+// little-endian loads at any alignment from the file image (aligned 8-byte loads + funnel)
+__device__ __forceinline__ uint64_t ldu64(const uint8_t* p) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p), a8 = a & ~uintptr_t(7);
+    const uint32_t sh = uint32_t(a & 7) * 8u;
+    const uint64_t lo = __ldg(reinterpret_cast<const uint64_t*>(a8));
+    if (!sh) return lo;
+    const uint64_t hi = __ldg(reinterpret_cast<const uint64_t*>(a8 + 8));
+    return (lo >> sh) | (hi << (64u - sh));
+}
+__device__ __forceinline__ uint32_t ldu32(const uint8_t* p) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p), a4 = a & ~uintptr_t(3);
+    const uint32_t sh = uint32_t(a & 3) * 8u;
+    const uint32_t lo = __ldg(reinterpret_cast<const uint32_t*>(a4));
+    if (!sh) return lo;
+    return __funnelshift_r(lo, __ldg(reinterpret_cast<const uint32_t*>(a4 + 4)), sh);
+}
 // inclusive warp scan: shfl.up hands back a predicate that is false for the lanes without a source
 #define DINT_SCAN_STEP(v, o)                                                        \
     asm volatile(                                                                   \

@@ -243,7 +243,7 @@ int index_header_parse(int kind, const uint8_t* bin, size_t len, dint_index_head
         set_error(std::string("index .bin: ") + m);
         return DINT_E_FORMAT;
     };
-    if (kind < 0 || kind > DINT_INDEX_BLOCK_INTERPOLATIVE) return DINT_E_ARG;
+    if (kind < 0 || kind > DINT_INDEX_BLOCK_U32) return DINT_E_ARG;
     size_t off = 8;
     if (len < off + 5 + 32) return bad("truncated header");
     const uint32_t log_s0 = bin[off], log_s1 = bin[off + 1];
@@ -263,7 +263,7 @@ int index_header_parse(int kind, const uint8_t* bin, size_t len, dint_index_head
     if (h->lists_len > len - off) return bad("m_lists out of range");
     off += size_t(h->lists_len);
     h->docs_dict_off = off;
-    if (kind != DINT_INDEX_BLOCK_INTERPOLATIVE) {  // (a block_freq_index has nothing behind m_lists)
+    if (kind < DINT_INDEX_BLOCK_INTERPOLATIVE) {  // (a block_freq_index has nothing behind m_lists)
         size_t used = 0;
         if (!mapped_extent(kind, bin + off, len - off, &used)) return bad("docs dictionary");
         off += used;
@@ -669,7 +669,7 @@ int dint_index_plan_create(int kind, const void* bin_, size_t len, uint32_t bloc
     }
 }
 static int index_plan_create_impl(int kind, const void* bin_, size_t len, uint32_t block_size, dint_index_plan** out) {
-    if (!bin_ || !out || kind < 0 || kind > DINT_INDEX_BLOCK_INTERPOLATIVE) return DINT_E_ARG;
+    if (!bin_ || !out || kind < 0 || kind > DINT_INDEX_BLOCK_U32) return DINT_E_ARG;
     g_error.clear();
     if (!block_size) block_size = kDefaultBlock;
     const uint8_t* bin = static_cast<const uint8_t*>(bin_);
@@ -700,7 +700,7 @@ static int index_plan_create_impl(int kind, const void* bin_, size_t len, uint32
     if (plan->lists_len > len - off) return bad("m_lists out of range");
     off += size_t(plan->lists_len);
     plan->docs_dict_off = off;
-    if (kind == DINT_INDEX_BLOCK_INTERPOLATIVE) {  // block_freq_index: nothing behind m_lists
+    if (kind >= DINT_INDEX_BLOCK_INTERPOLATIVE) {  // block_freq_index: nothing behind m_lists
         plan->freqs_dict_off = plan->end_off = off;
     } else {
         dint_dict tmp;

@@ -18,22 +18,6 @@
 
 namespace dintk {
 
-// little-endian loads at any alignment from the file image (aligned 8-byte loads + funnel)
-__device__ __forceinline__ uint64_t ldu64(const uint8_t* p) {
-    const uintptr_t a = reinterpret_cast<uintptr_t>(p), a8 = a & ~uintptr_t(7);
-    const uint32_t sh = uint32_t(a & 7) * 8u;
-    const uint64_t lo = __ldg(reinterpret_cast<const uint64_t*>(a8));
-    if (!sh) return lo;
-    const uint64_t hi = __ldg(reinterpret_cast<const uint64_t*>(a8 + 8));
-    return (lo >> sh) | (hi << (64u - sh));
-}
-__device__ __forceinline__ uint32_t ldu32(const uint8_t* p) {
-    const uintptr_t a = reinterpret_cast<uintptr_t>(p), a4 = a & ~uintptr_t(3);
-    const uint32_t sh = uint32_t(a & 3) * 8u;
-    const uint32_t lo = __ldg(reinterpret_cast<const uint32_t*>(a4));
-    if (!sh) return lo;
-    return __funnelshift_r(lo, __ldg(reinterpret_cast<const uint32_t*>(a4 + 4)), sh);
-}
 // `len` (<= 64) bits at bit position `pos` of a little-endian u64 word array that starts at `words` (any alignment)
 __device__ __forceinline__ uint64_t ef_bits(const uint8_t* words, uint64_t pos, uint32_t len) {
     if (!len) return 0;

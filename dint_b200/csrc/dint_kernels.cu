@@ -20,6 +20,7 @@
 #include "dint_cuda_util.hpp"
 #include "dint_decoder.cuh"
 #include "dint_strips.cuh"
+#include "dint_block_codecs.cuh"
 #include "dint_internal.hpp"
 
 namespace dintk {
@@ -1127,8 +1128,12 @@ int dint_decode_index_planned(const dint_dict* docs_dict, const dint_dict* freqs
                               static_cast<cudaStream_t>(stream));
 }
 
-int dint_decode_index_interpolative(const uint8_t* d_lists, size_t lists_bytes, const dint_block* d_blocks, size_t n_blocks,
-                                    uint32_t block_size, uint32_t* d_docids, uint32_t* d_freqs, void* stream) {
+int dint_decode_index_blocks(int kind, const uint8_t* d_lists, size_t lists_bytes, const dint_block* d_blocks, size_t n_blocks,
+                             uint32_t block_size, uint32_t* d_docids, uint32_t* d_freqs, void* stream) {
+    if (kind != DINT_INDEX_BLOCK_INTERPOLATIVE && kind != DINT_INDEX_BLOCK_VBYTE && kind != DINT_INDEX_BLOCK_U32) {
+        dint::set_error("dint_decode_index_blocks: kind is not one of the dictionary-less block codecs");
+        return DINT_E_ARG;
+    }
     if (n_blocks == 0) return DINT_OK;
     if (!d_lists || !d_blocks || (!d_docids && !d_freqs) || (reinterpret_cast<uintptr_t>(d_blocks) & 15)) return DINT_E_ARG;
     if (!block_size) block_size = dint::kDefaultBlock;
@@ -1136,13 +1141,32 @@ int dint_decode_index_interpolative(const uint8_t* d_lists, size_t lists_bytes, 
     cudaPointerAttributes pa;
     CUDA_TRY(cudaPointerGetAttributes(&pa, d_lists));
     if (pa.type != cudaMemoryTypeDevice && pa.type != cudaMemoryTypeManaged) {
-        dint::set_error("dint_decode_index_interpolative: d_lists is not device memory (no CPU fallback)");
+        dint::set_error("dint_decode_index_blocks: d_lists is not device memory (no CPU fallback)");
         return DINT_E_NODEVICE;
     }
     device_guard g(pa.device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
     // every block is interpolative: the kernel's "partial block" threshold is put above the largest block
-    return launch_index_tails(pa.device, d_lists, lists_bytes, d_blocks, n_blocks, block_size + 1u, d_docids, d_freqs,
-                              static_cast<cudaStream_t>(stream));
+    if (kind == DINT_INDEX_BLOCK_INTERPOLATIVE)
+        return launch_index_tails(pa.device, d_lists, lists_bytes, d_blocks, n_blocks, block_size + 1u, d_docids, d_freqs, st);
+    // vbyte_block / u32_block: one warp per block, 8 warps per CTA
+    device_info di;
+    int rc = get_device_info(pa.device, &di);
+    if (rc) return rc;
+    const int grid = int(std::max<uint64_t>(1, std::min<uint64_t>((n_blocks + 7) / 8, uint64_t(di.sms) * 8)));
+    if (kind == DINT_INDEX_BLOCK_VBYTE)
+        index_plain_blocks_kernel<PLAIN_VBYTE><<<grid, 256, 0, st>>>(d_lists, lists_bytes, d_blocks, n_blocks, d_docids, d_freqs);
+    else
+        index_plain_blocks_kernel<PLAIN_U32><<<grid, 256, 0, st>>>(d_lists, lists_bytes, d_blocks, n_blocks, d_docids, d_freqs);
+    ++g_launches;
+    CUDA_TRY(cudaGetLastError());
+    return DINT_OK;
+}
+
+int dint_decode_index_interpolative(const uint8_t* d_lists, size_t lists_bytes, const dint_block* d_blocks, size_t n_blocks,
+                                    uint32_t block_size, uint32_t* d_docids, uint32_t* d_freqs, void* stream) {
+    return dint_decode_index_blocks(DINT_INDEX_BLOCK_INTERPOLATIVE, d_lists, lists_bytes, d_blocks, n_blocks, block_size, d_docids,
+                                    d_freqs, stream);
 }
 
 int dint_checksum_lists(const uint32_t* d_values, const uint64_t* d_list_offsets, size_t n_lists, uint64_t* d_sums,

@@ -17,7 +17,7 @@ import torch
 from . import capi, shard
 
 TYPES = ("single_rect_dint", "single_packed_dint", "multi_packed_dint")
-INDEX_TYPES = TYPES + ("block_interpolative",)  # frozen index files: + block_freq_index<interpolative_block>
+INDEX_TYPES = TYPES + ("block_interpolative", "block_vbyte", "block_u32")  # frozen index files: + block_freq_index<...>
 
 
 def _require_cuda(device):
@@ -170,7 +170,7 @@ class IndexFile:
                 self.plan = capi.DeviceIndexPlan(kind, bin_bytes, self.d_bin.data_ptr(), device=device, block_size=block_size, stream=st)
             p = self.plan
             self.docs_dict = self.freqs_dict = None
-            if kind != capi.INDEX_BLOCK_INTERPOLATIVE:
+            if kind < capi.INDEX_BLOCK_INTERPOLATIVE:
                 self.docs_dict = capi.Dictionary(kind, bin_bytes[p.docs_dict_off:p.freqs_dict_off], device=device, mapped=True)
                 self.freqs_dict = capi.Dictionary(kind, bin_bytes[p.freqs_dict_off:p.end_off], device=device, mapped=True)
             self.n_postings, self.n_lists = int(p.n_postings), int(p.n_lists)
@@ -180,7 +180,7 @@ class IndexFile:
         self.plan = capi.IndexPlan(kind, bin_bytes, block_size=block_size)
         p = self.plan
         self.docs_dict = self.freqs_dict = None
-        if kind != capi.INDEX_BLOCK_INTERPOLATIVE:
+        if kind < capi.INDEX_BLOCK_INTERPOLATIVE:
             self.docs_dict = capi.Dictionary(kind, bin_bytes[p.docs_dict_off:p.freqs_dict_off], device=device, mapped=True)
             self.freqs_dict = capi.Dictionary(kind, bin_bytes[p.freqs_dict_off:p.end_off], device=device, mapped=True)
         self.d_bin = _to_device_bytes(bin_bytes, self.dev)
@@ -211,10 +211,10 @@ class IndexFile:
             freqs = torch.empty(self.n_postings, dtype=torch.int32, device=self.dev)
         st = (stream or torch.cuda.current_stream(self.dev)).cuda_stream
         p = self.plan
-        if self.docs_dict is None:  # block_freq_index<interpolative_block>: every block is interpolative coded
-            capi.decode_index_interpolative(self.d_bin.data_ptr() + p.lists_off, p.lists_len, self.d_blocks.data_ptr(),
-                                            int(p.n_blocks), self.block_size, docids.data_ptr() if want_docs else None,
-                                            freqs.data_ptr() if want_freqs else None, stream=st)
+        if self.docs_dict is None:  # block_freq_index<interpolative | vbyte | u32 block>: every block by that codec
+            capi.decode_index_blocks(capi.KIND_OF_TYPE[self.type], self.d_bin.data_ptr() + p.lists_off, p.lists_len,
+                                     self.d_blocks.data_ptr(), int(p.n_blocks), self.block_size,
+                                     docids.data_ptr() if want_docs else None, freqs.data_ptr() if want_freqs else None, stream=st)
             return docids, freqs
         if engine == "strips":
             dp, fp = self.discover(stream)

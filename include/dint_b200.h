@@ -61,7 +61,7 @@
 extern "C" {
 #endif
 
-#define DINT_B200_ABI_VERSION 6 /* 5: device-side discovery (dint_vroom_discover, dint_index_discover, dint_device_plan_*); 6: dint_index_device_plan_create, dint_and_queries, dint_decode_index_interpolative */
+#define DINT_B200_ABI_VERSION 7 /* 5: device-side discovery (dint_vroom_discover, dint_index_discover, dint_device_plan_*); 6: dint_index_device_plan_create, dint_and_queries, dint_decode_index_interpolative; 7: dint_decode_index_blocks (+ vbyte_block, u32_block) */
 
 /* dictionary kinds == the reference's three dictionary types */
 enum {
@@ -71,8 +71,13 @@ enum {
     /* index files only (dint_index_plan_create / dint_index_device_plan_create): a frozen
      * block_freq_index<interpolative_block> ("block_interpolative", include/index_types.hpp:41) — the container
      * dict_freq_index mirrors (include/ds2i/block_freq_index.hpp, block_posting_list.hpp), no dictionaries, every
-     * block binary-interpolative coded; decoded by dint_decode_index_interpolative */
-    DINT_INDEX_BLOCK_INTERPOLATIVE = 3
+     * block binary-interpolative coded; decoded by dint_decode_index_blocks */
+    DINT_INDEX_BLOCK_INTERPOLATIVE = 3,
+    /* block_freq_index<vbyte_block> ("block_vbyte", index_types.hpp:45): TightVariableByte blocks
+     * (block_codecs.hpp:24-101, 357-375) */
+    DINT_INDEX_BLOCK_VBYTE = 4,
+    /* block_freq_index<u32_block> ("block_u32", index_types.hpp:44): raw u32 blocks (block_codecs.hpp:377-402) */
+    DINT_INDEX_BLOCK_U32 = 5
 };
 
 /* output modes of dint_decode_segments */
@@ -319,10 +324,15 @@ int dint_decode_index_planned(const dint_dict* docs_dict, const dint_dict* freqs
                               const dint_block* d_blocks, size_t n_blocks, uint32_t block_size, uint32_t* d_docids,
                               uint32_t* d_freqs, void* stream);
 
-/* block_freq_index<interpolative_block> (the first of the other block codecs behind the same ABI):
- * every block of the table — full ones included — is interpolative_block::decode'd
- * (include/ds2i/block_codecs.hpp:104-150; block_posting_list.hpp: decode_docs_block / decode_freqs_block) into
- * docid() / freq() values. d_blocks from a plan made with kind DINT_INDEX_BLOCK_INTERPOLATIVE. */
+/* The dictionary-less block codecs behind the same block table ("the other block codecs behind the same
+ * batch-decode ABI"): kind DINT_INDEX_BLOCK_INTERPOLATIVE / _VBYTE / _U32 selects interpolative_block, vbyte_block or
+ * u32_block ::decode (include/ds2i/block_codecs.hpp:104-150, 357-375, 377-402) for EVERY block of the table — full
+ * ones included — and the enumerator's docid() / freq() values are written (block_posting_list.hpp:113-124,
+ * 164-169, 195-208). d_blocks from a plan made with the same kind. Any other kind: DINT_E_ARG. */
+int dint_decode_index_blocks(int kind, const uint8_t* d_lists, size_t lists_bytes, const dint_block* d_blocks, size_t n_blocks,
+                             uint32_t block_size, uint32_t* d_docids, uint32_t* d_freqs, void* stream);
+
+/* dint_decode_index_blocks(DINT_INDEX_BLOCK_INTERPOLATIVE, ...) */
 int dint_decode_index_interpolative(const uint8_t* d_lists, size_t lists_bytes, const dint_block* d_blocks, size_t n_blocks,
                                     uint32_t block_size, uint32_t* d_docids, uint32_t* d_freqs, void* stream);
 

@@ -319,7 +319,7 @@ int oracle_index_parse(int kind, const uint8_t* bin, size_t len, oracle_index_in
     off += info->lists_len;
     if (off > len) return -1;
     info->docs_dict_off = off;
-    if (kind == ORACLE_BLOCK_INTERPOLATIVE) { /* block_freq_index.hpp:138-146: no dictionaries behind m_lists */
+    if (kind >= ORACLE_BLOCK_INTERPOLATIVE) { /* block_freq_index.hpp:138-146: no dictionaries behind m_lists */
         info->freqs_dict_off = info->end_off = off;
         return off == len ? 0 : -2;
     }
@@ -380,7 +380,7 @@ long oracle_index_decode(int kind, const uint8_t* bin, size_t len, uint32_t bloc
     if (list_n && info.n_lists > list_cap) return -1;
     uint64_t* ep = (uint64_t*)malloc((info.n_lists + 1) * 8);
     if (oracle_index_endpoints(bin, &info, ep) != 0) { free(ep); return -1; }
-    const int dictless = kind == ORACLE_BLOCK_INTERPOLATIVE; /* interpolative_block::decode for every block */
+    const int dictless = kind >= ORACLE_BLOCK_INTERPOLATIVE; /* BlockCodec::decode for every block */
     oracle_dict* dd = dictless ? NULL : oracle_dict_parse_mapped(kind, bin + info.docs_dict_off, len - info.docs_dict_off, NULL);
     oracle_dict* fd = dictless ? NULL : oracle_dict_parse_mapped(kind, bin + info.freqs_dict_off, len - info.freqs_dict_off, NULL);
     uint32_t* dbuf = (uint32_t*)malloc((size_t)(block_size + 512) * 4);
@@ -406,9 +406,16 @@ long oracle_index_decode(int kind, const uint8_t* bin, size_t len, uint32_t bloc
             memset(dbuf, 0, (size_t)(block_size + 512) * 4);
             memset(fbuf, 0, (size_t)(block_size + 512) * 4);
             const uint8_t* fdata;
-            if (dictless) { /* block_posting_list.hpp (decode_docs_block / decode_freqs_block) over block_codecs.hpp:130-150 */
+            if (kind == ORACLE_BLOCK_INTERPOLATIVE) { /* block_posting_list.hpp (decode_docs_block / decode_freqs_block) over block_codecs.hpp:130-150 */
                 fdata = block_data + oracle_interpolative_decode(block_data, dbuf, bmax - cur_base - (size - 1), size);
                 oracle_interpolative_decode(fdata, fbuf, 0xFFFFFFFFu, size);
+            } else if (kind == ORACLE_BLOCK_VBYTE) { /* vbyte_block::decode block_codecs.hpp:370-374 = TightVariableByte::decode :87-101 */
+                fdata = block_data + oracle_vbyte_decode(block_data, dbuf, size);
+                oracle_vbyte_decode(fdata, fbuf, size);
+            } else if (kind == ORACLE_BLOCK_U32) { /* u32_block::decode block_codecs.hpp:390-401: the raw little-endian values */
+                for (uint32_t i = 0; i < size; ++i) dbuf[i] = rd32(block_data + 4 * (size_t)i);
+                fdata = block_data + 4 * (size_t)size;
+                for (uint32_t i = 0; i < size; ++i) fbuf[i] = rd32(fdata + 4 * (size_t)i);
             } else {
                 fdata = block_data + oracle_block_decode(dd, block_data, dbuf, bmax - cur_base - (size - 1), size, block_size);
                 oracle_block_decode(fd, fdata, fbuf, 0xFFFFFFFFu, size, block_size);

@@ -21,7 +21,9 @@ extern "C" {
 enum { ORACLE_RECT = 0, ORACLE_PACKED = 1, ORACLE_MULTI = 2,
        /* index files only: block_freq_index<interpolative_block> (include/ds2i/block_freq_index.hpp, block_posting_list.hpp:
         * the container dict_freq_index mirrors) — no dictionaries, every block binary-interpolative coded */
-       ORACLE_BLOCK_INTERPOLATIVE = 3 };
+       ORACLE_BLOCK_INTERPOLATIVE = 3,
+       ORACLE_BLOCK_VBYTE = 4, /* block_freq_index<vbyte_block>: TightVariableByte blocks (block_codecs.hpp:357-375) */
+       ORACLE_BLOCK_U32 = 5 /* block_freq_index<u32_block>: raw u32 blocks (block_codecs.hpp:377-402) */ };
 
 typedef struct oracle_dict oracle_dict;
 

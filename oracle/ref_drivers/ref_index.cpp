@@ -50,6 +50,8 @@ using multi_packed_dint_index = dict_freq_index<multi_packed_builder, opt_dint_m
 // include/index_types.hpp:26: block_interpolative — the first of the other block codecs of block_freq_index
 // (SURVEY §8f rank 4); same container, no dictionaries, every block binary-interpolative coded
 using block_interpolative_index = block_freq_index<interpolative_block>;
+using block_vbyte_index = block_freq_index<vbyte_block>;  // index_types.hpp:45
+using block_u32_index = block_freq_index<u32_block>;      // index_types.hpp:44
 }  // namespace ds2i
 
 #include "util.hpp"
@@ -178,6 +180,8 @@ int main(int argc, char** argv) {
     if (t == "single_packed_dint") return run<single_packed_dint_index>(argc, argv);
     if (t == "multi_packed_dint") return run<multi_packed_dint_index>(argc, argv);
     if (t == "block_interpolative") return run<block_interpolative_index>(argc, argv);
+    if (t == "block_vbyte") return run<block_vbyte_index>(argc, argv);
+    if (t == "block_u32") return run<block_u32_index>(argc, argv);
     std::cerr << "unknown type " << t << std::endl;
     return 2;
 }

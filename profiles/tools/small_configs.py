@@ -47,13 +47,16 @@ for type_ in g.TYPES:
                                         "block_size": idx.block_size, "lists_bytes": int(idx.plan.lists_len),
                                         "G_ints_per_s_strips": 2 * idx.n_postings / us_s / 1e3,
                                         "discover_ms": dp.discover_ms + fp.discover_ms}
-# the first of the other block codecs: block_freq_index<interpolative_block> (every block interpolative)
-bi = driver.IndexFile("block_interpolative", G.bytes("index.block_interpolative.bin"), plan="device")
-d = torch.empty(bi.n_postings, dtype=torch.int32, device=dev); f = torch.empty_like(d)
-us_bi = timed(lambda: bi.scan(d, f), 200)
-res["block_interpolative_index_scan"] = {"us_per_pass": us_bi, "postings": bi.n_postings, "G_ints_per_s": 2 * bi.n_postings / us_bi / 1e3,
-                                         "block_table_device_ms": bi.plan.build_ms,
-                                         "reference_cpu": "ref_index scan block_interpolative: 113 ms per scan (58.7 M ints/s), 1 thread, build container"}
+# the other block codecs behind the same block table: block_freq_index<interpolative_block | vbyte_block | u32_block>
+REF_CPU = {"block_interpolative": "113 ms per scan (58.7 M ints/s)", "block_vbyte": "36 ms per scan (183 M ints/s)",
+           "block_u32": "20 ms per scan (327 M ints/s)"}
+for t in ("block_interpolative", "block_vbyte", "block_u32"):
+    bi = driver.IndexFile(t, G.bytes(f"index.{t}.bin"), plan="device")
+    d = torch.empty(bi.n_postings, dtype=torch.int32, device=dev); f = torch.empty_like(d)
+    us_bi = timed(lambda: bi.scan(d, f), 200)
+    res[f"{t}_index_scan"] = {"us_per_pass": us_bi, "postings": bi.n_postings, "G_ints_per_s": 2 * bi.n_postings / us_bi / 1e3,
+                              "lists_bytes": int(bi.plan.lists_len), "block_table_device_ms": bi.plan.build_ms,
+                              "reference_cpu": f"ref_index scan {t}: {REF_CPU[t]}, 1 thread, build container"}
 # config 3
 type_ = "single_packed_dint"
 vf = driver.VroomFile(type_, G.bytes(G.vroom_name(type_, "docs")), G.bytes(G.dict_name(type_, "docs")))

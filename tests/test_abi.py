@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), f"{n} declared in include/dint_b200.h but not exported"
     assert sorted(capi.SYMBOLS) == names
-    assert L.dint_abi_version() == 6
+    assert L.dint_abi_version() == 7
 
 
 def test_struct_layouts_match_header():
@@ -67,6 +67,10 @@ def test_no_silent_cpu_fallback(golden):
     assert L.dint_index_device_plan_create(1, a.ctypes.data, len(a), a.ctypes.data, 0, 256, None, C.byref(h)) == capi.E_NODEVICE
     rc = L.dint_and_queries(buf.ctypes.data, buf.ctypes.data, 1, buf.ctypes.data, buf.ctypes.data, 1, buf.ctypes.data, None)
     assert rc in (capi.E_NODEVICE, -3)  # no device to ask about the pointer: a CUDA error, never a CPU answer
+    for kind in (3, 4, 5):  # the dictionary-less block codecs: host memory is refused
+        rc = L.dint_decode_index_blocks(kind, buf.ctypes.data, 64, buf.ctypes.data, 1, 256, buf.ctypes.data, buf.ctypes.data, None)
+        assert rc in (capi.E_NODEVICE, -3)
+    assert L.dint_decode_index_blocks(1, buf.ctypes.data, 64, buf.ctypes.data, 1, 256, buf.ctypes.data, buf.ctypes.data, None) == -1
     assert not buf.any()
 
 

@@ -283,17 +283,18 @@ def test_index_device_plan_block128_and_corrupt_files(golden, golden128):
 
 
 @pytest.mark.parametrize("plan", ("host", "device"))
-def test_block_interpolative_index_scan(golden, oracle, plan):
-    """SURVEY §8f rank 4, first codec: a frozen block_freq_index<interpolative_block> (reference-built) decoded through
-    the same block-table ABI: every block goes through the interpolative kernel; == collection == oracle"""
-    data = golden.bytes("index.block_interpolative.bin")
-    idx = driver.IndexFile("block_interpolative", data, plan=plan)
+@pytest.mark.parametrize("type_", ("block_interpolative", "block_vbyte", "block_u32"))
+def test_block_codec_index_scan(golden, oracle, type_, plan):
+    """frozen block_freq_index<interpolative_block | vbyte_block | u32_block> files (reference-built)
+    decoded through the same block-table ABI (dint_decode_index_blocks): == collection == oracle"""
+    data = golden.bytes(f"index.{type_}.bin")
+    idx = driver.IndexFile(type_, data, plan=plan)
     assert idx.docs_dict is None and idx.n_postings == golden.n_postings
     d, f = idx.scan()
     d, f = _np(d), _np(f)
     assert g.sha(d.tobytes()) == golden.sha["docids_sha256"]
     assert g.sha(f.tobytes()) == golden.sha["freqs_sha256"]
-    wd, wf, _ = oracle.index_decode(3, data, golden.n_postings + 16)
+    wd, wf, _ = oracle.index_decode(capi.KIND_OF_TYPE[type_], data, golden.n_postings + 16)
     assert np.array_equal(d, wd) and np.array_equal(f, wf)
     d2, _ = idx.scan(want_freqs=False)
     _, f2 = idx.scan(want_docs=False)

@@ -279,16 +279,21 @@ def test_strip_units_tile_the_file(oracle, golden, type_, part):
     assert (cs["runs"] > 0) == bool((U["flags"] & 1).any()) and (flagged == 0 or cs["runs"] > 0)
 
 
-def test_block_interpolative_index_plan(golden, oracle):
+BLOCK_CODECS = ("block_interpolative", "block_vbyte", "block_u32")  # index_types.hpp:41, 45, 44
+
+
+@pytest.mark.parametrize("type_", BLOCK_CODECS)
+def test_block_codec_index_plan(golden, oracle, type_):
     """the host pre-pass of a dictionary-less block_freq_index: same container as dict_freq_index
     (block_posting_list.hpp mirrors dict_posting_list.hpp), nothing behind m_lists"""
-    data = golden.bytes("index.block_interpolative.bin")
-    plan = capi.IndexPlan(capi.INDEX_BLOCK_INTERPOLATIVE, data)
+    kind = capi.KIND_OF_TYPE[type_]
+    data = golden.bytes(f"index.{type_}.bin")
+    plan = capi.IndexPlan(kind, data)
     assert plan.n_lists == golden.n_lists and plan.n_postings == golden.n_postings
     assert plan.docs_dict_off == plan.freqs_dict_off == plan.end_off == len(data)
-    info = oracle.index_parse(3, data)
+    info = oracle.index_parse(kind, data)
     assert (plan.lists_off, plan.lists_len) == (info.lists_off, info.lists_len)
-    _, _, ln = oracle.index_decode(3, data, golden.n_postings + 16)
+    _, _, ln = oracle.index_decode(kind, data, golden.n_postings + 16)
     assert np.array_equal(np.diff(plan.list_offsets.astype(np.int64)), ln.astype(np.int64))
     with pytest.raises(capi.DintError):  # a DINT index is not a block_freq_index: bytes behind m_lists
-        capi.IndexPlan(capi.INDEX_BLOCK_INTERPOLATIVE, golden.bytes(golden.index_name("single_packed_dint")))
+        capi.IndexPlan(kind, golden.bytes(golden.index_name("single_packed_dint")))

@@ -81,12 +81,13 @@ def test_rect_and_packed_dictionaries_entrywise_identical(oracle, golden):
         oracle.dict_free(b)
 
 
-def test_block_interpolative_index_decodes_to_the_collection(golden, oracle):
-    """block_freq_index<interpolative_block> of the test collection, built and verified by the reference
-    (oracle/make_block_codec_fixture.py): the C restatement must reproduce the collection from it"""
+@pytest.mark.parametrize("kind,type_", ((3, "block_interpolative"), (4, "block_vbyte"), (5, "block_u32")))
+def test_block_codec_index_decodes_to_the_collection(golden, oracle, kind, type_):
+    """block_freq_index<interpolative_block | vbyte_block | u32_block> of the test collection, built and verified by
+    the reference (oracle/make_block_codec_fixture.py): the C restatement must reproduce the collection from each"""
     import hashlib
-    data = golden.bytes("index.block_interpolative.bin")
-    d, f, ln = oracle.index_decode(3, data, golden.n_postings + 16)
+    data = golden.bytes(f"index.{type_}.bin")
+    d, f, ln = oracle.index_decode(kind, data, golden.n_postings + 16)
     assert len(d) == golden.n_postings and len(ln) == golden.n_lists
     assert hashlib.sha256(d.tobytes()).hexdigest() == golden.sha["docids_sha256"]
     assert hashlib.sha256(f.tobytes()).hexdigest() == golden.sha["freqs_sha256"]
