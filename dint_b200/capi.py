@@ -47,7 +47,7 @@ SYMBOLS = [
     "dint_vroom_decode_resident", "dint_vroom_ctx_sync",
     "dint_vroom_discover", "dint_index_discover", "dint_device_plan_destroy", "dint_device_plan_num_lists",
     "dint_device_plan_num_ints", "dint_device_plan_num_units", "dint_device_plan_num_chains",
-    "dint_device_plan_num_sync_found", "dint_device_plan_retries", "dint_device_plan_discover_ms", "dint_device_plan_phase_ms",
+    "dint_device_plan_num_sync_found", "dint_device_plan_num_skimmed", "dint_device_plan_retries", "dint_device_plan_discover_ms", "dint_device_plan_phase_ms",
     "dint_device_plan_units", "dint_device_plan_list_offsets", "dint_device_plan_list_byte_offsets",
     "dint_decode_index_planned", "dint_vroom_ctx_create_discover", "dint_vroom_ctx_num_lists",
     "dint_vroom_ctx_num_ints", "dint_vroom_ctx_device_plan", "dint_vroom_ctx_results", "dint_and_queries",
@@ -127,7 +127,7 @@ def lib():
         L.dint_index_discover.argtypes = [vp, vp, vp, sz, vp, sz, u32, vp, C.POINTER(vp), C.POINTER(vp)]
         L.dint_device_plan_destroy.argtypes = [vp]
         L.dint_device_plan_destroy.restype = None
-        for f in ("num_lists", "num_ints", "num_units", "num_chains", "num_sync_found"):
+        for f in ("num_lists", "num_ints", "num_units", "num_chains", "num_sync_found", "num_skimmed"):
             getattr(L, "dint_device_plan_" + f).argtypes = [vp]
             getattr(L, "dint_device_plan_" + f).restype = u64
         L.dint_device_plan_retries.argtypes = [vp]
@@ -294,6 +294,7 @@ class DevicePlan:
         self.n_units = L.dint_device_plan_num_units(handle)
         self.n_chains = L.dint_device_plan_num_chains(handle)
         self.n_sync_found = L.dint_device_plan_num_sync_found(handle)
+        self.n_skimmed = L.dint_device_plan_num_skimmed(handle)
         self.retries = L.dint_device_plan_retries(handle)
         self.discover_ms = L.dint_device_plan_discover_ms(handle)
         self.phase_ms = [L.dint_device_plan_phase_ms(handle, i) for i in range(3)]

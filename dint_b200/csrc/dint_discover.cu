@@ -43,11 +43,11 @@ size_t walk_smem(const dint_dict* d, int warps) {
 }
 
 template <typename K>
-int walk_grid(K kernel, const dint_dict* d, int warps, uint64_t want_warps, int* grid, size_t* smem) {
+int walk_grid(K kernel, const dint_dict* d, int warps, uint64_t want_warps, int* grid, size_t* smem, size_t extra_smem = 0) {
     device_info di;
     int rc = get_device_info(d->device, &di);
     if (rc) return rc;
-    *smem = walk_smem(d, warps);
+    *smem = walk_smem(d, warps) + extra_smem;
     if (*smem > size_t(di.max_smem_optin)) {
         dint::set_error("discovery: length tables do not fit in shared memory");
         return DINT_E_ARG;
@@ -97,6 +97,7 @@ uint64_t dint_device_plan_num_ints(const dint_device_plan* p) { return p ? p->n_
 uint64_t dint_device_plan_num_units(const dint_device_plan* p) { return p ? p->n_units : 0; }
 uint64_t dint_device_plan_num_chains(const dint_device_plan* p) { return p ? p->n_chains : 0; }
 uint64_t dint_device_plan_num_sync_found(const dint_device_plan* p) { return p ? p->n_sync_found : 0; }
+uint64_t dint_device_plan_num_skimmed(const dint_device_plan* p) { return p ? p->n_skimmed : 0; }
 uint32_t dint_device_plan_retries(const dint_device_plan* p) { return p ? p->retries : 0; }
 double dint_device_plan_discover_ms(const dint_device_plan* p) { return p ? double(p->discover_ms) : 0.0; }
 double dint_device_plan_phase_ms(const dint_device_plan* p, int phase) {
@@ -141,6 +142,10 @@ int dint_vroom_discover(const dint_dict* d, const uint8_t* d_in, size_t in_bytes
     CUDA_TRY(cudaEventRecord(ev0, st));
     const dint::strip_limits& lim = dint::get_strip_limits();
     const bool multi = d->kind == DINT_DICT_MULTI;
+    auto env_bytes = [](const char* name, uint64_t dflt) -> uint64_t {  // tuning knobs (diagnostics)
+        const char* v = std::getenv(name);
+        return v && *v ? std::strtoull(v, nullptr, 10) : dflt;
+    };
 
     // ---- chain starts: byte 0, the caller's list starts, and what the speculative search finds ---------------
     std::vector<uint64_t> sync;
@@ -168,7 +173,7 @@ int dint_vroom_discover(const dint_dict* d, const uint8_t* d_in, size_t in_bytes
                 F.stride = stride;
                 F.n_targets = n_targets;
                 F.window = uint32_t(std::min<uint64_t>(stride, 2048) & ~uint64_t(31));
-                F.depth = 3;
+                F.depth = uint32_t(env_bytes("DINT_B200_SYNC_DEPTH", 3));
                 F.max_n = 256;  // evidence = three consecutive short lists (cheap to check; a Zipfian collection is full of them)
                 F.found = found.as<uint64_t>();
                 const size_t smem = walk_smem(d, 0);
@@ -210,24 +215,50 @@ int dint_vroom_discover(const dint_dict* d, const uint8_t* d_in, size_t in_bytes
     P.units_cap = 0;
     P.list_offsets = P.list_byte_offsets = nullptr;
     P.bases = nullptr;
-    dev_buf d_status;
+    P.chain_state = nullptr;
+    P.queue = nullptr;
+    P.cut_off = nullptr;
+    P.cuts = nullptr;
+    P.cut_counts = nullptr;
+    P.cut_bytes = 0;
+    dev_buf d_status;  // u32 status | u32 - | u64 chain queue of the thread walker / the skim pass
     CUDA_TRY(cudaMalloc(&d_status.p, 16));
     P.status = d_status.as<uint32_t>();
+    P.queue = reinterpret_cast<unsigned long long*>(d_status.as<uint32_t>() + 2);
+    // chains sorted longest first in O(n): buckets of 512 bytes
+    auto longest_first = [](std::vector<uint32_t>& ids, size_t lo, size_t hi, const std::vector<uint64_t>& se) {
+        constexpr uint64_t kBins = 512;
+        auto bin = [&](uint32_t slot) { return kBins - 1 - std::min<uint64_t>((se[slot + 1] - se[slot]) >> 9, kBins - 1); };
+        std::vector<uint32_t> first(kBins + 1, 0), tmp(ids.begin() + lo, ids.begin() + hi);
+        for (uint32_t v : tmp) ++first[bin(v) + 1];
+        for (uint64_t b = 0; b < kBins; ++b) first[b + 1] += first[b];
+        for (uint32_t v : tmp) ids[lo + first[bin(v)]++] = v;
+    };
 
     // One chain = one candidate list start + where the walk from it has to stop. Chains up to kLongChain bytes are
     // walked by one thread each, longer ones (stretches without a sync point: very long lists) and the few chains of a
     // repair round by one warp each. A chain keeps its walker: the two passes must pack its units identically.
     // (measured: a thread walks ~2-3 KB/ms, a warp ~7 KB/ms, and the longest chain of either kind bounds the pass)
-    const uint64_t kLongChain = std::max<uint64_t>(32 * 1024, std::min<uint64_t>(2 * used_stride, 96 * 1024));
+    // Long chains are first skimmed by a warp each (vroom_skim_kernel) and cut into pieces of about kCutBytes that
+    // start at list headers or at block boundaries inside a list; threads walk the pieces. A long chain the skim
+    // cannot cut (a long list of a single-stream codec, a malformed stretch) keeps its warp.
+    // (measured: a thread walks ~2-3 KB/ms, a warp ~7 KB/ms, and the longest chain of either kind bounds the pass)
+    // (gov2 sample x 256, 6.4 GB: long 48 KB / cut 16 KB: 130 ms; 63 / 21 KB: 158 ms; 96 / 32 KB: 182 ms; no skim: 234 ms)
+    const uint64_t kLongChain = env_bytes("DINT_B200_LONG_CHAIN", std::max<uint64_t>(24 * 1024, std::min<uint64_t>(used_stride + used_stride / 8, 96 * 1024)));
+    const uint64_t kCutBytes = env_bytes("DINT_B200_CUT_BYTES", std::max<uint64_t>(8 * 1024, std::min<uint64_t>(3 * used_stride / 8, 32 * 1024)));
     struct chain {
         uint64_t start, end;             // walk from start to the first list start >= end
         uint64_t lists, ints, units, reached;
         uint32_t status;
         bool by_warp, counted;
+        // a piece of a skimmed chain: integers of the current list still to come at start (0: a list header),
+        // the list's sum(v + 1) so far, whether the piece ends inside a list and the integers to come there
+        uint32_t rem0 = 0, acc0 = 0, end_rem = 0;
+        bool end_mid = false;
     };
     // ---- one pass over chains[ids]: device arrays are indexed by the position k in ids (slot 2k / 8k) ----------------
     struct pass_bufs {
-        dev_buf d_se, d_cnt, d_order, d_bases;
+        dev_buf d_se, d_cnt, d_order, d_bases, d_state;
         uint64_t n = 0, n_short = 0, n_long = 0;
     };
     auto prepare = [&](const std::vector<chain>& chains, const std::vector<uint32_t>& ids, pass_bufs& pb) -> int {
@@ -236,19 +267,28 @@ int dint_vroom_discover(const dint_dict* d, const uint8_t* d_in, size_t in_bytes
         if (!n) return DINT_OK;
         std::vector<uint64_t> se(2 * n + 2);
         std::vector<uint32_t> order(n);
+        std::vector<uint32_t> state(4 * n);
         // walk_params wants chain c = [chain_start[c], chain_start[c + 1]): give every chain its own pair
         for (uint64_t k = 0; k < n; ++k) {
-            se[2 * k] = chains[ids[k]].start;
-            se[2 * k + 1] = chains[ids[k]].end;
+            const chain& c = chains[ids[k]];
+            se[2 * k] = c.start;
+            se[2 * k + 1] = c.end;
+            state[4 * k] = c.rem0;
+            state[4 * k + 1] = c.acc0;
+            state[4 * k + 2] = c.end_mid ? 1u : 0u;
+            state[4 * k + 3] = c.end_rem;
         }
         for (uint64_t k = 0; k < n; ++k)
             if (!chains[ids[k]].by_warp) order[pb.n_short++] = uint32_t(2 * k);
         for (uint64_t k = 0; k < n; ++k)
             if (chains[ids[k]].by_warp) order[pb.n_short + pb.n_long++] = uint32_t(2 * k);
+        longest_first(order, 0, pb.n_short, se);
         CUDA_TRY(cudaMalloc(&pb.d_se.p, se.size() * 8));
         CUDA_TRY(cudaMalloc(&pb.d_cnt.p, 8 * n * 8));
         CUDA_TRY(cudaMalloc(&pb.d_bases.p, 8 * n * 8));
         CUDA_TRY(cudaMalloc(&pb.d_order.p, n * 4));
+        CUDA_TRY(cudaMalloc(&pb.d_state.p, n * 16));
+        CUDA_TRY(cudaMemcpyAsync(pb.d_state.p, state.data(), n * 16, cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemcpyAsync(pb.d_se.p, se.data(), se.size() * 8, cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemcpyAsync(pb.d_order.p, order.data(), n * 4, cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaStreamSynchronize(st));  // se / order go out of scope
@@ -260,12 +300,13 @@ int dint_vroom_discover(const dint_dict* d, const uint8_t* d_in, size_t in_bytes
         P.n_chains = 2 * pb.n;
         P.counts = pb.d_cnt.as<uint64_t>();
         P.bases = pb.d_bases.as<uint64_t>();
+        P.chain_state = pb.d_state.as<uint4>();
         CUDA_TRY(cudaMemsetAsync(d_status.p, 0, 16, st));
         if (pb.n_short) {
             P.chain_ids = pb.d_order.as<uint32_t>();
             P.n_ids = pb.n_short;
             const size_t smem = walk_smem(d, 0) + (emit ? walk_hotsum_bytes(d->view()) : 0);
-            const int grid = int((pb.n_short + 255) / 256);
+            const int grid = int(std::min<uint64_t>((pb.n_short + 255) / 256, uint64_t(di.sms) * 3));  // 3 CTAs per SM (launch bounds)
             if (emit) {
                 CUDA_TRY(cudaFuncSetAttribute(vroom_thread_walk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
                 vroom_thread_walk_kernel<true><<<grid, 256, smem, st>>>(P);
@@ -384,6 +425,90 @@ int dint_vroom_discover(const dint_dict* d, const uint8_t* d_in, size_t in_bytes
             const uint64_t e = i + 1 < sync.size() ? sync[i + 1] : uint64_t(in_bytes);
             chains.push_back(chain{sync[i], e, 0, 0, 0, 0, 0, e - sync[i] > kLongChain, false});
         }
+        // ---- skim pass: long chains -> pieces -------------------------------------------------------------------------
+        std::vector<uint32_t> long_ids;
+        for (size_t i = 0; i < chains.size(); ++i)
+            if (chains[i].by_warp) long_ids.push_back(uint32_t(i));
+        if (!long_ids.empty() && kCutBytes) {
+            const uint64_t nl = long_ids.size();
+            std::vector<uint64_t> se(2 * nl + 2), cut_off(nl + 1, 0);
+            std::vector<uint32_t> order(nl);
+            for (uint64_t j = 0; j < nl; ++j) {
+                const chain& c = chains[long_ids[j]];
+                se[2 * j] = c.start;
+                se[2 * j + 1] = c.end;
+                order[j] = uint32_t(2 * j);
+                cut_off[j + 1] = cut_off[j] + (c.end - c.start) / kCutBytes + 1;
+            }
+            longest_first(order, 0, nl, se);
+            dev_buf d_se, d_order, d_off, d_cuts, d_cnt;
+            CUDA_TRY(cudaMalloc(&d_se.p, se.size() * 8));
+            CUDA_TRY(cudaMalloc(&d_order.p, nl * 4));
+            CUDA_TRY(cudaMalloc(&d_off.p, (nl + 1) * 8));
+            CUDA_TRY(cudaMalloc(&d_cuts.p, cut_off[nl] * 16));
+            CUDA_TRY(cudaMalloc(&d_cnt.p, nl * 4));
+            CUDA_TRY(cudaMemcpyAsync(d_se.p, se.data(), se.size() * 8, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaMemcpyAsync(d_order.p, order.data(), nl * 4, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaMemcpyAsync(d_off.p, cut_off.data(), (nl + 1) * 8, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaMemsetAsync(d_cnt.p, 0, nl * 4, st));
+            CUDA_TRY(cudaMemsetAsync(d_status.p, 0, 16, st));
+            P.chain_start = d_se.as<uint64_t>();
+            P.n_chains = 2 * nl;
+            P.chain_ids = d_order.as<uint32_t>();
+            P.n_ids = nl;
+            P.cut_off = d_off.as<uint64_t>();
+            P.cuts = d_cuts.as<uint64_t>();
+            P.cut_counts = d_cnt.as<uint32_t>();
+            P.cut_bytes = kCutBytes;
+            int grid = 0;
+            size_t smem = 0;
+            rc = walk_grid(vroom_skim_kernel, d, kWalkWarps, nl, &grid, &smem, walk_hotsum_bytes(d->view()));
+            if (rc) return rc;
+            vroom_skim_kernel<<<grid, kWalkWarps * 32, smem, st>>>(P);
+            ++g_launches;
+            CUDA_TRY(cudaGetLastError());
+            std::vector<uint32_t> n_cuts(nl);
+            std::vector<uint64_t> cuts(2 * cut_off[nl]);
+            CUDA_TRY(cudaMemcpyAsync(n_cuts.data(), d_cnt.p, nl * 4, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaMemcpyAsync(cuts.data(), d_cuts.p, cuts.size() * 8, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            P.cut_off = nullptr;
+            P.cuts = nullptr;
+            P.cut_counts = nullptr;
+            std::vector<chain> pieces;
+            pieces.reserve(chains.size() + cut_off[nl]);
+            size_t j = 0;
+            for (size_t i = 0; i < chains.size(); ++i) {
+                if (j >= nl || long_ids[j] != i) {
+                    pieces.push_back(chains[i]);
+                    continue;
+                }
+                const chain whole = chains[i];
+                const uint64_t* cj = cuts.data() + 2 * cut_off[j];
+                const uint32_t m = std::min<uint64_t>(n_cuts[j], cut_off[j + 1] - cut_off[j]);
+                ++j;
+                chain cur = whole;  // [start, first cut), then [cut, next cut) ..., the last piece keeps the chain's end
+                for (uint32_t k = 0; k < m; ++k) {
+                    const uint64_t at = cj[2 * k];
+                    const uint32_t rem = uint32_t(cj[2 * k + 1]), acc = uint32_t(cj[2 * k + 1] >> 32);
+                    if (at <= cur.start || at >= whole.end) break;  // (cuts are strictly increasing inside the chain)
+                    cur.end = at;
+                    cur.end_mid = rem != 0;
+                    cur.end_rem = rem;
+                    cur.by_warp = false;
+                    pieces.push_back(cur);
+                    cur = whole;
+                    cur.start = at;
+                    cur.rem0 = rem;
+                    cur.acc0 = acc;
+                }
+                cur.by_warp = cur.rem0 == 0 && cur.end - cur.start > kLongChain;  // (a warp starts at list headers only)
+                pieces.push_back(cur);
+            }
+            chains.swap(pieces);
+            plan->n_skimmed = nl;
+            tr("skimmed");
+        }
         std::vector<uint32_t> todo(chains.size());
         for (size_t i = 0; i < chains.size(); ++i) todo[i] = uint32_t(i);
         std::vector<uint32_t> linked;  // the chains of the file, in order
@@ -395,6 +520,7 @@ int dint_vroom_discover(const dint_dict* d, const uint8_t* d_in, size_t in_bytes
             pass_bufs pb;
             rc = prepare(chains, todo, pb);
             if (rc) return rc;
+            tr("chains uploaded");
             rc = launch(pb, false);
             if (rc) return rc;
             const uint64_t n = pb.n, tiles = (n + 255) / 256;
@@ -418,6 +544,7 @@ int dint_vroom_discover(const dint_dict* d, const uint8_t* d_in, size_t in_bytes
             uint64_t totals[4] = {0, 0, 0, 0};
             CUDA_TRY(cudaMemcpyAsync(totals, S.totals, 32, cudaMemcpyDeviceToHost, st));
             CUDA_TRY(cudaStreamSynchronize(st));
+            tr("counted");
             if (totals[3] == 0) {
                 CUDA_TRY(cudaEventRecord(evc, st));
                 rc = allocate_outputs(totals[0], totals[1], totals[2], n);
@@ -433,6 +560,7 @@ int dint_vroom_discover(const dint_dict* d, const uint8_t* d_in, size_t in_bytes
                 }
                 rc = finish(totals[0], totals[1]);
                 if (rc) return rc;
+                tr("emitted");
                 *out = plan.release();
                 return DINT_OK;
             }
@@ -452,20 +580,34 @@ int dint_vroom_discover(const dint_dict* d, const uint8_t* d_in, size_t in_bytes
             // index of the chain that starts at a given byte: candidates are sorted by start, repairs are appended
             std::vector<std::pair<uint64_t, uint32_t>> by_start(chains.size());
             for (size_t i = 0; i < chains.size(); ++i) by_start[i] = {chains[i].start, uint32_t(i)};
-            std::sort(by_start.begin(), by_start.end());
-            auto find = [&](uint64_t off) -> int64_t {
-                auto it = std::lower_bound(by_start.begin(), by_start.end(), std::make_pair(off, uint32_t(0)));
-                return it != by_start.end() && it->first == off ? int64_t(it->second) : -1;
+            {  // the candidates are in file order, only the repairs appended behind them are not
+                const auto mid = std::is_sorted_until(by_start.begin(), by_start.end());
+                std::sort(mid, by_start.end());
+                std::inplace_merge(by_start.begin(), mid, by_start.end());
+            }
+            // the chain that continues at byte `off` behind chain `prev` (-1: none): a chain that starts at a list header
+            // if prev stopped at a list boundary; the next piece of the same skimmed chain if prev stopped inside a list
+            auto find = [&](uint64_t off, int64_t prev) -> int64_t {
+                const bool mid = prev >= 0 && chains[size_t(prev)].end_mid;
+                for (auto it = std::lower_bound(by_start.begin(), by_start.end(), std::make_pair(off, uint32_t(0)));
+                     it != by_start.end() && it->first == off; ++it) {
+                    const chain& c = chains[it->second];
+                    if (!mid && c.rem0 == 0) return int64_t(it->second);
+                    if (mid && c.rem0 != 0 && uint32_t(prev) + 1 == it->second) return int64_t(it->second);
+                }
+                return -1;
             };
-            auto next_start = [&](uint64_t off) -> uint64_t {  // first candidate start > off
+            auto next_start = [&](uint64_t off) -> uint64_t {  // first candidate list start > off
                 auto it = std::upper_bound(by_start.begin(), by_start.end(), std::make_pair(off, ~uint32_t(0)));
+                while (it != by_start.end() && chains[it->second].rem0 != 0) ++it;
                 return it != by_start.end() ? it->first : uint64_t(in_bytes);
             };
             // every overshoot points at a list start nobody covers yet (if the chain itself is a true one): repair all
             // of them in one round, not only the first one met from byte 0
             for (size_t i = 0; i < chains.size(); ++i) {
                 const chain& c = chains[i];
-                if (c.counted && c.status == WALK_OVERSHOOT && c.reached < in_bytes && find(c.reached) < 0) {
+                // (a piece that was to stop inside a list and did not is not a true one: nothing to repair behind it)
+                if (c.counted && c.status == WALK_OVERSHOOT && !c.end_mid && c.reached < in_bytes && find(c.reached, -1) < 0) {
                     const uint64_t e = next_start(c.reached);
                     chains.push_back(chain{c.reached, e, 0, 0, 0, 0, 0, true, false});
                     by_start.insert(std::upper_bound(by_start.begin(), by_start.end(), std::make_pair(c.reached, uint32_t(0))),
@@ -484,9 +626,14 @@ int dint_vroom_discover(const dint_dict* d, const uint8_t* d_in, size_t in_bytes
             // link from byte 0
             linked.clear();
             uint64_t off = 0;
+            int64_t prev = -1;
             bool complete = true;
             while (off < in_bytes) {
-                const int64_t i = find(off);
+                const int64_t i = find(off, prev);
+                if (i < 0 && prev >= 0 && chains[size_t(prev)].end_mid) {
+                    dint::set_error("vroom .bin: malformed list (device walk), chain at byte " + std::to_string(off));
+                    return DINT_E_FORMAT;
+                }
                 if (i < 0) {  // cannot happen after the repairs above; be safe
                     chains.push_back(chain{off, next_start(off), 0, 0, 0, 0, 0, true, false});
                     todo.push_back(uint32_t(chains.size() - 1));
@@ -500,6 +647,7 @@ int dint_vroom_discover(const dint_dict* d, const uint8_t* d_in, size_t in_bytes
                 }
                 linked.push_back(uint32_t(i));
                 off = c.reached;
+                prev = i;
             }
             if (complete) break;
             if (round >= 64) {

@@ -230,17 +230,20 @@ struct unit_packer {
 // multi block is in front of it). sel: 0..5 u16 codewords of class sel, 6..11 u8 codewords of class sel - 6.
 // out0: output index of its first integer. acc: sum(v + 1) in front of it, updated. Strips go to pk. Returns false
 // for a stream that does not tile n integers. a_end: ring address one past its last byte.
-template <bool EMIT>
+// SKIM: only where the stream ends and what it sums to (no strips): the pass that cuts long chains into pieces.
+template <bool EMIT, bool SKIM = false>
 __device__ __forceinline__ bool walk_stream(warp_state& ws, const walk_tables& wt, uint64_t in_base, uint32_t a0, uint32_t n,
                                             uint32_t sel, bool ls, bool brk, uint64_t out0, uint32_t& acc, unit_packer& pk,
                                             uint32_t rec_s, uint32_t strip_cw, uint32_t strip_shift, unsigned lane, uint32_t& a_end) {
     a_end = a0;
     if (n == 0) return true;
     const bool narrow = sel >= dint::kSelectors;
-    const walk_class wc = load_walk_class(wt, min(narrow ? sel - dint::kSelectors : sel, 7u));
+    const uint32_t cls = min(narrow ? sel - dint::kSelectors : sel, 7u);
+    const walk_class wc = load_walk_class(wt, cls);
     const uint32_t last_row = (narrow ? min(wc.rows, 256u) : wc.rows) - 1u;
     const uint32_t szsh = narrow ? 0u : 1u;
     const unsigned lt = lanemask_lt();
+    const uint32_t hotsum_s = wt.hotsum_s + cls * wt.hot_rows * 4u;
     uint32_t F = 0, done = 0, cw = 0, o_prev = 0;
     // the strip whose end is not known yet
     bool p_have = false, p_ls = false, p_run = false, p_brk = false;
@@ -279,9 +282,17 @@ __device__ __forceinline__ bool walk_stream(warp_state& ws, const walk_tables& w
                 uint32_t pay = ws.r32(a + (1u << szsh));
                 if (sym == 0u) pay &= 0xFFFFu;
                 sv = pay + 1u;
+            } else if (SKIM && symc < wt.hot_rows) {
+                sv = lds_u32(hotsum_s + (symc << 2));
             } else {
                 sv = __ldg(wt.sums + wc.row_base + symc);
             }
+        }
+        if (SKIM) {
+            acc += __reduce_add_sync(FULL, sv);
+            done += T;
+            F += adv;
+            continue;
         }
         const uint32_t s_incl = warp_inclusive_scan(sv);
         const uint32_t k = cw + __popc(V & lt);
@@ -326,7 +337,7 @@ __device__ __forceinline__ bool walk_stream(warp_state& ws, const walk_tables& w
         cw += __popc(V);
     }
     a_end = a0 + (F << szsh);
-    if (p_have) pk.add<EMIT>(lane, file_off(p_in), file_off(a_end), out0 + p_out, n - p_out, p_acc, sel, p_ls, p_run, p_brk);
+    if (!SKIM && p_have) pk.add<EMIT>(lane, file_off(p_in), file_off(a_end), out0 + p_out, n - p_out, p_acc, sel, p_ls, p_run, p_brk);
     return true;
 }
 
@@ -352,6 +363,16 @@ struct vroom_walk_params {
     uint64_t* list_byte_offsets;  // emit: optional
     uint32_t* status;             // emit: != 0 when the pass disagrees with the count pass
     uint32_t unit_ints, unit_bytes, strip_cw, strip_shift;
+    // where a chain starts / ends when that is not a list start (pieces of a long chain, cut by vroom_skim_kernel):
+    // [c / 2] = {integers of the current list still to come at the chain's start (0: a list header is next),
+    //            sum(v + 1) of that list so far, bit 0: the chain ENDS inside a list, integers still to come there}
+    unsigned long long* queue;    // thread walker / skim: next entry of chain_ids to hand out (zeroed before the launch)
+    const uint4* chain_state;     // null: every chain runs from a list start to a list start
+    // skim pass: the cuts of chain c go to cuts[2 * cut_off[c / 2] ...] = {file offset, list_rem | acc << 32}
+    const uint64_t* cut_off;      // [n_chains / 2 + 1]
+    uint64_t* cuts;
+    uint32_t* cut_counts;         // [n_chains / 2]
+    uint64_t cut_bytes;           // distance between two cuts
 };
 
 template <bool EMIT>
@@ -448,27 +469,105 @@ __global__ void __launch_bounds__(512, 2) vroom_walk_kernel(const vroom_walk_par
 
 
 // ---------------------------------------------------------------------------------------------------------
+// vroom .bin: the skim pass — one warp per LONG chain (a stretch without sync points: long lists). It walks the
+// chain like vroom_walk_kernel but builds nothing; every cut_bytes it records the next place a thread can start
+// from: a list header, or the selector byte of a block of a multi list together with the integers of the list
+// still to come and the list's sum(v + 1) so far. The pieces between two cuts are then walked by threads like every
+// other chain (a thread needs ~10 instructions per codeword, this tile walk ~4 per codeword and no bookkeeping).
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512, 2) vroom_skim_kernel(const vroom_walk_params P) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    walk_tables wt;
+    uint8_t* free0 = walk_setup<true>(P.dv, P.sums, smem, wt);
+    const unsigned lane = lane_id();
+    const uint32_t warp = threadIdx.x >> 5;
+    uint8_t* mine = free0 + size_t(warp) * kWalkWarpSmem;
+    const uint32_t ring_s = smem_u32(mine), rec_s = ring_s + uint32_t(kInBytes);
+    warp_state ws;
+    walk_init_input(ws, ring_s, P.in, P.in_bytes);
+    __syncthreads();
+    const uint64_t in_base = reinterpret_cast<uint64_t>(P.in);
+    unit_packer pk;  // not used by a skimming walk_stream
+    pk.init(nullptr, nullptr, 0, 0, 0, 0, 0);
+    for (;;) {
+        unsigned long long ci = 0;  // the queue hands the chains out longest first
+        if (lane == 0) ci = atomicAdd(P.queue, 1ull);
+        ci = shfl64(ci, 0);
+        if (ci >= P.n_ids) break;
+        const uint64_t c = P.chain_ids[ci];
+        const uint64_t start = P.chain_start[c], end = P.chain_start[c + 1];
+        const uint64_t cap = P.cut_off[(c >> 1) + 1] - P.cut_off[c >> 1];
+        uint64_t* dst = P.cuts + 2 * P.cut_off[c >> 1];
+        uint64_t n_cuts = 0, last_cut = start, pos = start;
+        auto cut = [&](uint64_t at, uint32_t rem, uint32_t acc) {
+            if (lane == 0) {
+                dst[2 * n_cuts] = at;
+                dst[2 * n_cuts + 1] = uint64_t(rem) | (uint64_t(acc) << 32);
+            }
+            ++n_cuts;
+            last_cut = at;
+        };
+        uint32_t p = ws.set_anchor(in_base + start, ~uint64_t(0));
+        while (pos < end) {
+            if (p > 0x60000000u) p = ws.set_anchor(in_base + pos, ~uint64_t(0));
+            if (pos - last_cut >= P.cut_bytes && n_cuts < cap) cut(pos, 0u, 0u);
+            ws.ensure_input(p, 16u, lane);
+            const uint32_t b = lane < 10u ? ws.rb(p + lane) : 0u;
+            const uint32_t term = __ballot_sync(FULL, (b & 128u) != 0u);
+            const uint32_t t1 = term ? uint32_t(__ffs(term)) - 1u : 32u;
+            const uint32_t term2 = t1 < 31u ? term & ~((2u << t1) - 1u) : 0u;
+            const uint32_t t2 = term2 ? uint32_t(__ffs(term2)) - 1u : 32u;
+            if (t1 > 4u || t2 > t1 + 5u || pos + t2 + 1u > P.in_bytes) break;  // malformed: the walkers will say so
+            const uint32_t n = __reduce_add_sync(FULL, lane <= t1 ? (b & 127u) << (7u * lane) : 0u);
+            p += t2 + 1u;
+            uint32_t acc = 0, a_end = p;
+            bool ok = true;
+            if (!P.multi) {
+                ok = walk_stream<false, true>(ws, wt, in_base, p, n, 0u, true, false, 0, acc, pk, rec_s, P.strip_cw, P.strip_shift, lane, a_end);
+                p = a_end;
+            } else {
+                for (uint32_t done = 0; ok && done < n; done += P.block_size) {
+                    if (done) {
+                        const uint64_t at = ws.anchor + p - in_base;
+                        if (at - last_cut >= P.cut_bytes && at < end && n_cuts < cap) cut(at, n - done, acc);
+                    }
+                    const uint32_t size = min(P.block_size, n - done);
+                    ws.ensure_input(p, 16u, lane);
+                    const uint32_t sel = ws.rb(p);
+                    if (sel >= 2u * dint::kSelectors || (sel % dint::kSelectors) >= wt.n_classes) {
+                        ok = false;
+                        break;
+                    }
+                    ok = walk_stream<false, true>(ws, wt, in_base, p + 1u, size, sel, false, false, 0, acc, pk, rec_s, P.strip_cw,
+                                                  P.strip_shift, lane, a_end);
+                    p = a_end;
+                }
+            }
+            pos = ws.anchor + p - in_base;
+            if (!ok || pos > P.in_bytes) break;
+        }
+        if (lane == 0) P.cut_counts[c >> 1] = uint32_t(n_cuts);
+    }
+    cp_async_wait_all();
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
 // vroom .bin: one THREAD per chain — the reference's scalar walk (vroom_env/decode.cpp:139-150 over
 // dint_codecs.hpp:45-101 / 530-611) run by tens of thousands of threads at once, each on its own stretch of the
 // file between two sync points. One loop trip handles one token (a codeword, or the switch to the next block /
-// list), so the lanes of a warp stay in the same code whatever the lengths of their lists are.
+// list), so the lanes of a warp stay in the same code whatever the lengths of their lists are. A thread that has
+// finished its chain takes the next one from a queue inside the same loop (the host hands the chains out longest
+// first): no lane waits for the longest chain of its warp.
 // ---------------------------------------------------------------------------------------------------------
 template <bool EMIT>
-__global__ void __launch_bounds__(256, 4) vroom_thread_walk_kernel(const vroom_walk_params P) {
+__global__ void __launch_bounds__(256, 3) vroom_thread_walk_kernel(const vroom_walk_params P) {
     extern __shared__ __align__(16) uint8_t smem[];
     walk_tables wt;
     walk_setup<EMIT>(P.dv, P.sums, smem, wt);
     __syncthreads();
-    const uint64_t t = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (t >= P.n_ids) return;
-    const uint64_t c = P.chain_ids[t];
-    const uint64_t start = P.chain_start[c], end = P.chain_start[c + 1];
+    uint64_t c = 0, end = 0;
     uint64_t list_base = 0, int_base = 0, slot = 0;
-    if (EMIT) {
-        list_base = P.bases[4 * c];
-        int_base = P.bases[4 * c + 1];
-        slot = P.bases[4 * c + 2];
-    }
     const uint64_t in_base = reinterpret_cast<uint64_t>(P.in);
     // The 32 bytes under the cursor live in registers (two aligned 16-byte loads); a codeword is served from them and
     // a new 16-byte piece is fetched only when the cursor leaves the window: every lane reads its own stretch of
@@ -552,11 +651,15 @@ __global__ void __launch_bounds__(256, 4) vroom_thread_walk_kernel(const vroom_w
         ++u_strips;
     };
 
-    uint64_t pos = start, lists = 0, ints = 0;
+    uint64_t pos = 0, lists = 0, ints = 0;
     uint32_t status = WALK_OK;
     uint32_t list_rem = 0, str_rem = 0;  // integers of the list behind the current stream / left in the current stream
     uint32_t acc = 0;                    // sum(v + 1) of the list so far
     bool first_block = false;
+    // a piece of a long chain starts and / or ends at a block boundary inside a list (vroom_skim_kernel)
+    bool end_mid = false;
+    uint32_t end_rem = 0;
+    bool walking = false;
     // current stream
     uint32_t sel = 0, sb = 2, last_row = 0, hotlen_s = 0, group_s = 0, detail_s = 0, row_base = 0, lut_g = 0, hotsum_s = 0;
     // open strip
@@ -564,7 +667,35 @@ __global__ void __launch_bounds__(256, 4) vroom_thread_walk_kernel(const vroom_w
     uint32_t s_acc = 0, s_ints = 0, cw = 0;
     bool s_ls = false, s_run = false;
     for (;;) {
+        if (!walking) {
+            // ---- next chain of the queue ------------------------------------------------------------------------
+            const unsigned long long k = atomicAdd(P.queue, 1ull);
+            if (k >= P.n_ids) break;
+            c = P.chain_ids[k];
+            pos = P.chain_start[c];
+            end = P.chain_start[c + 1];
+            if (EMIT) {
+                list_base = P.bases[4 * c];
+                int_base = P.bases[4 * c + 1];
+                slot = P.bases[4 * c + 2];
+            }
+            lists = ints = closed = 0;
+            status = WALK_OK;
+            list_rem = str_rem = acc = end_rem = 0;
+            first_block = end_mid = open = overflow = false;
+            if (P.chain_state) {
+                const uint4 cs = __ldg(P.chain_state + (c >> 1));
+                list_rem = cs.x;
+                acc = cs.y;
+                end_mid = (cs.z & 1u) != 0u;
+                end_rem = cs.w;
+            }
+            walking = true;
+        }
+        bool fin = true;  // left true by every `break` out of the token below: the chain is over (or malformed)
+        do {
         if (str_rem == 0u) {
+            if (list_rem != 0u && end_mid && pos >= end) break;  // the next piece starts at this block
             if (list_rem == 0u) {
                 // ---- between two lists: header::read (vroom_env/codecs.hpp:117-123) ---------------------------------
                 if (pos >= end) break;
@@ -602,7 +733,10 @@ __global__ void __launch_bounds__(256, 4) vroom_thread_walk_kernel(const vroom_w
                 list_rem = n;
                 acc = 0;
                 first_block = true;
-                if (n == 0u) continue;
+                if (n == 0u) {
+                    fin = false;
+                    break;
+                }
             }
             // ---- next stream of the list: a multi block behind its selector byte, or the whole single list -------
             uint32_t size = list_rem;
@@ -686,17 +820,22 @@ __global__ void __launch_bounds__(256, 4) vroom_thread_walk_kernel(const vroom_w
             cw = 0;
             s_ls = s_run = false;
         }
-    }
-    close_unit();
-    if (status == WALK_OK && pos != end) status = WALK_OVERSHOOT;
-    if (status == WALK_OK && overflow) status = WALK_TABLE_FULL;
-    if (!EMIT) {
-        P.counts[4 * c] = lists;
-        P.counts[4 * c + 1] = ints;
-        P.counts[4 * c + 2] = closed;
-        P.counts[4 * c + 3] = uint64_t(status) | (pos << 8);
-    } else if (status != WALK_OK || lists != P.counts[4 * c] || ints != P.counts[4 * c + 1] || closed != P.counts[4 * c + 2]) {
-        atomicMax(P.status, status ? status : uint32_t(WALK_MALFORMED));
+        fin = false;
+        } while (false);
+        if (!fin) continue;
+        // ---- the chain is over ---------------------------------------------------------------------------------
+        close_unit();
+        if (status == WALK_OK && (pos != end || list_rem != (end_mid ? end_rem : 0u))) status = WALK_OVERSHOOT;
+        if (status == WALK_OK && overflow) status = WALK_TABLE_FULL;
+        if (!EMIT) {
+            P.counts[4 * c] = lists;
+            P.counts[4 * c + 1] = ints;
+            P.counts[4 * c + 2] = closed;
+            P.counts[4 * c + 3] = uint64_t(status) | (pos << 8);
+        } else if (status != WALK_OK || lists != P.counts[4 * c] || ints != P.counts[4 * c + 1] || closed != P.counts[4 * c + 2]) {
+            atomicMax(P.status, status ? status : uint32_t(WALK_MALFORMED));
+        }
+        walking = false;
     }
 }
 

@@ -154,6 +154,7 @@ struct dint_device_plan {
     float phase_ms[3] = {0.f, 0.f, 0.f};      // sync search, count pass(es), emit pass
     uint32_t retries = 0;                     // count passes repeated because a speculative sync point was wrong
     uint64_t n_sync_found = 0;                // sync points the speculative search contributed
+    uint64_t n_skimmed = 0;                   // long chains cut into thread-sized pieces by the skim pass
 };
 
 // Fixed-size header of a frozen dict_freq_index .bin: everything the host reads of the file when the block table is

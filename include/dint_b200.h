@@ -279,6 +279,7 @@ uint64_t dint_device_plan_num_ints(const dint_device_plan* p);
 uint64_t dint_device_plan_num_units(const dint_device_plan* p);
 uint64_t dint_device_plan_num_chains(const dint_device_plan* p);
 uint64_t dint_device_plan_num_sync_found(const dint_device_plan* p); /* list starts the speculative search contributed */
+uint64_t dint_device_plan_num_skimmed(const dint_device_plan* p);    /* long chains (no list start found inside) cut into pieces at block boundaries */
 uint32_t dint_device_plan_retries(const dint_device_plan* p);        /* count passes repeated after a wrong sync point */
 double dint_device_plan_discover_ms(const dint_device_plan* p);      /* device timeline of the discovery, CUDA events */
 double dint_device_plan_phase_ms(const dint_device_plan* p, int phase); /* 0 sync search, 1 count pass(es), 2 emit pass */
