@@ -306,7 +306,9 @@ int dint_vroom_discover(const dint_dict* d, const uint8_t* d_in, size_t in_bytes
             P.chain_ids = pb.d_order.as<uint32_t>();
             P.n_ids = pb.n_short;
             const size_t smem = walk_smem(d, 0) + (emit ? walk_hotsum_bytes(d->view()) : 0);
-            const int grid = int(std::min<uint64_t>((pb.n_short + 255) / 256, uint64_t(di.sms) * 3));  // 3 CTAs per SM (launch bounds)
+            // persistent CTAs (the threads take chains from the queue): 3 per SM fit the emit pass's registers
+            const uint64_t ctas = emit ? 3 : env_bytes("DINT_B200_COUNT_CTAS", 3);
+            const int grid = int(std::min<uint64_t>((pb.n_short + 255) / 256, uint64_t(di.sms) * ctas));
             if (emit) {
                 CUDA_TRY(cudaFuncSetAttribute(vroom_thread_walk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
                 vroom_thread_walk_kernel<true><<<grid, 256, smem, st>>>(P);

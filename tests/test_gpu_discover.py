@@ -93,6 +93,57 @@ def test_discover_edge_streams(golden, oracle, type_):
     oracle.dict_free(ho)
 
 
+@pytest.mark.parametrize("knobs", ((2048, 1024), (4096, 300), (1024, 0), (1 << 30, 1024)))
+@pytest.mark.parametrize("type_", g.TYPES)
+def test_skim_pass_cuts_anywhere(golden, type_, knobs, monkeypatch):
+    """the skim pass (long chains -> pieces that start at block boundaries inside a list) with the thresholds turned
+    down so that nearly every chain is cut every few blocks / with the skim switched off (warps walk the long chains) /
+    with nothing long enough to skim: the tables decode to the reference's output and the list table is the host walk's"""
+    long_chain, cut = knobs
+    monkeypatch.setenv("DINT_B200_LONG_CHAIN", str(long_chain))
+    monkeypatch.setenv("DINT_B200_CUT_BYTES", str(cut))
+    for part, fused_key, mode in (("docs", "docids_sha256", capi.MODE_DOCIDS), ("freqs", "freqs_sha256", capi.MODE_FREQS)):
+        bin_ = golden.bytes(golden.vroom_name(type_, part))
+        dict_bytes = golden.bytes(golden.dict_name(type_, part))
+        host = capi.VroomPlan(capi.Dictionary(KINDS[type_], dict_bytes), bin_)
+        for stride in (0, capi.NO_SYNC_SEARCH):
+            vf = driver.VroomFile(type_, bin_, dict_bytes, plan="device", sync_stride=stride)
+            assert vf.n_lists == golden.n_lists and vf.n_ints == golden.n_postings
+            assert g.sha(_np(vf.decode(mode=mode)).tobytes()) == golden.sha[fused_key], (part, stride)
+            assert np.array_equal(vf.d_list_offsets.cpu().numpy().astype(np.uint64), host.list_offsets)
+            assert np.array_equal(vf.d_list_byte_offsets.cpu().numpy().astype(np.uint64), host.list_byte_offsets)
+            if cut == 0 or long_chain == 1 << 30:
+                assert vf.dplan.n_skimmed == 0
+            else:
+                assert vf.dplan.n_skimmed >= 1
+                if type_ == "multi_packed_dint" and stride == capi.NO_SYNC_SEARCH:
+                    assert vf.dplan.n_chains > len(bin_) // (4 * max(cut, 1024))  # cut inside the lists as well
+
+
+def test_skim_pass_malformed_long_list(golden):
+    """a long multi_packed list with a broken selector byte in the middle: the skim stops cutting there, the walk of
+    the last piece reports the file as malformed"""
+    type_ = "multi_packed_dint"
+    dict_bytes = golden.bytes(golden.dict_name(type_, "docs"))
+    di = sb.DictImage(capi.KIND_OF_TYPE[type_], dict_bytes)
+    rng = np.random.default_rng(5)
+    lists = _random_lists(di, rng, 3, 200000)
+    data = bytearray(b"".join(sb.encode_vroom_list(di, v, block_size=256, selectors=[0, 6, 3]) for v in lists))
+    vf = driver.VroomFile(type_, bytes(data), dict_bytes, plan="device", sync_stride=capi.NO_SYNC_SEARCH)
+    assert vf.n_ints == sum(len(v) for v in lists) and vf.dplan.n_skimmed == 1
+    host = capi.VroomPlan(capi.Dictionary(KINDS[type_], dict_bytes), bytes(data))
+    # the selector byte of a block in the middle of the longest list
+    k = int(np.argmax([len(v) for v in lists]))
+    segs = host.segments
+    lo, hi = int(host.list_offsets[k]), int(host.list_offsets[k + 1])
+    mine = segs[(segs["out_off"] >= lo) & (segs["out_off"] < hi)]
+    assert len(mine) > 8
+    data[int(mine[len(mine) // 2]["in_off"])] = 0xFF
+    with pytest.raises(capi.DintError) as e:
+        driver.VroomFile(type_, bytes(data), dict_bytes, plan="device", sync_stride=capi.NO_SYNC_SEARCH)
+    assert e.value.code == -2
+
+
 def test_discover_rejects_malformed_files(golden):
     type_ = "single_packed_dint"
     bin_ = golden.bytes(golden.vroom_name(type_, "docs"))
