@@ -244,8 +244,12 @@ int dint_vroom_discover(const dint_dict* d, const uint8_t* d_in, size_t in_bytes
     // cannot cut (a long list of a single-stream codec, a malformed stretch) keeps its warp.
     // (measured: a thread walks ~2-3 KB/ms, a warp ~7 KB/ms, and the longest chain of either kind bounds the pass)
     // (gov2 sample x 256, 6.4 GB: long 48 KB / cut 16 KB: 130 ms; 63 / 21 KB: 158 ms; 96 / 32 KB: 182 ms; no skim: 234 ms)
-    const uint64_t kLongChain = env_bytes("DINT_B200_LONG_CHAIN", std::max<uint64_t>(24 * 1024, std::min<uint64_t>(used_stride + used_stride / 8, 96 * 1024)));
-    const uint64_t kCutBytes = env_bytes("DINT_B200_CUT_BYTES", std::max<uint64_t>(8 * 1024, std::min<uint64_t>(3 * used_stride / 8, 32 * 1024)));
+    // (gov2 sample x 1, 25 MB, stride 4 KB: long 8 KB / cut 4 KB: 19 ms; 16 / 8 KB: 29 ms; 24 / 8 KB: 35 ms — a small
+    // file is bound by its longest thread chain; the 1.5 GB freqs file x 256, stride 10 KB: 24 / 8 KB: 118 ms,
+    // 11.5 / 4 KB: 144 ms — a large one by the bytes the skim pass has to walk)
+    const uint64_t min_long = std::min<uint64_t>(std::max<uint64_t>(uint64_t(in_bytes) >> 16, 8 * 1024), 24 * 1024);
+    const uint64_t kLongChain = env_bytes("DINT_B200_LONG_CHAIN", std::max<uint64_t>(min_long, std::min<uint64_t>(used_stride + used_stride / 8, 96 * 1024)));
+    const uint64_t kCutBytes = env_bytes("DINT_B200_CUT_BYTES", std::max<uint64_t>(std::max<uint64_t>(min_long / 3, 4 * 1024), std::min<uint64_t>(3 * used_stride / 8, 32 * 1024)));
     struct chain {
         uint64_t start, end;             // walk from start to the first list start >= end
         uint64_t lists, ints, units, reached;
@@ -497,14 +501,15 @@ int dint_vroom_discover(const dint_dict* d, const uint8_t* d_in, size_t in_bytes
                     cur.end = at;
                     cur.end_mid = rem != 0;
                     cur.end_rem = rem;
-                    cur.by_warp = false;
+                    // (a warp starts and stops at list headers only: a long list of a single-stream codec keeps its warp)
+                    cur.by_warp = cur.rem0 == 0 && !cur.end_mid && cur.end - cur.start > kLongChain;
                     pieces.push_back(cur);
                     cur = whole;
                     cur.start = at;
                     cur.rem0 = rem;
                     cur.acc0 = acc;
                 }
-                cur.by_warp = cur.rem0 == 0 && cur.end - cur.start > kLongChain;  // (a warp starts at list headers only)
+                cur.by_warp = cur.rem0 == 0 && cur.end - cur.start > kLongChain;
                 pieces.push_back(cur);
             }
             chains.swap(pieces);
@@ -631,7 +636,13 @@ int dint_vroom_discover(const dint_dict* d, const uint8_t* d_in, size_t in_bytes
             int64_t prev = -1;
             bool complete = true;
             while (off < in_bytes) {
-                const int64_t i = find(off, prev);
+                int64_t i = -1;
+                if (prev >= 0 && size_t(prev) + 1 < chains.size() && chains[size_t(prev) + 1].start == off) {
+                    // the usual case: the next candidate in file order (same acceptance rule as find)
+                    const bool mid = chains[size_t(prev)].end_mid;
+                    if (mid == (chains[size_t(prev) + 1].rem0 != 0)) i = prev + 1;
+                }
+                if (i < 0) i = find(off, prev);
                 if (i < 0 && prev >= 0 && chains[size_t(prev)].end_mid) {
                     dint::set_error("vroom .bin: malformed list (device walk), chain at byte " + std::to_string(off));
                     return DINT_E_FORMAT;

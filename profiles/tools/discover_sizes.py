@@ -23,6 +23,6 @@ for part in ("docs", "freqs"):
             dp = capi.DevicePlan.discover_vroom(d, d_in.data_ptr(), d_in.numel(), 256, None, 0, stream=st)
             wall = (time.perf_counter() - t0) * 1e3
         out.append({"part": part, "K": K, "MB": d_in.numel() / 1e6, "wall_ms": wall, "device_ms": dp.discover_ms, "phases": dp.phase_ms,
-                    "chains": dp.n_chains, "retries": dp.retries, "G_ints_s": dp.n_ints / dp.discover_ms / 1e6})
+                    "chains": dp.n_chains, "skimmed": dp.n_skimmed, "retries": dp.retries, "G_ints_s": dp.n_ints / dp.discover_ms / 1e6})
         print(json.dumps(out[-1]), flush=True)
         del dp, d_in
