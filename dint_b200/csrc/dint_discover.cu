@@ -249,7 +249,8 @@ int dint_vroom_discover(const dint_dict* d, const uint8_t* d_in, size_t in_bytes
     // 11.5 / 4 KB: 144 ms — a large one by the bytes the skim pass has to walk)
     const uint64_t min_long = std::min<uint64_t>(std::max<uint64_t>(uint64_t(in_bytes) >> 16, 8 * 1024), 24 * 1024);
     const uint64_t kLongChain = env_bytes("DINT_B200_LONG_CHAIN", std::max<uint64_t>(min_long, std::min<uint64_t>(used_stride + used_stride / 8, 96 * 1024)));
-    const uint64_t kCutBytes = env_bytes("DINT_B200_CUT_BYTES", std::max<uint64_t>(std::max<uint64_t>(min_long / 3, 4 * 1024), std::min<uint64_t>(3 * used_stride / 8, 32 * 1024)));
+    uint64_t kCutBytes = env_bytes("DINT_B200_CUT_BYTES", std::max<uint64_t>(std::max<uint64_t>(min_long / 3, 4 * 1024), std::min<uint64_t>(3 * used_stride / 8, 32 * 1024)));
+    if (kCutBytes) kCutBytes = std::max<uint64_t>(kCutBytes, 64);  // (the cut table is sized by chain length / kCutBytes)
     struct chain {
         uint64_t start, end;             // walk from start to the first list start >= end
         uint64_t lists, ints, units, reached;

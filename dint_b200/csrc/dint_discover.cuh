@@ -416,6 +416,10 @@ __global__ void __launch_bounds__(512, 2) vroom_walk_kernel(const vroom_walk_par
                 break;
             }
             const uint32_t n = __reduce_add_sync(FULL, lane <= t1 ? (b & 127u) << (7u * lane) : 0u);
+            if (uint64_t(n) > 256ull * (P.in_bytes - pos)) {  // a byte encodes at most 256 integers (a run codeword)
+                status = WALK_MALFORMED;
+                break;
+            }
             if (EMIT && lane == 0) {
                 P.list_offsets[list_base + lists] = int_base + ints;
                 if (P.list_byte_offsets) P.list_byte_offsets[list_base + lists] = pos;
@@ -519,6 +523,7 @@ __global__ void __launch_bounds__(512, 2) vroom_skim_kernel(const vroom_walk_par
             const uint32_t t2 = term2 ? uint32_t(__ffs(term2)) - 1u : 32u;
             if (t1 > 4u || t2 > t1 + 5u || pos + t2 + 1u > P.in_bytes) break;  // malformed: the walkers will say so
             const uint32_t n = __reduce_add_sync(FULL, lane <= t1 ? (b & 127u) << (7u * lane) : 0u);
+            if (uint64_t(n) > 256ull * (P.in_bytes - pos)) break;
             p += t2 + 1u;
             uint32_t acc = 0, a_end = p;
             bool ok = true;
@@ -720,7 +725,8 @@ __global__ void __launch_bounds__(256, 3) vroom_thread_walk_kernel(const vroom_w
                         }
                     hdr += k + 1u;
                 }
-                if (!ok || pos + hdr > P.in_bytes) {
+                // (a byte encodes at most 256 integers — a one-byte run codeword: a larger n cannot be a list of this file)
+                if (!ok || pos + hdr > P.in_bytes || uint64_t(n) > 256ull * (P.in_bytes - pos)) {
                     status = WALK_MALFORMED;
                     break;
                 }

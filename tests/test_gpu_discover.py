@@ -151,6 +151,16 @@ def test_discover_rejects_malformed_files(golden):
     with pytest.raises(capi.DintError) as e:
         driver.VroomFile(type_, bin_[:len(bin_) - 5], dict_bytes, plan="device", sync_stride=capi.NO_SYNC_SEARCH)
     assert e.value.code == -2
+    # a header that announces more integers than the rest of the file can hold (a byte encodes at most 256): refused at
+    # the header, not after walking to the end of the file
+    host = capi.VroomPlan(capi.Dictionary(KINDS[type_], dict_bytes), bin_)
+    broken = bytearray(bin_)
+    at = int(host.list_byte_offsets[len(host.list_byte_offsets) // 2])
+    broken[at:at + 5] = bytes([0x7F, 0x7F, 0x7F, 0x7F, 0x8F])
+    for stride in (0, capi.NO_SYNC_SEARCH):
+        with pytest.raises(capi.DintError) as e:
+            driver.VroomFile(type_, bytes(broken), dict_bytes, plan="device", sync_stride=stride)
+        assert e.value.code == -2
     # an empty file is fine: nothing to decode
     vf = driver.VroomFile(type_, b"", dict_bytes, plan="device")
     assert vf.n_lists == 0 and vf.n_ints == 0
